@@ -1,0 +1,134 @@
+/* egspr_b200.h -- C ABI of the B200-native Equi-GSPR registration hot path.
+ *
+ * The reference (alexandor91/se3-equi-graph-registration) has NO native/FFI layer: its boundary
+ * for this path is the Python nn.Module / function API of the three runnable scripts plus the
+ * torch_cluster.knn_graph call.  Each entry point below names the reference interface it replaces
+ * (path:line under the reference tree; 3dm = src/3dmatch_train_egnn_with_batch.py,
+ * evl = src/eval_egnn_metrics.py).  The Python mirror of that API
+ * (se3-equi-graph-registration_b200/modules.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises, allocates device memory, or throws
+ *   - return value: 0 = ok, <0 = EGSPR_E_* (invalid argument / unsupported shape / launch failure)
+ *   - outputs and workspaces are caller-allocated; *_workspace_bytes() tells how much
+ *   - node / edge ids: the clouds of a batch are addressed as ONE graph with global node id
+ *     g = cloud * n + i; edges never cross clouds
+ */
+#ifndef EGSPR_B200_H
+#define EGSPR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGSPR_OK 0
+#define EGSPR_E_INVALID (-1)      /* null pointer / non-positive size / k out of range        */
+#define EGSPR_E_UNSUPPORTED (-2)  /* shape outside what the kernels are compiled for           */
+#define EGSPR_E_WORKSPACE (-3)    /* workspace too small                                       */
+#define EGSPR_E_LAUNCH (-4)       /* cudaGetLastError() != cudaSuccess after a launch          */
+
+#define EGSPR_HIDDEN 32           /* hidden width the kernels are specialised for (3dm:1600)   */
+#define EGSPR_MAX_K 32            /* neighbours per node supported by the warp-select k-NN     */
+
+/* layer-pack layout (floats) produced by the host mirror from the live nn.Parameters; see
+ * se3-equi-graph-registration_b200/packing.py and DESIGN.md "weight packs" */
+#define EGSPR_LAYER_PACK_FLOATS 7104
+#define EGSPR_EMBED_PACK_FLOATS 1056
+#define EGSPR_HEAD_PACK_FLOATS 2640
+
+int egspr_version(void);
+const char *egspr_error_string(int code);
+
+/* ---- a1: torch_cluster.knn_graph(x, k, loop=True) call sites 3dm:1005-1006, evl:1156-1157 ------
+ * x [clouds][n][3] f32 -> nbr [clouds][n][k] i32: the k nearest points of the same cloud (self
+ * included), ascending by (d2, index); d2 = fma(dz,dz,fma(dy,dy,dx*dx)) in fp32.  Slots that
+ * cannot be filled (n < k) hold -1.  All clouds are processed by one launch. */
+int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t *nbr, void *stream);
+
+/* ---- a2: get_edges_from_idx / get_edges_batch 3dm:372-403 -------------------------------------
+ * nbr -> the reference's edge tensor edges[clouds][2][n*k] i64 (row = neighbour, col = centre,
+ * cloud-local ids) for callers that want the torch_cluster layout. */
+int egspr_nbr_to_edges(const int32_t *nbr, int clouds, int n, int k, int64_t *edges, void *stream);
+
+/* ---- a9: unsorted_segment_sum 3dm:343-348, re-cast as a one-time graph transpose ----------------
+ * Aggregation in E_GCL is over row = edge_index[0] (the NEIGHBOUR id), so every node
+ * sums over its reverse-kNN set.  These build, once per graph, the row-major CSR the layer kernels
+ * pull from: csr_ptr[G+1], and per sorted position p: csr_row[p] (global row id), csr_col[p] (global
+ * col id), csr_eid[p] (original edge id inside its cloud); within a row, positions are in ascending
+ * original edge order (= the order scatter_add_ visits them on CPU).  G = clouds*n.
+ * err_flag (optional, device int) is set to 1 if any id is out of range (such edges are dropped). */
+size_t egspr_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int egspr_csr_from_nbr(const int32_t *nbr, int clouds, int n, int k, int32_t *csr_ptr,
+                       int32_t *csr_row, int32_t *csr_col, int32_t *csr_eid, void *workspace,
+                       size_t workspace_bytes, int32_t *err_flag, void *stream);
+int egspr_csr_from_edges(const int64_t *edges, int clouds, int n, int64_t edges_per_cloud,
+                         int32_t *csr_ptr, int32_t *csr_row, int32_t *csr_col, int32_t *csr_eid,
+                         void *workspace, size_t workspace_bytes, int32_t *err_flag, void *stream);
+
+/* stand-alone unsorted_segment_sum(data, segment_ids, num_segments) 3dm:343-348: build the CSR with
+ * egspr_csr_from_edges (row = segment_ids, one "cloud"), then out[g][c] = sum over the segment in
+ * ascending original order.  data [E][channels], out [num_segments][channels]. */
+int egspr_segment_sum(const float *data, int channels, const int32_t *csr_ptr, const int32_t *csr_eid,
+                      int64_t num_segments, float *out, void *stream);
+
+/* ---- a11 (head of EGNN.forward 3dm:332): embedding_in, plus the per-node halves P,Q of layer 0's
+ * first edge-MLP Linear (W1 [h_row|h_col|geo] = P[row] + Q[col] + Wgeo geo + b, bias folded in Q).
+ * feat [G][32] -> h [G][32], P [G][32], Q [G][32]; x3 [G][3] -> x4 [G][4] (16-byte padded copy used
+ * by the layer kernels).  embed_pack == NULL: h = feat (stand-alone E_GCL call). x4 == NULL: skip. */
+int egspr_node_embed(const float *feat, const float *x3, int64_t num_nodes, const float *embed_pack,
+                     const float *layer0_pack, float *h, float *x4, float *P, float *Q, void *stream);
+
+/* ---- a3-a10: one E_GCL.forward (3dm:280-289) for every cloud of the batch in one launch ---------
+ * Reads h,x4,P,Q of the layer input, writes h_out,x4_out (and x3_out [G][3] if not NULL) and either
+ * the next layer's P_out,Q_out (next_pack != NULL) or, after the last layer, embedding_out(h_out)
+ * into h_out (out_pack != NULL, 3dm:337).  Outputs must not alias inputs (other CTAs still gather
+ * the layer input).  edge_attr: optional [clouds*edges_per_cloud] per-edge scalar indexed through
+ * csr_eid (NULL = constant edge_attr_const, the reference's ones, 3dm:387; a layer built with
+ * edges_in_d=0 has a zero edge_attr column in its pack).
+ * impl: 0 = fp32 CUDA-core path, 2 edges per thread; 1 = same, 1 edge per thread. */
+int egspr_egcl_forward(const float *h, const float *x4, const float *P, const float *Q,
+                       const int32_t *csr_ptr, const int32_t *csr_row, const int32_t *csr_col,
+                       const int32_t *csr_eid, const float *edge_attr, float edge_attr_const,
+                       int64_t num_nodes, int64_t edges_per_cloud, int n_per_cloud,
+                       const float *layer_pack, const float *next_pack, const float *out_pack,
+                       float *h_out, float *x4_out, float *x3_out, float *P_out, float *Q_out,
+                       int impl, void *stream);
+
+/* ---- a15: weighted Kabsch / Procrustes block 3dm:726-758 (evl:786-818) --------------------------
+ * One CTA per pair: centroids, H = sum w (p-cs)(q-ct)^T + 1e-6 I, 3x3 SVD (fp64 Jacobi), R = V U^T
+ * with the det<0 fix on the smallest-sigma row of Vt, t = ct - R cs.  mask (optional, [pairs][n])
+ * restricts the point set (train variant: GT inliers); an empty set gives R=I, t=0 (3dm:708-711).
+ * w is used as given (already normalised by the caller).  Outputs R [pairs][9], t [pairs][3],
+ * Hout [pairs][9] (optional). */
+int egspr_kabsch(const float *p, const float *q, const float *w, const float *mask, int pairs, int n,
+                 float *R, float *t, float *Hout, void *stream);
+
+/* ---- a14: eval-variant weights evl:691-783 + Kabsch on the ORIGINAL coords, all n points --------
+ * Per pair: sim0 = <feat_src,feat_tgt>, top-128 set (ties -> lower index), p0 = mlp([h_out_src|
+ * h_out_tgt][argmax]), the scatter/renormalise/softmax chain of SURVEY A.4, then Kabsch.
+ * Also the egnn_equi_loss partial sums (3dm:860-893): loss_parts [pairs][2] =
+ * (sum_n label*|R_gt x_src_out + t_gt - x_tgt_out|^2, sum_n (cos(h_src_out,h_tgt_out)-label)^2). */
+int egspr_head_eval(const float *feat_src, const float *feat_tgt, const float *x_src,
+                    const float *x_tgt, const float *h_out_src, const float *h_out_tgt,
+                    const float *x_out_src, const float *x_out_tgt, const float *labels,
+                    const float *gt_pose, const float *head_pack, int pairs, int n, int top_k,
+                    float *w_out, float *R, float *t, float *Hout, float *loss_parts, void *stream);
+
+/* ---- a13: train-variant weights 3dm:696-724 + Kabsch on the EGNN coords of the GT inliers -------
+ * w = softmax over {i: labels!=0} of <h_out_src,h_out_tgt>, /(sum+1e-6).  Same outputs as above;
+ * sim_out [pairs][n] receives the similarity scores (used by the host for top-k / BCE / sim loss). */
+int egspr_head_train(const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                     const float *x_out_tgt, const float *labels, const float *gt_pose, int pairs,
+                     int n, float *w_out, float *sim_out, float *R, float *t, float *Hout,
+                     float *loss_parts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGSPR_B200_H */

@@ -1,0 +1,217 @@
+// Row-major CSR ("reverse k-NN lists") of the batch graph, built once per graph.
+//
+// E_GCL aggregates with unsorted_segment_sum(..., row) where row = edge_index[0]
+// (src/3dmatch_train_egnn_with_batch.py:253-254, 263-265, 343-348); for knn_graph output row is
+// the NEIGHBOUR id, so node g sums over {e : row[e] = g}, a variable-length set.  Instead of
+// scatter-add atomics per layer, the edge list is transposed once: a counting sort by row
+// (integer atomics only decide slots; a per-row rank pass then restores ascending edge order, so
+// the result is deterministic and sums run in the same order as scatter_add_ on CPU).
+#include "egspr_common.cuh"
+
+namespace egspr {
+
+struct NbrSource {   // edges implied by nbr[cloud][i][s]: row = nbr, col = i, e = i*k+s
+    const int32_t *nbr; int n, k;
+    __device__ __forceinline__ void get(int cloud, int64_t e, int64_t epc, int &r, int &c) const {
+        r = nbr[cloud * epc + e]; c = (int)(e / k);
+    }
+};
+struct EdgeSource {  // edges[cloud][2][E] int64 (torch_cluster / reference layout)
+    const int64_t *edges; int n;
+    __device__ __forceinline__ void get(int cloud, int64_t e, int64_t epc, int &r, int &c) const {
+        r = (int)edges[(cloud * 2 + 0) * epc + e]; c = (int)edges[(cloud * 2 + 1) * epc + e];
+    }
+};
+
+__device__ __forceinline__ bool fix_range(int &v, int n) {
+    if ((unsigned)v < (unsigned)n) return false;
+    v = v < 0 ? 0 : n - 1;
+    return true;
+}
+
+template <class Src>
+__global__ void csr_count_kernel(Src src, int n, int64_t epc, int32_t *__restrict__ deg,
+                                 int32_t *__restrict__ err_flag) {
+    const int cloud = blockIdx.y;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < epc; e += (int64_t)gridDim.x * blockDim.x) {
+        int r, c;
+        src.get(cloud, e, epc, r, c);
+        bool bad = fix_range(r, n);
+        bad |= fix_range(c, n);
+        if (bad && err_flag) *err_flag = 1;
+        atomicAdd(&deg[(int64_t)cloud * n + r], 1);
+    }
+}
+
+// one CTA per cloud: ptr[cloud*n+i] = cloud*epc + exclusive_scan(deg); deg is reset to 0 (it
+// becomes the fill cursor)
+__global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t *__restrict__ deg, int n, int64_t epc,
+                                                        int32_t *__restrict__ ptr, int clouds) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int cloud = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    int32_t *d = deg + (int64_t)cloud * n;
+    int32_t *p = ptr + (int64_t)cloud * n;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? d[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_tot[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane], u = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += w; }
+            warp_tot[lane] = u - t;   // exclusive warp offsets
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + warp_tot[warp] + s - v;
+        if (i < n) { p[i] = (int32_t)(cloud * epc) + excl; d[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (cloud == clouds - 1 && threadIdx.x == 0) ptr[(int64_t)clouds * n] = (int32_t)(clouds * epc);
+}
+
+template <class Src>
+__global__ void csr_fill_kernel(Src src, int n, int64_t epc, int32_t *__restrict__ cursor,
+                                const int32_t *__restrict__ ptr, int32_t *__restrict__ tmp) {
+    const int cloud = blockIdx.y;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < epc; e += (int64_t)gridDim.x * blockDim.x) {
+        int r, c;
+        src.get(cloud, e, epc, r, c);
+        fix_range(r, n);
+        const int64_t g = (int64_t)cloud * n + r;
+        const int slot = atomicAdd(&cursor[g], 1);
+        tmp[ptr[g] + slot] = (int32_t)e;
+    }
+}
+
+// warp per node: rank the row's edge ids (restores ascending edge order) and emit the sorted lists
+template <class Src>
+__global__ void __launch_bounds__(256) csr_emit_kernel(Src src, int n, int64_t epc, int64_t num_nodes,
+                                                       const int32_t *__restrict__ ptr,
+                                                       const int32_t *__restrict__ tmp,
+                                                       int32_t *__restrict__ csr_row,
+                                                       int32_t *__restrict__ csr_col,
+                                                       int32_t *__restrict__ csr_eid) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t g = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); g < num_nodes; g += warps) {
+        const int base = ptr[g], deg = ptr[g + 1] - base;
+        const int cloud = (int)(g / n);
+        if (deg <= 32) {
+            const int e = lane < deg ? tmp[base + lane] : 0x7fffffff;
+            int rank = 0;
+            for (int j = 0; j < deg; ++j) rank += (__shfl_sync(0xffffffffu, e, j) < e);
+            if (lane < deg) {
+                int r, c;
+                src.get(cloud, e, epc, r, c);
+                fix_range(c, n);
+                csr_eid[base + rank] = e;
+                csr_row[base + rank] = (int32_t)g;
+                csr_col[base + rank] = cloud * n + c;
+            }
+        } else {
+            for (int i = lane; i < deg; i += 32) {
+                const int e = tmp[base + i];
+                int rank = 0;
+                for (int j = 0; j < deg; ++j) rank += (tmp[base + j] < e);
+                int r, c;
+                src.get(cloud, e, epc, r, c);
+                fix_range(c, n);
+                csr_eid[base + rank] = e;
+                csr_row[base + rank] = (int32_t)g;
+                csr_col[base + rank] = cloud * n + c;
+            }
+        }
+    }
+}
+
+template <class Src>
+static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, int32_t *csr_row,
+                     int32_t *csr_col, int32_t *csr_eid, void *ws, size_t ws_bytes, int32_t *err_flag,
+                     cudaStream_t st) {
+    const int64_t G = (int64_t)clouds * n, E = (int64_t)clouds * epc;
+    if (clouds > 65535 || E >= (int64_t)0x7fffffff || G >= (int64_t)0x7fffffff) return EGSPR_E_UNSUPPORTED;
+    if (ws_bytes < egspr_csr_workspace_bytes(G, E)) return EGSPR_E_WORKSPACE;
+    int32_t *deg = (int32_t *)ws;
+    int32_t *tmp = deg + ((G + 31) / 32) * 32;
+    if (cudaMemsetAsync(deg, 0, sizeof(int32_t) * G, st) != cudaSuccess) return EGSPR_E_LAUNCH;
+    int64_t gx = (epc + 255) / 256;
+    if (gx > 2048) gx = 2048;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, clouds);
+    csr_count_kernel<<<grid, 256, 0, st>>>(src, n, epc, deg, err_flag);
+    csr_scan_kernel<<<clouds, 1024, 0, st>>>(deg, n, epc, csr_ptr, clouds);
+    csr_fill_kernel<<<grid, 256, 0, st>>>(src, n, epc, deg, csr_ptr, tmp);
+    int64_t gw = (G + 7) / 8;
+    if (gw > 148 * 32) gw = 148 * 32;
+    csr_emit_kernel<<<(unsigned)gw, 256, 0, st>>>(src, n, epc, G, csr_ptr, tmp, csr_row, csr_col, csr_eid);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+// unsorted_segment_sum (3dm:343-348) as a deterministic pull over the CSR: warp per segment,
+// lanes over channels, entries in ascending original order
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float *__restrict__ data, int channels,
+                                                          const int32_t *__restrict__ ptr,
+                                                          const int32_t *__restrict__ eid, int64_t segments,
+                                                          float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t g = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); g < segments; g += warps) {
+        const int lo = ptr[g], hi = ptr[g + 1];
+        for (int c = lane; c < channels; c += 32) {
+            float acc = 0.f;
+            for (int p = lo; p < hi; ++p) acc += __ldg(data + (int64_t)eid[p] * channels + c);
+            out[g * channels + c] = acc;
+        }
+    }
+}
+
+}  // namespace egspr
+
+extern "C" int egspr_segment_sum(const float *data, int channels, const int32_t *csr_ptr, const int32_t *csr_eid,
+                                 int64_t num_segments, float *out, void *stream) {
+    using namespace egspr;
+    if (!data || !csr_ptr || !csr_eid || !out || channels <= 0 || num_segments <= 0) return EGSPR_E_INVALID;
+    int64_t gw = (num_segments + 7) / 8;
+    if (gw > 148 * 32) gw = 148 * 32;
+    segment_sum_kernel<<<(unsigned)gw, 256, 0, (cudaStream_t)stream>>>(data, channels, csr_ptr, csr_eid, num_segments, out);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" size_t egspr_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges) {
+    return sizeof(int32_t) * (size_t)(((num_nodes + 31) / 32) * 32 + num_edges + 32);
+}
+
+extern "C" int egspr_csr_from_nbr(const int32_t *nbr, int clouds, int n, int k, int32_t *csr_ptr,
+                                  int32_t *csr_row, int32_t *csr_col, int32_t *csr_eid, void *workspace,
+                                  size_t workspace_bytes, int32_t *err_flag, void *stream) {
+    using namespace egspr;
+    if (!nbr || !csr_ptr || !csr_row || !csr_col || !csr_eid || !workspace || clouds <= 0 || n <= 0 || k <= 0)
+        return EGSPR_E_INVALID;
+    NbrSource src{nbr, n, k};
+    return csr_build(src, clouds, n, (int64_t)n * k, csr_ptr, csr_row, csr_col, csr_eid, workspace,
+                     workspace_bytes, err_flag, (cudaStream_t)stream);
+}
+
+extern "C" int egspr_csr_from_edges(const int64_t *edges, int clouds, int n, int64_t edges_per_cloud,
+                                    int32_t *csr_ptr, int32_t *csr_row, int32_t *csr_col, int32_t *csr_eid,
+                                    void *workspace, size_t workspace_bytes, int32_t *err_flag, void *stream) {
+    using namespace egspr;
+    if (!edges || !csr_ptr || !csr_row || !csr_col || !csr_eid || !workspace || clouds <= 0 || n <= 0 ||
+        edges_per_cloud <= 0)
+        return EGSPR_E_INVALID;
+    EdgeSource src{edges, n};
+    return csr_build(src, clouds, n, edges_per_cloud, csr_ptr, csr_row, csr_col, csr_eid, workspace,
+                     workspace_bytes, err_flag, (cudaStream_t)stream);
+}

@@ -1,0 +1,498 @@
+// Correspondence-weight head + weighted Kabsch / 3x3 SVD pose solve, one CTA per registration pair.
+//
+// Replaces the per-pair Python loops of CrossAttentionPoseRegression.forward:
+//   eval variant  src/eval_egnn_metrics.py:691-818   (weights from the input-feature similarity,
+//                 top-128 / mlp / scatter / renormalise / softmax chain, Kabsch on ORIGINAL coords)
+//   train variant src/3dmatch_train_egnn_with_batch.py:696-758 (softmax of output-feature similarity
+//                 over the GT inliers, Kabsch on the EGNN coords)
+// and the cuSOLVER launch + `if det<0` host sync per pair (:741-751) with an in-kernel fp64 Jacobi SVD.
+#include "egspr_common.cuh"
+
+namespace egspr {
+
+constexpr int HD_THREADS = 256;
+constexpr int HD_WARPS = HD_THREADS / 32;
+
+struct BlockScratch {
+    float red[HD_WARPS][16];
+    float bc[16];
+    unsigned hist[256];
+    unsigned long long red64[HD_WARPS];
+    unsigned u[8];
+};
+
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], BlockScratch &sc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sc.red[warp][i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < HD_WARPS; ++w) s += sc.red[w][threadIdx.x];
+        sc.bc[threadIdx.x] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = sc.bc[i];
+}
+
+__device__ __forceinline__ float block_max(float v, BlockScratch &sc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) sc.red[warp][0] = v;
+    __syncthreads();
+    float m = sc.red[0][0];
+#pragma unroll
+    for (int w = 1; w < HD_WARPS; ++w) m = fmaxf(m, sc.red[w][0]);
+    return m;
+}
+
+// ---- 3x3 SVD by one-sided Jacobi in fp64, R = V diag(1,1,det) U^T  (3dm:741-751) ---------------
+__device__ void kabsch_solve(const double (&Hm)[3][3], double (&R)[3][3]) {
+    double A[3][3], V[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { A[i][j] = Hm[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
+            double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { alpha += A[i][p] * A[i][p]; beta += A[i][q] * A[i][q]; gamma += A[i][p] * A[i][q]; }
+            if (fabs(gamma) > 1e-17 * sqrt(alpha * beta) && gamma != 0.0) {
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double ap = A[i][p], aq = A[i][q];
+                    A[i][p] = c * ap - s * aq; A[i][q] = s * ap + c * aq;
+                    const double vp = V[i][p], vq = V[i][q];
+                    V[i][p] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    double sig[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sig[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+    // order columns by descending sigma (LAPACK order: the det fix flips the SMALLEST-sigma row of Vt)
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (sig[o0] < sig[o1]) { int t = o0; o0 = o1; o1 = t; }
+    if (sig[o1] < sig[o2]) { int t = o1; o1 = o2; o2 = t; }
+    if (sig[o0] < sig[o1]) { int t = o0; o0 = o1; o1 = t; }
+    const int ord[3] = {o0, o1, o2};
+    double U[3][3], W[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int s = ord[j];
+        const double inv = sig[s] > 1e-300 ? 1.0 / sig[s] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { U[i][j] = A[i][s] * inv; W[i][j] = V[i][s]; }
+    }
+    const double smax = sig[o0];
+    if (!(smax > 0.0)) {   // H == 0: any basis; LAPACK returns identity factors
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) R[i][j] = (i == j) ? 1.0 : 0.0;
+        return;
+    }
+    if (sig[o1] <= 1e-14 * smax) {   // rank 1: complete U with any unit vector orthogonal to U0
+        const double ax = fabs(U[0][0]), ay = fabs(U[1][0]), az = fabs(U[2][0]);
+        double e[3] = {0, 0, 0};
+        e[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = 1.0;
+        const double d = e[0] * U[0][0] + e[1] * U[1][0] + e[2] * U[2][0];
+        double v[3] = {e[0] - d * U[0][0], e[1] - d * U[1][0], e[2] - d * U[2][0]};
+        const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        U[0][1] = v[0] / nv; U[1][1] = v[1] / nv; U[2][1] = v[2] / nv;
+    }
+    if (sig[o2] <= 1e-14 * smax) {   // rank <= 2: third left vector = U0 x U1 (sign is fixed below)
+        U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+        U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+        U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+    }
+    auto det3 = [](const double (&M)[3][3]) {
+        return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+               M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+    };
+    const double d = det3(W) * det3(U) < 0.0 ? -1.0 : 1.0;   // det(V U^T) < 0 -> Vt[-1,:] *= -1
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R[i][j] = W[i][0] * U[j][0] + W[i][1] * U[j][1] + d * W[i][2] * U[j][2];
+}
+
+// p,q: point rows with `stride` floats; w: weights in shared or global memory (0 for excluded points).
+// Writes R[9], t[3], Hout[9] for this CTA's pair.  `count` = number of included points (0 -> I, 0).
+__device__ void block_kabsch(const float *__restrict__ p, const float *__restrict__ q, int stride,
+                             const float *w, int n, int count, float *__restrict__ R, float *__restrict__ t,
+                             float *__restrict__ Hout, BlockScratch &sc) {
+    float c[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+        const float wi = w[i];
+        if (wi != 0.f) {
+            c[0] = fmaf(wi, p[i * stride], c[0]); c[1] = fmaf(wi, p[i * stride + 1], c[1]); c[2] = fmaf(wi, p[i * stride + 2], c[2]);
+            c[3] = fmaf(wi, q[i * stride], c[3]); c[4] = fmaf(wi, q[i * stride + 1], c[4]); c[5] = fmaf(wi, q[i * stride + 2], c[5]);
+        }
+    }
+    block_sum<6>(c, sc);
+    float hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+        const float wi = w[i];
+        if (wi != 0.f) {
+            const float a0 = wi * (p[i * stride] - c[0]), a1 = wi * (p[i * stride + 1] - c[1]), a2 = wi * (p[i * stride + 2] - c[2]);
+            const float b0 = q[i * stride] - c[3], b1 = q[i * stride + 1] - c[4], b2 = q[i * stride + 2] - c[5];
+            hm[0] = fmaf(a0, b0, hm[0]); hm[1] = fmaf(a0, b1, hm[1]); hm[2] = fmaf(a0, b2, hm[2]);
+            hm[3] = fmaf(a1, b0, hm[3]); hm[4] = fmaf(a1, b1, hm[4]); hm[5] = fmaf(a1, b2, hm[5]);
+            hm[6] = fmaf(a2, b0, hm[6]); hm[7] = fmaf(a2, b1, hm[7]); hm[8] = fmaf(a2, b2, hm[8]);
+        }
+    }
+    block_sum<9>(hm, sc);
+    if (threadIdx.x == 0) {
+        if (count == 0) {
+            for (int i = 0; i < 9; ++i) { R[i] = (i % 4 == 0) ? 1.f : 0.f; if (Hout) Hout[i] = 0.f; }
+            t[0] = t[1] = t[2] = 0.f;
+        } else {
+            hm[0] += 1e-6f; hm[4] += 1e-6f; hm[8] += 1e-6f;                       // regulariser :738
+            double Hd[3][3], Rd[3][3];
+            for (int i = 0; i < 9; ++i) { Hd[i / 3][i % 3] = (double)hm[i]; if (Hout) Hout[i] = hm[i]; }
+            kabsch_solve(Hd, Rd);
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) R[i * 3 + j] = (float)Rd[i][j];
+                t[i] = (float)((double)c[3 + i] - (Rd[i][0] * c[0] + Rd[i][1] * c[1] + Rd[i][2] * c[2]));  // :754
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float dot32(const float *__restrict__ a, const float *__restrict__ b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 u = ldg4(a + 4 * i), v = ldg4(b + 4 * i);
+        s = fmaf(u.x, v.x, s); s = fmaf(u.y, v.y, s); s = fmaf(u.z, v.z, s); s = fmaf(u.w, v.w, s);
+    }
+    return s;
+}
+
+// egnn_equi_loss partial sums (3dm:860-893) for this pair
+__device__ void block_equi_loss(const float *__restrict__ hs, const float *__restrict__ ht,
+                                const float *__restrict__ xs, const float *__restrict__ xt,
+                                const float *__restrict__ labels, const float *__restrict__ gt, int n,
+                                float *__restrict__ loss_parts, BlockScratch &sc) {
+    float g[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g[3 * i] = __ldg(gt + 4 * i); g[3 * i + 1] = __ldg(gt + 4 * i + 1); g[3 * i + 2] = __ldg(gt + 4 * i + 2);
+        g[9 + i] = __ldg(gt + 4 * i + 3);
+    }
+    float acc[2] = {0.f, 0.f};
+    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+        const float lab = __ldg(labels + i);
+        const float x0 = xs[3 * i], x1 = xs[3 * i + 1], x2 = xs[3 * i + 2];
+        float ch = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float d = (g[3 * r] * x0 + g[3 * r + 1] * x1 + g[3 * r + 2] * x2 + g[9 + r]) - xt[3 * i + r];
+            ch = fmaf(d, d, ch);
+        }
+        acc[0] = fmaf(ch, lab, acc[0]);
+        const float ab = dot32(hs + (size_t)i * H, ht + (size_t)i * H);
+        const float aa = dot32(hs + (size_t)i * H, hs + (size_t)i * H), bb = dot32(ht + (size_t)i * H, ht + (size_t)i * H);
+        // F.cosine_similarity: x.y / (max(|x|,eps) * max(|y|,eps)), eps = 1e-8
+        const float cs = ab / (fmaxf(sqrtf(aa), 1e-8f) * fmaxf(sqrtf(bb), 1e-8f));
+        acc[1] = fmaf(cs - lab, cs - lab, acc[1]);
+    }
+    block_sum<2>(acc, sc);
+    if (threadIdx.x == 0) { loss_parts[0] = acc[0]; loss_parts[1] = acc[1]; }
+}
+
+__device__ __forceinline__ unsigned order_key(float f) {   // ascending float order == ascending uint order
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct HeadEvalArgs {
+    const float *feat_src, *feat_tgt, *x_src, *x_tgt, *h_out_src, *h_out_tgt, *x_out_src, *x_out_tgt, *labels,
+        *gt_pose, *head_pack;
+    int n, top_k;
+    float *w_out, *R, *t, *Hout, *loss_parts;
+};
+
+__global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArgs a) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ BlockScratch sc;
+    float *ssim = dyn;            // [n] sim0, later the weights
+    const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t nb = (size_t)b * n;
+    // 1. input-feature similarity (evl:691)
+    unsigned long long best = 0ull;
+    for (int i = tid; i < n; i += HD_THREADS) {
+        const float s = dot32(a.feat_src + (nb + i) * H, a.feat_tgt + (nb + i) * H);
+        ssim[i] = s;
+        const unsigned long long cand = ((unsigned long long)order_key(s) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+        best = cand > best ? cand : best;
+    }
+    // 2. argmax (top_indices[:,0]; ties -> lowest index)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if (lane == 0) sc.red64[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long m = sc.red64[0];
+        for (int w = 1; w < HD_WARPS; ++w) m = sc.red64[w] > m ? sc.red64[w] : m;
+        sc.u[0] = 0xffffffffu - (unsigned)(m & 0xffffffffull);   // i0
+    }
+    // 3. k-th largest key by 4-pass radix select (evl:694 topk, k=128)
+    const int kk = a.top_k < n ? a.top_k : n;
+    unsigned prefix = 0, pmask = 0;
+    int want = kk;                 // rank (1-based, from the top) still to locate inside the prefix class
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        __syncthreads();
+        sc.hist[tid] = 0;          // HD_THREADS == 256 bins
+        __syncthreads();
+        for (int i = tid; i < n; i += HD_THREADS) {
+            const unsigned key = order_key(ssim[i]);
+            if ((key & pmask) == prefix) atomicAdd(&sc.hist[(key >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, bin = 255;
+            for (; bin > 0; --bin) {
+                if (cum + (int)sc.hist[bin] >= want) break;
+                cum += (int)sc.hist[bin];
+            }
+            sc.u[1] = (unsigned)bin; sc.u[2] = (unsigned)(want - cum);
+        }
+        __syncthreads();
+        prefix |= sc.u[1] << shift; pmask |= 0xffu << shift; want = (int)sc.u[2];
+    }
+    const unsigned kth_key = prefix;          // `want` = how many elements equal to kth_key belong to the top-k
+    const int i0 = (int)sc.u[0];
+    // 4. p0 = mlp([h_out_src | h_out_tgt][i0])  (evl:736-742; only pred[0] survives the scatter)
+    if (warp == 0) {
+        const float zs = __ldg(a.h_out_src + (nb + i0) * H + lane), zt = __ldg(a.h_out_tgt + (nb + i0) * H + lane);
+        const float *hp = a.head_pack;
+        float h0 = __ldg(hp + HOFF_B0 + lane);
+        for (int i = 0; i < 32; ++i) h0 = fmaf(__ldg(hp + HOFF_W0T + 32 * i + lane), __shfl_sync(0xffffffffu, zs, i), h0);
+        for (int i = 0; i < 32; ++i) h0 = fmaf(__ldg(hp + HOFF_W0T + 32 * (32 + i) + lane), __shfl_sync(0xffffffffu, zt, i), h0);
+        h0 = fmaxf(h0, 0.f);
+        float h1 = lane < 16 ? __ldg(hp + HOFF_B1 + lane) : 0.f;
+        for (int i = 0; i < 32; ++i) {
+            const float v = __shfl_sync(0xffffffffu, h0, i);
+            if (lane < 16) h1 = fmaf(__ldg(hp + HOFF_W1T + 16 * i + lane), v, h1);
+        }
+        h1 = fmaxf(h1, 0.f);
+        float pr = lane < 16 ? h1 * __ldg(hp + HOFF_W2 + lane) : 0.f;
+        pr = warp_sum(pr);
+        if (lane == 0) sc.bc[15] = pr + __ldg(hp + HOFF_B2);
+    }
+    __syncthreads();
+    const float p0 = sc.bc[15];
+    // 5. final weights: members of the top-k set take p0 when the (quirky) conditions hold (evl:761-768)
+    float part[1] = {0.f};
+    unsigned eq_carry = 0;       // equals seen in earlier index chunks
+    for (int base = 0; base < n; base += HD_THREADS) {
+        const int i = base + tid;
+        float s = 0.f;
+        unsigned key = 0;
+        if (i < n) { s = ssim[i]; key = order_key(s); }
+        const bool is_eq = (i < n) && key == kth_key;
+        const unsigned bal = __ballot_sync(0xffffffffu, is_eq);
+        __syncthreads();
+        if (lane == 0) sc.hist[warp] = __popc(bal);
+        __syncthreads();
+        unsigned before = eq_carry, total = 0;
+        for (int w = 0; w < HD_WARPS; ++w) { const unsigned c = sc.hist[w]; if (w < warp) before += c; total += c; }
+        before += __popc(bal & ((1u << lane) - 1u));
+        eq_carry += total;
+        const bool member = (i < n) && (key > kth_key || (is_eq && (int)before < want));
+        float f = s;
+        if (member && p0 > 0.5f && (fabsf(p0 - 1.0f) < s || p0 < s)) f = p0;
+        if (i < n) { ssim[i] = f; part[0] += f; }
+    }
+    block_sum<1>(part, sc);
+    const float inv_s = 1.0f / (part[0] + 1e-6f);                                  // evl:771
+    float mx = -3.4e38f;
+    for (int i = tid; i < n; i += HD_THREADS) { const float f = ssim[i] * inv_s; ssim[i] = f; mx = fmaxf(mx, f); }
+    mx = block_max(mx, sc);
+    float z[1] = {0.f};
+    for (int i = tid; i < n; i += HD_THREADS) { const float e = expf(ssim[i] - mx); ssim[i] = e; z[0] += e; }   // softmax evl:774
+    block_sum<1>(z, sc);
+    const float inv_z = 1.0f / z[0];
+    float sw[1] = {0.f};
+    for (int i = tid; i < n; i += HD_THREADS) { const float w = ssim[i] * inv_z; ssim[i] = w; sw[0] += w; }
+    block_sum<1>(sw, sc);
+    const float inv_w = 1.0f / (sw[0] + 1e-6f);                                    // evl:783
+    for (int i = tid; i < n; i += HD_THREADS) {
+        const float w = ssim[i] * inv_w;
+        ssim[i] = w;
+        if (a.w_out) a.w_out[nb + i] = w;
+    }
+    __syncthreads();
+    // 6. Kabsch on the original coordinates, all n points (evl:717-718, 786-818)
+    block_kabsch(a.x_src + nb * 3, a.x_tgt + nb * 3, 3, ssim, n, n, a.R + b * 9, a.t + b * 3,
+                 a.Hout ? a.Hout + b * 9 : nullptr, sc);
+    // 7. egnn_equi_loss partial sums on the EGNN outputs (evl:687)
+    if (a.loss_parts)
+        block_equi_loss(a.h_out_src + nb * H, a.h_out_tgt + nb * H, a.x_out_src + nb * 3, a.x_out_tgt + nb * 3,
+                        a.labels + nb, a.gt_pose + b * 16, n, a.loss_parts + b * 2, sc);
+}
+
+struct HeadTrainArgs {
+    const float *h_out_src, *h_out_tgt, *x_out_src, *x_out_tgt, *labels, *gt_pose;
+    int n;
+    float *w_out, *sim_out, *R, *t, *Hout, *loss_parts;
+};
+
+__global__ void __launch_bounds__(HD_THREADS) head_train_kernel(const HeadTrainArgs a) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ BlockScratch sc;
+    float *ssim = dyn;
+    const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
+    const size_t nb = (size_t)b * n;
+    float mx = -3.4e38f;
+    float cnt[1] = {0.f};
+    for (int i = tid; i < n; i += HD_THREADS) {
+        const float s = dot32(a.h_out_src + (nb + i) * H, a.h_out_tgt + (nb + i) * H);   // 3dm:681, 717
+        if (a.sim_out) a.sim_out[nb + i] = s;
+        const bool valid = __ldg(a.labels + nb + i) != 0.f;                              // 3dm:696
+        ssim[i] = valid ? s : -3.4e38f;
+        if (valid) { mx = fmaxf(mx, s); cnt[0] += 1.f; }
+    }
+    mx = block_max(mx, sc);
+    block_sum<1>(cnt, sc);
+    float z[1] = {0.f};
+    for (int i = tid; i < n; i += HD_THREADS) {
+        const float v = ssim[i];
+        const float e = v > -3.0e38f ? expf(v - mx) : 0.f;                               // softmax over the valid set 3dm:718
+        ssim[i] = e; z[0] += e;
+    }
+    block_sum<1>(z, sc);
+    const float inv_z = z[0] > 0.f ? 1.0f / z[0] : 0.f;
+    float sw[1] = {0.f};
+    for (int i = tid; i < n; i += HD_THREADS) { const float w = ssim[i] * inv_z; ssim[i] = w; sw[0] += w; }
+    block_sum<1>(sw, sc);
+    const float inv_w = 1.0f / (sw[0] + 1e-6f);                                          // 3dm:724
+    for (int i = tid; i < n; i += HD_THREADS) {
+        const float w = ssim[i] * inv_w;
+        ssim[i] = w;
+        if (a.w_out) a.w_out[nb + i] = w;
+    }
+    __syncthreads();
+    block_kabsch(a.x_out_src + nb * 3, a.x_out_tgt + nb * 3, 3, ssim, n, (int)(cnt[0] + 0.5f), a.R + b * 9,
+                 a.t + b * 3, a.Hout ? a.Hout + b * 9 : nullptr, sc);
+    if (a.loss_parts)
+        block_equi_loss(a.h_out_src + nb * H, a.h_out_tgt + nb * H, a.x_out_src + nb * 3, a.x_out_tgt + nb * 3,
+                        a.labels + nb, a.gt_pose + b * 16, n, a.loss_parts + b * 2, sc);
+}
+
+__global__ void __launch_bounds__(HD_THREADS) kabsch_kernel(const float *__restrict__ p, const float *__restrict__ q,
+                                                            const float *__restrict__ w, const float *__restrict__ mask,
+                                                            int n, float *R, float *t, float *Hout) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ BlockScratch sc;
+    const int b = blockIdx.x;
+    const size_t nb = (size_t)b * n;
+    float cnt[1] = {0.f};
+    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+        const bool inc = !mask || __ldg(mask + nb + i) != 0.f;
+        dyn[i] = inc ? __ldg(w + nb + i) : 0.f;
+        if (inc) cnt[0] += 1.f;
+    }
+    block_sum<1>(cnt, sc);
+    block_kabsch(p + nb * 3, q + nb * 3, 3, dyn, n, (int)(cnt[0] + 0.5f), R + b * 9, t + b * 3,
+                 Hout ? Hout + b * 9 : nullptr, sc);
+}
+
+constexpr int HD_MAX_N = 48 * 1024;   // n floats of dynamic shared memory (<= 192 KB)
+
+template <class K>
+static int ensure_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return EGSPR_E_LAUNCH;
+    }
+    return EGSPR_OK;
+}
+
+}  // namespace egspr
+
+extern "C" int egspr_kabsch(const float *p, const float *q, const float *w, const float *mask, int pairs, int n,
+                            float *R, float *t, float *Hout, void *stream) {
+    using namespace egspr;
+    if (!p || !q || !w || !R || !t || pairs <= 0 || n < 0) return EGSPR_E_INVALID;
+    if (n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
+    const size_t smem = sizeof(float) * (size_t)(n > 0 ? n : 1);
+    if (int e = ensure_smem(kabsch_kernel, smem)) return e;
+    kabsch_kernel<<<pairs, HD_THREADS, smem, (cudaStream_t)stream>>>(p, q, w, mask, n, R, t, Hout);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_head_eval(const float *feat_src, const float *feat_tgt, const float *x_src, const float *x_tgt,
+                               const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                               const float *x_out_tgt, const float *labels, const float *gt_pose,
+                               const float *head_pack, int pairs, int n, int top_k, float *w_out, float *R, float *t,
+                               float *Hout, float *loss_parts, void *stream) {
+    using namespace egspr;
+    if (!feat_src || !feat_tgt || !x_src || !x_tgt || !h_out_src || !h_out_tgt || !head_pack || !R || !t || pairs <= 0 ||
+        n <= 0 || top_k <= 0)
+        return EGSPR_E_INVALID;
+    if (loss_parts && (!x_out_src || !x_out_tgt || !labels || !gt_pose)) return EGSPR_E_INVALID;
+    if (n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
+    const size_t smem = sizeof(float) * (size_t)n;
+    if (int e = ensure_smem(head_eval_kernel, smem)) return e;
+    HeadEvalArgs a{feat_src, feat_tgt, x_src, x_tgt, h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose,
+                   head_pack, n, top_k, w_out, R, t, Hout, loss_parts};
+    head_eval_kernel<<<pairs, HD_THREADS, smem, (cudaStream_t)stream>>>(a);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_head_train(const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                                const float *x_out_tgt, const float *labels, const float *gt_pose, int pairs, int n,
+                                float *w_out, float *sim_out, float *R, float *t, float *Hout, float *loss_parts,
+                                void *stream) {
+    using namespace egspr;
+    if (!h_out_src || !h_out_tgt || !x_out_src || !x_out_tgt || !labels || !R || !t || pairs <= 0 || n <= 0)
+        return EGSPR_E_INVALID;
+    if (loss_parts && !gt_pose) return EGSPR_E_INVALID;
+    if (n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
+    const size_t smem = sizeof(float) * (size_t)n;
+    if (int e = ensure_smem(head_train_kernel, smem)) return e;
+    HeadTrainArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose, n, w_out, sim_out, R, t, Hout, loss_parts};
+    head_train_kernel<<<pairs, HD_THREADS, smem, (cudaStream_t)stream>>>(a);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_version(void) { return 100; }
+
+extern "C" const char *egspr_error_string(int code) {
+    switch (code) {
+        case EGSPR_OK: return "ok";
+        case EGSPR_E_INVALID: return "invalid argument (null pointer, non-positive size, aliasing outputs)";
+        case EGSPR_E_UNSUPPORTED: return "unsupported shape for the compiled kernels";
+        case EGSPR_E_WORKSPACE: return "workspace too small";
+        case EGSPR_E_LAUNCH: return "CUDA launch failed";
+        default: return "unknown egspr error";
+    }
+}

@@ -1,0 +1,136 @@
+"""RegistrationEngine: the whole inference hot path for a batch of pairs as one launch sequence.
+
+What the reference's eval loop does per batch (src/eval_egnn_metrics.py:1122-1250):
+  .to(device) x5  ->  2*B knn_graph calls  ->  2*B get_edges_batch  ->  model(...)  ->  .cpu()
+here: one H2D copy per input into persistent device buffers laid out clouds-major
+([2B,N,*]: clouds 0..B-1 = sources, B..2B-1 = targets), then
+  k-NN (1 launch, all 2B clouds) -> CSR transpose (memset + 4 launches) -> embed (1) ->
+  3 fused E_GCL layers (3) -> eval head + Kabsch (1)
+on one stream, optionally replayed as a CUDA graph; the int64 [B,2,E] edge tensors of the
+reference API are never materialised on this path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+
+H = 32
+
+
+class RegistrationEngine:
+    def __init__(self, model, batch, n=2048, k=16, device=None, use_graph=True):
+        """model: modules.CrossAttentionPoseRegression (its parameters stay the source of truth)."""
+        self.model = model
+        self.B, self.N, self.k = int(batch), int(n), int(k)
+        self.device = torch.device(device if device is not None else next(model.parameters()).device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RegistrationEngine needs a CUDA device: the egspr_b200 hot path has no CPU fallback")
+        if self.N < self.k:
+            raise ValueError("need at least k points per cloud")
+        self.use_graph = use_graph
+        B, N, dev = self.B, self.N, self.device
+        C = 2 * B
+        G, E = C * N, C * N * self.k
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dt=f32: torch.empty(s, dtype=dt, device=dev)
+        # inputs (clouds-major)
+        self.feat = z(C, N, H); self.x = z(C, N, 3)
+        self.labels = torch.zeros(B, N, dtype=f32, device=dev)
+        self.gt_pose = torch.eye(4, dtype=f32, device=dev).repeat(B, 1, 1).contiguous()
+        # graph
+        self.nbr = z(C, N, self.k, dt=i32)
+        self.csr_ptr = z(G + 1, dt=i32); self.csr_row = z(E, dt=i32); self.csr_col = z(E, dt=i32); self.csr_eid = z(E, dt=i32)
+        self.ws_bytes = _lib.lib().egspr_csr_workspace_bytes(G, E)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.err = torch.zeros(1, dtype=i32, device=dev)
+        # layer state (ping-pong)
+        self.h = [z(G, H), z(G, H)]; self.x4 = [z(G, 4), z(G, 4)]
+        self.P = [z(G, H), z(G, H)]; self.Q = [z(G, H), z(G, H)]
+        self.x_out = z(C, N, 3)
+        # outputs
+        self.R = z(B, 3, 3); self.t = z(B, 3); self.Hm = z(B, 3, 3); self.w = z(B, N); self.loss_parts = z(B, 2)
+        self.h_out = None
+        self._graph = None
+        self._graph_key = None
+        self.impl = 0
+        self.launches_per_step = 0
+
+    # ---- input staging -----------------------------------------------------------------------
+    def load(self, src_feat, src_pts, tgt_feat, tgt_pts, labels=None, gt_pose=None):
+        """Copy one batch (host pinned or device tensors, [B,N,*]) into the persistent buffers."""
+        B = self.B
+        self.feat[:B].copy_(src_feat, non_blocking=True); self.feat[B:].copy_(tgt_feat, non_blocking=True)
+        self.x[:B].copy_(src_pts, non_blocking=True); self.x[B:].copy_(tgt_pts, non_blocking=True)
+        if labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+        if gt_pose is not None:
+            self.gt_pose.copy_(gt_pose, non_blocking=True)
+
+    # ---- launch sequence ---------------------------------------------------------------------
+    def _enqueue(self):
+        lib = _lib.lib()
+        p = ops._ptr
+        B, N, k = self.B, self.N, self.k
+        C = 2 * B
+        G = C * N
+        layers, pin, pout = self.model.egnn.packs()
+        head = self.model._pack_head.get()
+        st = ops._stream()
+        n_launch = 0
+        _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), st), "egspr_knn_build"); n_launch += 1
+        _lib.check(lib.egspr_csr_from_nbr(p(self.nbr), C, N, k, p(self.csr_ptr), p(self.csr_row), p(self.csr_col),
+                                          p(self.csr_eid), p(self.ws), self.ws_bytes, p(self.err), st), "egspr_csr_from_nbr")
+        n_launch += 4
+        _lib.check(lib.egspr_node_embed(p(self.feat), p(self.x), G, p(pin), p(layers[0]), p(self.h[0]), p(self.x4[0]),
+                                        p(self.P[0]), p(self.Q[0]), st), "egspr_node_embed"); n_launch += 1
+        cur = 0
+        L = len(layers)
+        for i in range(L):
+            last = i == L - 1
+            nxt = 1 - cur
+            _lib.check(lib.egspr_egcl_forward(
+                p(self.h[cur]), p(self.x4[cur]), p(self.P[cur]), p(self.Q[cur]),
+                p(self.csr_ptr), p(self.csr_row), p(self.csr_col), p(self.csr_eid), None, 1.0,
+                G, N * k, N, p(layers[i]), None if last else p(layers[i + 1]), p(pout) if last else None,
+                p(self.h[nxt]), p(self.x4[nxt]), p(self.x_out) if last else None,
+                None if last else p(self.P[nxt]), None if last else p(self.Q[nxt]), int(self.impl), st), "egspr_egcl_forward")
+            n_launch += 1
+            cur = nxt
+        self.h_out = self.h[cur].view(C, N, H)
+        ho, xo = self.h_out, self.x_out
+        _lib.check(lib.egspr_head_eval(p(self.feat[:B]), p(self.feat[B:]), p(self.x[:B]), p(self.x[B:]),
+                                       p(ho[:B]), p(ho[B:]), p(xo[:B]), p(xo[B:]), p(self.labels), p(self.gt_pose),
+                                       p(head), B, N, int(self.model.top_k), p(self.w), p(self.R), p(self.t), p(self.Hm),
+                                       p(self.loss_parts), st), "egspr_head_eval"); n_launch += 1
+        self.launches_per_step = n_launch
+
+    def run(self):
+        """Enqueue the hot path on the current stream (CUDA-graph replay when enabled)."""
+        with torch.cuda.device(self.device):
+            if not self.use_graph:
+                self._enqueue()
+                return
+            packs = self.model.egnn.packs()
+            key = tuple(t.data_ptr() for t in packs[0]) + (packs[1].data_ptr(), packs[2].data_ptr(),
+                                                           self.model._pack_head.get().data_ptr(), self.impl)
+            if self._graph is None or key != self._graph_key:
+                self._enqueue()                      # warm-up outside capture (function attributes, lazy init)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self._graph, self._graph_key = g, key
+            self._graph.replay()
+
+    def register(self, src_feat, src_pts, tgt_feat, tgt_pts, labels=None, gt_pose=None):
+        """Full step: stage inputs, run, return (R [B,3,3], t [B,3]) device tensors."""
+        self.load(src_feat, src_pts, tgt_feat, tgt_pts, labels, gt_pose)
+        self.run()
+        return self.R, self.t
+
+    def outputs(self):
+        B = self.B
+        return {"R": self.R, "t": self.t, "w": self.w, "H": self.Hm,
+                "h_src": self.h_out[:B], "h_tgt": self.h_out[B:], "x_src": self.x_out[:B], "x_tgt": self.x_out[B:],
+                "equi_loss": self.loss_parts.sum() / (B * self.N), "nbr": self.nbr}

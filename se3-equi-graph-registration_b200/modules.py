@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's Python interface for the registration hot path.
+
+Same class / function names, constructor + forward signatures, sub-module and parameter names as
+the reference (paths under its tree; 3dm = src/3dmatch_train_egnn_with_batch.py,
+evl = src/eval_egnn_metrics.py), so `checkpoints/checkpoint-3dmatch.pth` loads unchanged and the
+classes drop into the train / eval scripts:
+
+  E_GCL                          3dm:185-289
+  EGNN                           3dm:293-340
+  CrossAttentionPoseRegression   3dm:585-796 (train variant) / evl:594-827 (eval variant)
+  unsorted_segment_sum           3dm:343-348
+  knn_graph                      torch_cluster.knn_graph call sites 3dm:1005-1006, evl:1156-1157
+  get_edges_batch                3dm:380-403
+  save_checkpoint / load_checkpoint  3dm:1310-1395
+
+The forward passes run on the hand-written sm_100a kernels through the C ABI (ops.py); there is no
+CPU or eager-PyTorch fallback -- CPU tensors raise.
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, packing
+
+
+# ---------------------------------------------------------------------------------------------
+# functions
+# ---------------------------------------------------------------------------------------------
+def knn_graph(x, k, batch=None, loop=False, flow="source_to_target", cosine=False, num_workers=1):
+    """torch_cluster.knn_graph replacement (same signature).  x [N,3] CUDA f32 -> LongTensor [2,N*k]
+    with edge_index[0] = neighbour ids (k per centre, nearest first), edge_index[1] = centre ids."""
+    if batch is not None or cosine:
+        raise NotImplementedError("egspr_b200.knn_graph: use knn_graph_batch for batches; cosine is unsupported")
+    if x.dim() != 2 or x.shape[1] != 3:
+        raise ValueError("x must be [N,3]")
+    if not loop:
+        raise NotImplementedError("the reference builds its graphs with loop=True (3dm:1005); loop=False is not built")
+    nbr = ops.knn_build(x.unsqueeze(0).to(torch.float32), k)
+    edges = ops.nbr_to_edges(nbr)[0]
+    if flow == "target_to_source":
+        edges = edges.flip(0)
+    return edges
+
+
+def knn_graph_batch(x, k):
+    """x [B,N,3] -> edges LongTensor [B,2,N*k]: the stacked per-item knn_graph(x[i], k, loop=True)
+    the reference assembles in a Python loop (3dm:1003-1013), in one launch."""
+    return ops.nbr_to_edges(ops.knn_build(x.to(torch.float32), k))
+
+
+def get_edges_batch(graph_idx, n_nodes, batch_size):
+    """3dm:380-403 -> ([row, col], edge_attr = ones[E*batch_size, 1]) on the graph's device."""
+    row, col = graph_idx[0], graph_idx[1]
+    edge_attr = torch.ones(row.numel() * batch_size, 1, device=row.device)
+    if batch_size == 1:
+        return [row, col], edge_attr
+    rows = [row + n_nodes * i for i in range(batch_size)]
+    cols = [col + n_nodes * i for i in range(batch_size)]
+    return [torch.cat(rows), torch.cat(cols)], edge_attr
+
+
+def unsorted_segment_sum(data, segment_ids, num_segments):
+    """3dm:343-348, deterministic (ascending edge order) instead of atomics."""
+    import ctypes
+    from . import _lib
+    data = ops._req(data, "data", torch.float32, 2)
+    ids = ops._req(segment_ids, "segment_ids", torch.int64, 1)
+    E, C = data.shape
+    edges = torch.stack([ids, torch.zeros_like(ids)]).unsqueeze(0)
+    g = ops.csr_from_edges(edges, num_segments)
+    out = torch.empty((num_segments, C), dtype=torch.float32, device=data.device)
+    with torch.cuda.device(data.device):
+        _lib.check(_lib.lib().egspr_segment_sum(ops._ptr(data), C, ops._ptr(g.ptr), ops._ptr(g.eid), num_segments,
+                                                ops._ptr(out), ops._stream()), "egspr_segment_sum")
+    return out
+
+
+def _edges_to_tensor(edges):
+    """[row, col] list / tuple / [2,E] tensor -> [1,2,E] int64 contiguous."""
+    if isinstance(edges, (list, tuple)):
+        edges = torch.stack([edges[0], edges[1]])
+    if edges.dim() == 2:
+        edges = edges.unsqueeze(0)
+    return edges.to(torch.int64).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# E_GCL
+# ---------------------------------------------------------------------------------------------
+class E_GCL(nn.Module):
+    """Multi-head E(n) graph conv layer with the 77-wide geometric edge input (3dm:185-289).
+    Parameter layout identical to the reference; forward runs the fused CUDA layer kernel."""
+
+    def __init__(self, input_nf, output_nf, hidden_nf, edges_in_d=0, num_heads=1,
+                 act_fn=nn.SiLU(), residual=True, attention=False, normalize=False, tanh=False, device='cuda:0'):
+        super().__init__()
+        self.residual = residual
+        self.attention = attention
+        self.normalize = normalize
+        self.tanh = tanh
+        self.num_heads = num_heads
+        self.device = device
+        input_edge = input_nf * 2
+        edge_coords_nf = 1
+        so3_feat_dim = 9
+        feature_dim = input_edge + edges_in_d + edge_coords_nf + so3_feat_dim + 2          # 3dm:199
+        self.edge_mlps = nn.ModuleList([
+            nn.Sequential(nn.Linear(feature_dim, hidden_nf // num_heads), act_fn,
+                          nn.Linear(hidden_nf // num_heads, hidden_nf // num_heads))
+            for _ in range(num_heads)])
+        self.layer_norm = nn.LayerNorm(hidden_nf)
+        self.node_mlp = nn.Sequential(nn.Linear(hidden_nf + input_nf, hidden_nf), act_fn,
+                                      nn.Linear(hidden_nf, output_nf))
+        layer = nn.Linear(hidden_nf, edge_coords_nf, bias=False)
+        nn.init.xavier_uniform_(layer.weight, gain=1e-3)                                   # 3dm:220
+        coord_mlp = [nn.Linear(hidden_nf, hidden_nf), act_fn, layer]
+        if self.tanh:
+            coord_mlp.append(nn.Tanh())
+        self.coord_mlp = nn.Sequential(*coord_mlp)
+        self._act_is_silu = isinstance(act_fn, nn.SiLU)
+        self._pack = packing.PackCache(lambda: list(self.parameters()), lambda: packing.pack_layer(self))
+
+    def _check_supported(self):
+        if not self._act_is_silu or self.tanh or self.normalize or not self.residual:
+            raise NotImplementedError(
+                "egspr_b200 E_GCL kernels implement the shipped configuration only: act_fn=SiLU, residual=True, "
+                "normalize=False, tanh=False (3dm:1600-1603)")
+
+    def layer_pack(self):
+        self._check_supported()
+        return self._pack.get()
+
+    def forward(self, h, edge_index, coord, edge_attr=None):
+        """(h [N,32], [row,col], coord [N,3], edge_attr [E,1]|None) -> (h', coord', edge_attr)  3dm:280-289"""
+        graph = ops.csr_from_edges(_edges_to_tensor(edge_index), h.shape[0])
+        ea = None if edge_attr is None else edge_attr.to(torch.float32)
+        h2, x2 = ops.egnn_forward(h.unsqueeze(0), coord.unsqueeze(0), graph, [self.layer_pack()], None, None,
+                                  edge_attr=ea, edge_attr_const=0.0)
+        return h2[0], x2[0], edge_attr
+
+
+# ---------------------------------------------------------------------------------------------
+# EGNN
+# ---------------------------------------------------------------------------------------------
+class EGNN(nn.Module):
+    """3dm:293-340.  `num_heads` is an extra keyword (default 4): the shipped checkpoints carry 4
+    edge-MLP heads per layer although the reference constructor never forwards num_heads
+    (SURVEY F2), so 4 is what makes `load_state_dict(strict=True)` succeed."""
+
+    def __init__(self, in_node_nf, hidden_nf, out_node_nf, in_edge_nf=0, device='cuda:0', act_fn=nn.SiLU(),
+                 n_layers=5, residual=True, attention=True, normalize=False, tanh=False, num_heads=4):
+        super().__init__()
+        self.hidden_nf = hidden_nf
+        self.device = device
+        self.n_layers = n_layers
+        self.embedding_in = nn.Linear(in_node_nf, self.hidden_nf)
+        self.embedding_out = nn.Linear(self.hidden_nf, out_node_nf)
+        for i in range(0, n_layers):
+            self.add_module("gcl_%d" % i, E_GCL(self.hidden_nf, self.hidden_nf, self.hidden_nf, edges_in_d=in_edge_nf,
+                                                num_heads=num_heads, act_fn=act_fn, residual=residual,
+                                                attention=attention, normalize=normalize, tanh=tanh, device=device))
+        self._pack_in = packing.PackCache(lambda: list(self.embedding_in.parameters()),
+                                          lambda: packing.pack_linear32(self.embedding_in))
+        self._pack_out = packing.PackCache(lambda: list(self.embedding_out.parameters()),
+                                           lambda: packing.pack_linear32(self.embedding_out))
+        self.impl = 0
+        self.to(device)                                                                     # 3dm:326
+
+    def packs(self):
+        layers = [self._modules["gcl_%d" % i].layer_pack() for i in range(self.n_layers)]
+        return layers, self._pack_in.get(), self._pack_out.get()
+
+    def forward_batch(self, h, x, graph, edge_attr=None, edge_attr_const=1.0):
+        """Batched form used by the head and the engine: h [C,N,32], x [C,N,3], graph = ops.BatchGraph."""
+        layers, pin, pout = self.packs()
+        return ops.egnn_forward(h, x, graph, layers, pin, pout, edge_attr=edge_attr,
+                                edge_attr_const=edge_attr_const, impl=self.impl)
+
+    def forward(self, h, x, edges, edge_attr):
+        """(h [N,32], x [N,3], [row,col], edge_attr [E,1]) -> (h [N,32], x [N,3])  3dm:328-340"""
+        graph = ops.csr_from_edges(_edges_to_tensor(edges), h.shape[0])
+        ea = None if edge_attr is None else edge_attr.to(torch.float32)
+        ho, xo = self.forward_batch(h.unsqueeze(0).to(torch.float32), x.unsqueeze(0).to(torch.float32), graph,
+                                    edge_attr=ea, edge_attr_const=0.0)
+        return ho[0], xo[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# losses (small reductions on device tensors)
+# ---------------------------------------------------------------------------------------------
+def egnn_equi_loss(h_src, x_src, h_tgt, x_tgt, R_gt, t_gt, labels):
+    """3dm:860-893."""
+    xs = torch.einsum("bij,bnj->bni", R_gt, x_src) + t_gt[:, None, :]
+    rot = (((xs - x_tgt) ** 2).sum(-1) * labels).mean()
+    cs = F.cosine_similarity(h_src, h_tgt, dim=-1)
+    return rot + F.mse_loss(cs, labels.float())
+
+
+def pose_loss(pred_rot, pred_translation, gt_pose, delta=1.5):
+    """3dm:896-962 -> (rotation_loss [B], translation_loss [B])."""
+    gt_t, gt_R = gt_pose[:, :3, 3], gt_pose[:, :3, :3]
+    Rd = torch.matmul(pred_rot.transpose(-1, -2), gt_R)
+    tr = Rd.diagonal(dim1=-2, dim2=-1).sum(-1)
+    rl = torch.arccos(torch.clamp((tr - 1) / 2, min=-1, max=1))
+    cos = (pred_translation * gt_t).sum(-1) / (pred_translation.norm(dim=-1) * gt_t.norm(dim=-1))
+    return rl, torch.arccos(torch.clamp(cos, min=-1, max=1))
+
+
+# ---------------------------------------------------------------------------------------------
+# CrossAttentionPoseRegression
+# ---------------------------------------------------------------------------------------------
+class CrossAttentionPoseRegression(nn.Module):
+    """EGNN on both clouds + correspondence-weight head + weighted Kabsch pose.
+
+    `variant`: 'train' = 3dm:634-796 (weights = softmax of output-feature similarity over the GT
+    inliers, Kabsch on EGNN coords), 'eval' = evl:643-827 (weights from the input-feature
+    similarity / top-128 / mlp chain, Kabsch on the original coords, all points; the reference
+    body only works for B=1 -- here every pair of the batch is treated as its own B=1 call),
+    None (default) = 'train' while self.training else 'eval'.
+    All parameters of the reference exist (incl. the dead shared_mlp_decoder / shallow_mlp_pose /
+    bn1 / bn2) so strict checkpoint loading works."""
+
+    def __init__(self, egnn, num_nodes=2048, hidden_nf=33, device='cuda:0', variant=None):
+        super().__init__()
+        self.egnn = egnn
+        self.hidden_nf = hidden_nf
+        self.num_nodes = num_nodes
+        self.device = device
+        self.variant = variant
+        self.mlp = nn.Sequential(nn.Linear(2 * hidden_nf, hidden_nf), nn.ReLU(),
+                                 nn.Linear(hidden_nf, hidden_nf // 2), nn.ReLU(),
+                                 nn.Linear(hidden_nf // 2, 1))
+        self.shared_mlp_decoder = nn.Sequential(nn.Linear((32 + 3) * 2, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU())
+        self.shallow_mlp_pose = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 7))
+        self.global_pooling = nn.AdaptiveMaxPool1d(1)
+        self.mean_pooling = nn.AdaptiveAvgPool1d(1)
+        self.bn1 = nn.BatchNorm1d(self.hidden_nf)
+        self.bn2 = nn.BatchNorm1d(self.hidden_nf + 3)
+        self.initialize_weights()
+        self._pack_head = packing.PackCache(lambda: list(self.mlp.parameters()), lambda: packing.pack_head(self.mlp))
+        self.top_k = 128
+
+    def initialize_weights(self):
+        for layer in self.mlp:
+            if isinstance(layer, nn.Linear):
+                nn.init.xavier_uniform_(layer.weight)
+                nn.init.zeros_(layer.bias)
+
+    def _variant(self):
+        return self.variant if self.variant is not None else ("train" if self.training else "eval")
+
+    def _egnn_both(self, h_src, x_src, edges_src, edge_attr_src, h_tgt, x_tgt, edges_tgt, edge_attr_tgt):
+        B, N, _ = h_src.shape
+        g_src = edges_src if isinstance(edges_src, ops.BatchGraph) else ops.csr_from_edges(edges_src.to(torch.int64), N)
+        g_tgt = edges_tgt if isinstance(edges_tgt, ops.BatchGraph) else ops.csr_from_edges(edges_tgt.to(torch.int64), N)
+        hs, xs = self.egnn.forward_batch(h_src.to(torch.float32), x_src.to(torch.float32), g_src,
+                                         edge_attr=edge_attr_src, edge_attr_const=0.0 if edge_attr_src is not None else 1.0)
+        ht, xt = self.egnn.forward_batch(h_tgt.to(torch.float32), x_tgt.to(torch.float32), g_tgt,
+                                         edge_attr=edge_attr_tgt, edge_attr_const=0.0 if edge_attr_tgt is not None else 1.0)
+        return hs, xs, ht, xt
+
+    def forward(self, h_src, x_src, edges_src, edge_attr_src, h_tgt, x_tgt, edges_tgt, edge_attr_tgt, corr, labels, gt_pose):
+        """Same 11 inputs / 9 outputs as the reference (3dm:634, 796; evl:643, 827):
+        (R [B,3,3], t [B,3], corr_loss+sim_loss | None, egnn_equi_loss, h_src, x_src, h_tgt, x_tgt, labels).
+        edges_* : [B,2,E] int64 (or a prebuilt ops.BatchGraph); edge_attr_* : [B,E,1] or None (= ones)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError(
+                "egspr_b200 round 1 ships the forward (inference / validation) kernels; run under torch.no_grad(). "
+                "Backward kernels are listed under 'next' in DESIGN.md")
+        B, N, _ = h_src.shape
+        labels_f = labels.to(torch.float32).reshape(B, N)
+        hs, xs, ht, xt = self._egnn_both(h_src, x_src, edges_src, edge_attr_src, h_tgt, x_tgt, edges_tgt, edge_attr_tgt)
+        if self._variant() == "eval":
+            R, t, w, Hm, lp = ops.head_eval(h_src.to(torch.float32), h_tgt.to(torch.float32), x_src.to(torch.float32),
+                                            x_tgt.to(torch.float32), hs, ht, xs, xt, labels_f, gt_pose,
+                                            self._pack_head.get(), top_k=self.top_k)
+            total_loss = lp.sum(0).sum() / (B * N)                                           # evl:687
+            self.last_aux = {"w": w, "H": Hm}
+            return R, t, None, total_loss, hs, xs, ht, xt, labels
+        R, t, w, sim, Hm, lp = ops.head_train(hs, ht, xs, xt, labels_f, gt_pose)
+        total_loss = lp.sum(0).sum() / (B * N)                                               # 3dm:677
+        self.last_aux = {"w": w, "H": Hm}
+        # correspondence BCE on the top-128 + similarity-consistency loss (3dm:681-694, 760-781)
+        k = min(self.top_k, N)
+        _, top_idx = torch.topk(sim, k=k, dim=-1)
+        Fd = hs.shape[-1]
+        chs = torch.gather(hs, 1, top_idx.unsqueeze(-1).expand(-1, -1, Fd))
+        cht = torch.gather(ht, 1, top_idx.unsqueeze(-1).expand(-1, -1, Fd))
+        cl = torch.gather(labels_f, 1, top_idx)
+        scores = self.mlp(torch.cat([chs, cht], dim=-1).view(-1, 2 * Fd)).view(B, k)
+        corr_loss = F.binary_cross_entropy_with_logits(scores, cl)
+        raw = (h_src.to(torch.float32) * h_tgt.to(torch.float32)).sum(-1)
+        simn = (sim - sim.mean()) / (sim.std() + 1e-6)
+        rawn = (raw - raw.mean()) / (raw.std() + 1e-6)
+        sim_loss = F.mse_loss(simn, rawn)
+        return R, t, corr_loss + sim_loss, total_loss, hs, xs, ht, xt, labels
+
+
+# ---------------------------------------------------------------------------------------------
+# checkpoints (3dm:1310-1395)
+# ---------------------------------------------------------------------------------------------
+def save_checkpoint(save_dir, epoch, egnn, cross_attention, optimizer=None, pointnet=None, best=False):
+    os.makedirs(save_dir, exist_ok=True)
+    ck = {"epoch": epoch, "egnn_state_dict": egnn.state_dict(),
+          "cross_attention_state_dict": cross_attention.state_dict()}
+    if optimizer is not None:
+        ck["optimizer_state_dict"] = optimizer.state_dict()
+    if pointnet is not None:
+        ck["pointnet_state_dict"] = pointnet.state_dict()
+    path = os.path.join(save_dir, "best_checkpoint.pth" if best else f"model_epoch_{epoch}.pth")
+    torch.save(ck, path)
+    return path
+
+
+def load_checkpoint(checkpoint_path, pointnet, egnn, cross_attention, optimizer=None, use_pointnet=False, device='cuda:0'):
+    """Same contract as 3dm:1351-1395: strict load of 'egnn_state_dict' and
+    'cross_attention_state_dict' (+ optional pointnet / optimizer); returns (checkpoint, epoch)."""
+    if not os.path.isfile(checkpoint_path):
+        raise FileNotFoundError(f"Checkpoint file not found at: {checkpoint_path}")
+    ck = torch.load(checkpoint_path, map_location=device, weights_only=True)
+    egnn.load_state_dict(ck["egnn_state_dict"])
+    cross_attention.load_state_dict(ck["cross_attention_state_dict"])
+    if use_pointnet and pointnet is not None and "pointnet_state_dict" in ck:
+        pointnet.load_state_dict(ck["pointnet_state_dict"])
+    if optimizer is not None and "optimizer_state_dict" in ck:
+        optimizer.load_state_dict(ck["optimizer_state_dict"])
+    return ck, ck.get("epoch", 0)

@@ -1,0 +1,222 @@
+"""Thin functional layer over the C ABI (include/egspr_b200.h): argument checking, output
+allocation with torch (device memory + streams are PyTorch's job), ctypes calls on the current
+CUDA stream.  Every function requires CUDA tensors; there is no CPU path."""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+H = 32
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, name, dtype, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the egspr_b200 hot path has no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def knn_build(x, k):
+    """x [C,N,3] f32 -> nbr [C,N,k] i32 (nearest first, ties -> lower index, self included)."""
+    x = _req(x, "x", torch.float32, 3)
+    C, N, D = x.shape
+    if D != 3:
+        raise ValueError("k-NN is built over 3-d points")
+    nbr = torch.empty((C, N, k), dtype=torch.int32, device=x.device)
+    if C * N == 0:
+        return nbr
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().egspr_knn_build(_ptr(x), C, N, k, _ptr(nbr), _stream()), "egspr_knn_build")
+    return nbr
+
+
+def nbr_to_edges(nbr):
+    """nbr [C,N,k] i32 -> edges [C,2,N*k] i64 in torch_cluster.knn_graph layout."""
+    nbr = _req(nbr, "nbr", torch.int32, 3)
+    C, N, k = nbr.shape
+    edges = torch.empty((C, 2, N * k), dtype=torch.int64, device=nbr.device)
+    with torch.cuda.device(nbr.device):
+        _lib.check(_lib.lib().egspr_nbr_to_edges(_ptr(nbr), C, N, k, _ptr(edges), _stream()), "egspr_nbr_to_edges")
+    return edges
+
+
+@dataclass
+class BatchGraph:
+    """Row-major CSR of a batch of per-cloud graphs (global node ids)."""
+    ptr: torch.Tensor     # [G+1] i32
+    row: torch.Tensor     # [E] i32
+    col: torch.Tensor     # [E] i32
+    eid: torch.Tensor     # [E] i32  original edge id inside the cloud
+    clouds: int
+    n: int
+    edges_per_cloud: int
+    err: torch.Tensor     # [1] i32, 1 if an index was out of range
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise IndexError("edge index out of range for the given number of nodes")
+
+
+def _csr_alloc(C, N, epc, device):
+    G, E = C * N, C * epc
+    lib = _lib.lib()
+    ws_bytes = lib.egspr_csr_workspace_bytes(G, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    g = BatchGraph(torch.empty(G + 1, dtype=torch.int32, device=device),
+                   torch.empty(E, dtype=torch.int32, device=device),
+                   torch.empty(E, dtype=torch.int32, device=device),
+                   torch.empty(E, dtype=torch.int32, device=device),
+                   C, N, epc, torch.zeros(1, dtype=torch.int32, device=device))
+    return g, ws, ws_bytes
+
+
+def csr_from_nbr(nbr):
+    nbr = _req(nbr, "nbr", torch.int32, 3)
+    C, N, k = nbr.shape
+    g, ws, ws_bytes = _csr_alloc(C, N, N * k, nbr.device)
+    with torch.cuda.device(nbr.device):
+        _lib.check(_lib.lib().egspr_csr_from_nbr(_ptr(nbr), C, N, k, _ptr(g.ptr), _ptr(g.row), _ptr(g.col), _ptr(g.eid),
+                                                 _ptr(ws), ws_bytes, _ptr(g.err), _stream()), "egspr_csr_from_nbr")
+    return g
+
+
+def csr_from_edges(edges, n):
+    """edges [C,2,E] i64 (row = edge_index[0], col = edge_index[1], cloud-local ids)."""
+    edges = _req(edges, "edges", torch.int64, 3)
+    C, two, E = edges.shape
+    if two != 2:
+        raise ValueError("edges must be [C,2,E]")
+    if E == 0:
+        raise ValueError("empty edge list")
+    g, ws, ws_bytes = _csr_alloc(C, n, E, edges.device)
+    with torch.cuda.device(edges.device):
+        _lib.check(_lib.lib().egspr_csr_from_edges(_ptr(edges), C, n, E, _ptr(g.ptr), _ptr(g.row), _ptr(g.col), _ptr(g.eid),
+                                                   _ptr(ws), ws_bytes, _ptr(g.err), _stream()), "egspr_csr_from_edges")
+    return g
+
+
+def egnn_forward(feat, x, graph, layer_packs, embed_in_pack, embed_out_pack, edge_attr=None,
+                 edge_attr_const=1.0, impl=0, return_layers=False):
+    """EGNN.forward (3dm:328-340) for all clouds of a batch.
+    feat [C,N,32], x [C,N,3] -> h_out [C,N,32], x_out [C,N,3].
+    embed_in_pack / embed_out_pack may be None (stand-alone E_GCL stack)."""
+    feat = _req(feat, "h", torch.float32, 3)
+    x = _req(x, "x", torch.float32, 3)
+    C, N, F = feat.shape
+    if F != H:
+        raise NotImplementedError(f"feature width must be {H}, got {F}")
+    if (C, N) != (graph.clouds, graph.n) or tuple(x.shape) != (C, N, 3):
+        raise ValueError("feature / coordinate / graph shapes disagree")
+    if edge_attr is not None:
+        edge_attr = _req(edge_attr, "edge_attr", torch.float32).reshape(-1)
+        if edge_attr.numel() != C * graph.edges_per_cloud:
+            raise ValueError("edge_attr must have one scalar per edge")
+    dev = feat.device
+    G = C * N
+    lib = _lib.lib()
+    hbuf = [torch.empty((G, H), dtype=torch.float32, device=dev) for _ in range(2)]
+    xbuf = [torch.empty((G, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+    pbuf = [torch.empty((G, H), dtype=torch.float32, device=dev) for _ in range(2)]
+    qbuf = [torch.empty((G, H), dtype=torch.float32, device=dev) for _ in range(2)]
+    x_out = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+    layers = []
+    with torch.cuda.device(dev):
+        st = _stream()
+        _lib.check(lib.egspr_node_embed(_ptr(feat), _ptr(x), G, _ptr(embed_in_pack), _ptr(layer_packs[0]),
+                                        _ptr(hbuf[0]), _ptr(xbuf[0]), _ptr(pbuf[0]), _ptr(qbuf[0]), st), "egspr_node_embed")
+        cur = 0
+        L = len(layer_packs)
+        for i in range(L):
+            last = i == L - 1
+            nxt = 1 - cur
+            want_x3 = last or return_layers
+            x3 = x_out if last else (torch.empty((C, N, 3), dtype=torch.float32, device=dev) if return_layers else None)
+            _lib.check(lib.egspr_egcl_forward(
+                _ptr(hbuf[cur]), _ptr(xbuf[cur]), _ptr(pbuf[cur]), _ptr(qbuf[cur]),
+                _ptr(graph.ptr), _ptr(graph.row), _ptr(graph.col), _ptr(graph.eid),
+                _ptr(edge_attr), float(edge_attr_const), G, graph.edges_per_cloud, N,
+                _ptr(layer_packs[i]), None if last else _ptr(layer_packs[i + 1]),
+                _ptr(embed_out_pack) if last else None,
+                _ptr(hbuf[nxt]), _ptr(xbuf[nxt]), _ptr(x3) if want_x3 else None,
+                None if last else _ptr(pbuf[nxt]), None if last else _ptr(qbuf[nxt]), int(impl), st), "egspr_egcl_forward")
+            cur = nxt
+            if return_layers and not last:
+                layers.append((hbuf[cur].view(C, N, H).clone(), x3))
+    h_out = hbuf[cur].view(C, N, H)
+    if return_layers:
+        return h_out, x_out, layers
+    return h_out, x_out
+
+
+def kabsch(p, q, w, mask=None):
+    """Batched weighted Kabsch (3dm:726-758).  p,q [B,n,3], w [B,n] -> R [B,3,3], t [B,3], H [B,3,3]."""
+    p = _req(p, "p", torch.float32, 3)
+    q = _req(q, "q", torch.float32, 3)
+    w = _req(w, "w", torch.float32, 2)
+    B, n, _ = p.shape
+    if mask is not None:
+        mask = _req(mask.to(torch.float32), "mask", torch.float32, 2)
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=p.device)
+    t = torch.empty((B, 3), dtype=torch.float32, device=p.device)
+    Hm = torch.empty((B, 3, 3), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().egspr_kabsch(_ptr(p), _ptr(q), _ptr(w), _ptr(mask), B, n, _ptr(R), _ptr(t), _ptr(Hm), _stream()),
+                   "egspr_kabsch")
+    return R, t, Hm
+
+
+def head_eval(feat_src, feat_tgt, x_src, x_tgt, h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose,
+              head_pack, top_k=128):
+    """Eval-variant weights + Kabsch (evl:691-818), every pair treated as its own B=1 call.
+    Returns R [B,3,3], t [B,3], w [B,n], H [B,3,3], loss_parts [B,2]."""
+    ts = [_req(v, nm, torch.float32, 3) for v, nm in
+          ((feat_src, "feat_src"), (feat_tgt, "feat_tgt"), (x_src, "x_src"), (x_tgt, "x_tgt"),
+           (h_out_src, "h_out_src"), (h_out_tgt, "h_out_tgt"), (x_out_src, "x_out_src"), (x_out_tgt, "x_out_tgt"))]
+    B, n, _ = ts[0].shape
+    labels = _req(labels.to(torch.float32), "labels", torch.float32, 2)
+    gt_pose = _req(gt_pose.to(torch.float32), "gt_pose", torch.float32, 3)
+    dev = ts[0].device
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    t = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    Hm = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    w = torch.empty((B, n), dtype=torch.float32, device=dev)
+    lp = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().egspr_head_eval(*[_ptr(v) for v in ts], _ptr(labels), _ptr(gt_pose), _ptr(head_pack),
+                                              B, n, int(top_k), _ptr(w), _ptr(R), _ptr(t), _ptr(Hm), _ptr(lp), _stream()),
+                   "egspr_head_eval")
+    return R, t, w, Hm, lp
+
+
+def head_train(h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose):
+    """Train-variant weights + Kabsch (3dm:696-758).  Returns R, t, w, sim, H, loss_parts."""
+    ts = [_req(v, nm, torch.float32, 3) for v, nm in
+          ((h_out_src, "h_out_src"), (h_out_tgt, "h_out_tgt"), (x_out_src, "x_out_src"), (x_out_tgt, "x_out_tgt"))]
+    B, n, _ = ts[0].shape
+    labels = _req(labels.to(torch.float32), "labels", torch.float32, 2)
+    gt_pose = _req(gt_pose.to(torch.float32), "gt_pose", torch.float32, 3)
+    dev = ts[0].device
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    t = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    Hm = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    w = torch.empty((B, n), dtype=torch.float32, device=dev)
+    sim = torch.empty((B, n), dtype=torch.float32, device=dev)
+    lp = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().egspr_head_train(*[_ptr(v) for v in ts], _ptr(labels), _ptr(gt_pose), B, n,
+                                               _ptr(w), _ptr(sim), _ptr(R), _ptr(t), _ptr(Hm), _ptr(lp), _stream()),
+                   "egspr_head_train")
+    return R, t, w, sim, Hm, lp

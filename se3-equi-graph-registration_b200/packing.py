@@ -1,0 +1,98 @@
+"""Weight packs: the live nn.Parameters (checkpoint layout) re-laid-out for the
+kernels.  state_dict stays the single source of truth -- packs are derived tensors, rebuilt
+whenever a parameter's storage or version counter changes (optimizer step, load_state_dict).
+
+Layouts mirror csrc/egspr_common.cuh (OFF_* constants).  Reference shapes:
+  gcl_i.edge_mlps.{g}.0.weight (8,77|76)  gcl_i.edge_mlps.{g}.2.weight (8,8)   3dm:202-208
+  gcl_i.layer_norm (32)                                                         3dm:209
+  gcl_i.node_mlp.0.weight (32,64), .2.weight (32,32)                            3dm:212-216
+  gcl_i.coord_mlp.0.weight (32,32), .2.weight (1,32) no bias                    3dm:219-229
+  embedding_in/out (32,32)                                                      3dm:320-321
+  mlp.0 (32,64), mlp.2 (16,32), mlp.4 (1,16)                                    3dm:594-600
+"""
+import torch
+
+H = 32
+LAYER_PACK = 7104
+EMBED_PACK = 1056
+HEAD_PACK = 2640
+
+OFF = dict(WG=0, W2P=384, B2=640, LNG=672, LNB=704, WC1=736, BC1=1760, WC2=1792, WN1T=1824, BN1=3872,
+           WN2T=3904, BN2=4928, WPT=4960, WQT=5984, BQ=7008, WEA=7040)
+
+
+def _put(buf, off, t):
+    t = t.detach().reshape(-1).to(torch.float32)
+    buf[off:off + t.numel()] = t
+
+
+def pack_layer(gcl):
+    """gcl: an E_GCL-shaped module (edge_mlps, layer_norm, node_mlp, coord_mlp)."""
+    heads = list(gcl.edge_mlps)
+    w1 = torch.cat([m[0].weight for m in heads], dim=0)        # [32, F]
+    b1 = torch.cat([m[0].bias for m in heads], dim=0)
+    F_in = w1.shape[1]
+    if w1.shape[0] != H or len(heads) != 4 or F_in not in (76, 77):
+        raise NotImplementedError(
+            f"egspr_b200 kernels are specialised for hidden_nf=32, num_heads=4, edges_in_d in (0,1); got "
+            f"hidden={w1.shape[0]}, heads={len(heads)}, edge feature width={F_in}")
+    buf = torch.zeros(LAYER_PACK, dtype=torch.float32, device=w1.device)
+    _put(buf, OFF["WG"], w1[:, 64:76].t().contiguous())                       # [12][32]
+    _put(buf, OFF["W2P"], torch.stack([m[2].weight.t() for m in heads]))      # [4][in 8][out 8]
+    _put(buf, OFF["B2"], torch.cat([m[2].bias for m in heads]))
+    _put(buf, OFF["LNG"], gcl.layer_norm.weight)
+    _put(buf, OFF["LNB"], gcl.layer_norm.bias)
+    _put(buf, OFF["WC1"], gcl.coord_mlp[0].weight)                            # [out][in]
+    _put(buf, OFF["BC1"], gcl.coord_mlp[0].bias)
+    _put(buf, OFF["WC2"], gcl.coord_mlp[2].weight[0])
+    _put(buf, OFF["WN1T"], gcl.node_mlp[0].weight.t().contiguous())           # [64][32]
+    _put(buf, OFF["BN1"], gcl.node_mlp[0].bias)
+    _put(buf, OFF["WN2T"], gcl.node_mlp[2].weight.t().contiguous())
+    _put(buf, OFF["BN2"], gcl.node_mlp[2].bias)
+    _put(buf, OFF["WPT"], w1[:, 0:32].t().contiguous())
+    _put(buf, OFF["WQT"], w1[:, 32:64].t().contiguous())
+    _put(buf, OFF["BQ"], b1)
+    if F_in == 77:
+        _put(buf, OFF["WEA"], w1[:, 76])
+    return buf
+
+
+def pack_linear32(lin):
+    if tuple(lin.weight.shape) != (H, H):
+        raise NotImplementedError(f"embedding Linear must be 32x32 for the egspr_b200 kernels, got {tuple(lin.weight.shape)}")
+    buf = torch.zeros(EMBED_PACK, dtype=torch.float32, device=lin.weight.device)
+    _put(buf, 0, lin.weight.t().contiguous())
+    _put(buf, 1024, lin.bias)
+    return buf
+
+
+def pack_head(mlp):
+    l0, l1, l2 = mlp[0], mlp[2], mlp[4]
+    if tuple(l0.weight.shape) != (32, 64) or tuple(l1.weight.shape) != (16, 32) or tuple(l2.weight.shape) != (1, 16):
+        raise NotImplementedError("correspondence mlp must be 64->32->16->1 (hidden_nf=32)")
+    buf = torch.zeros(HEAD_PACK, dtype=torch.float32, device=l0.weight.device)
+    _put(buf, 0, l0.weight.t().contiguous())      # [64][32]
+    _put(buf, 2048, l0.bias)
+    _put(buf, 2080, l1.weight.t().contiguous())   # [32][16]
+    _put(buf, 2592, l1.bias)
+    _put(buf, 2608, l2.weight[0])
+    _put(buf, 2624, l2.bias)
+    return buf
+
+
+class PackCache:
+    """Rebuilds a pack only when one of the source parameters changed (data_ptr or _version)."""
+
+    def __init__(self, params_fn, build_fn):
+        self._params_fn = params_fn
+        self._build_fn = build_fn
+        self._key = None
+        self._val = None
+
+    def get(self):
+        key = tuple((p.data_ptr(), p._version, p.device) for p in self._params_fn())
+        if key != self._key:
+            with torch.no_grad():
+                self._val = self._build_fn()
+            self._key = key
+        return self._val
