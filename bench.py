@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Registration-throughput benchmark (BASELINE.json metric: registration pairs/s, EGNN forward on
+both clouds + correspondence-weight head + SVD pose, k-NN graph build included, 2048 points).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of 64 synthetic 3DMatch-shaped pairs per GPU
+(BASELINE.json configs[1]); multi-GPU = pair-sharded replicas, no data-path collective (weak
+scaling).  Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "registration pairs/sec (k-NN graph + EGNN fwd on both clouds + weight head + Kabsch SVD pose) at 2048 pts"
+UNIT = "pairs/s"
+PAIRS_PER_GPU = 64
+N_POINTS = 2048
+K_NEIGH = 16
+HIDDEN = 32
+CKPT = os.path.join(ROOT, "tests", "golden", "checkpoint-3dmatch.pth")
+# gather-inclusive algorithmic bytes of the fused edge kernel per cloud*layer:
+#   E*(2*H*4 + 2*12 + 4) + N*(H*4 + 12),  E = N*k
+EDGE_BYTES_PER_CLOUD_LAYER = N_POINTS * K_NEIGH * (2 * HIDDEN * 4 + 2 * 12 + 4) + N_POINTS * (HIDDEN * 4 + 12)
+
+
+def shard_range(total, rank, world):
+    """Contiguous slice [lo, hi) of `total` pairs owned by `rank` (pair-sharded replicas)."""
+    return total * rank // world, total * (rank + 1) // world
+
+
+def max_over_ranks(value, device):
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline = the oracle port of the reference's eval path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pairs(pairs, seed, threads):
+    """Runs the reference's CPU path (oracle port: k-NN per the stated spec + eval-variant forward,
+    src/eval_egnn_metrics.py:1154-1243) on `pairs` synthetic pairs, one at a time like evl:1122
+    (batch_size 1).  Returns elapsed seconds."""
+    from oracle import egnn_oracle as O
+    from oracle import knn_oracle
+    import se3_equi_graph_registration_b200.synthetic as synthetic
+    torch.set_num_threads(threads)
+    sd = torch.load(CKPT, map_location="cpu", weights_only=True)["cross_attention_state_dict"]
+    data = synthetic.make_batch(seed, pairs, n=N_POINTS)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for b in range(pairs):
+            sl = slice(b, b + 1)
+            ns = torch.from_numpy(knn_oracle.knn(data["src_pts"][b].numpy(), K_NEIGH, threads=threads))
+            nt = torch.from_numpy(knn_oracle.knn(data["tgt_pts"][b].numpy(), K_NEIGH, threads=threads))
+            es = torch.stack(O.edges_from_nbr(ns))[None]
+            et = torch.stack(O.edges_from_nbr(nt))[None]
+            O.forward_eval(sd, data["src_feat"][sl], data["src_pts"][sl], es, data["tgt_feat"][sl], data["tgt_pts"][sl], et,
+                           data["labels"][sl], data["gt_pose"][sl])
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_pairs = 4                           # bounded sample of the 64-pair workload per step
+    from oracle import knn_oracle
+    knn_oracle.build()
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pairs(1, 1000, threads)
+    t = 0.0
+    for s in range(args.steps):
+        t += cpu_reference_pairs(sample_pairs, 2000 + s, threads)
+    value = sample_pairs * args.steps / t
+    sample = (f"{sample_pairs} of the {PAIRS_PER_GPU} pairs per step, batch_size 1 as evl:1122, oracle port "
+              f"(torch CPU ops) + brute-force k-NN spec in C, {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "3DMatch-shaped inference, BASELINE configs[1]: 64 pairs/GPU x 2 clouds x 2048 pts, 32-d unit-norm feats, "
+                        "k=16 (loop=True), 3 E_GCL layers x 4 heads, checkpoint-3dmatch.pth, eval-variant head",
+            "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus, "points": N_POINTS, "k": K_NEIGH,
+            "parallelism": f"pair-sharded replicas x{n_gpus}, no data-path collective",
+            "l2": "4 resident input batches rotated + 256 MiB L2 flush between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    import se3_equi_graph_registration_b200 as P
+    from se3_equi_graph_registration_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.lib()                                      # fail loudly if the CUDA library is missing
+    model = P.build_model(CKPT, device=dev)
+    B = PAIRS_PER_GPU
+    lo, _ = shard_range(B * world, rank, world)     # this rank's first global pair id -> distinct seeds per rank
+    n_rot = 4
+    host = [P.synthetic.make_batch(100 + rank * n_rot + i, B, n=N_POINTS, pin=True) for i in range(n_rot)]
+    devb = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    eng = P.RegistrationEngine(model, batch=B, n=N_POINTS, k=K_NEIGH, device=dev, use_graph=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "labels", "gt_pose")
+
+    def step_resident(i):
+        d = devb[i % n_rot]
+        eng.register(*[d[k] for k in keys])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM --------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                               # evict L2 between timed steps (outside the event pair)
+        evs[i][0].record()
+        step_resident(i)
+        evs[i][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    ms_total = max_over_ranks(ms_total, dev)
+    ms_per_step = ms_total / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: host pinned inputs -> H2D -> hot path -> D2H of (R, t), every step ---------------
+    out_R = torch.empty((B, 3, 3), dtype=torch.float32).pin_memory()
+    out_t = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        h = host[i % n_rot]
+        eng.register(*[h[k] for k in keys])
+        out_R.copy_(eng.R, non_blocking=True)
+        out_t.copy_(eng.t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the poses on the host
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    e2e_wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / args.steps
+    e2e_value = B * world / (max(e2e_ms, e2e_wall_ms) * 1e-3)
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in keys)
+    d2h = out_R.numel() * 4 + out_t.numel() * 4
+
+    # ---- roofline of the dominant kernel (fused E_GCL layer), timed alone on its stream ---------
+    roof = None
+    cpu = None
+    if rank == 0:
+        layer_ms = eng_layer_time(eng, reps=20)
+        alg_bytes = EDGE_BYTES_PER_CLOUD_LAYER * 2 * B
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_bytes / (layer_ms * 1e-3) / 1e9
+        roof = {"kernel": "egcl_layer_kernel (fused edge+reduce+node update, 1 launch per layer)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "peak_source": "MEASURED_PEAKS.json burst" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_launch": alg_bytes,
+                "launch_ms": layer_ms, "traffic": load_traffic()}
+        # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------
+        threads = os.cpu_count() or 1
+        from oracle import knn_oracle
+        knn_oracle.build()
+        cpu_reference_pairs(1, 999, threads)
+        n_s, t_s = 0, 0.0
+        while t_s < 10.0 and n_s < 64:
+            t_s += cpu_reference_pairs(4, 3000 + n_s, threads)
+            n_s += 4
+        cpu = {"value": n_s / t_s, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_s} pairs of the same workload, one at a time (batch_size 1 as evl:1122), k-NN included"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": max(e2e_ms, e2e_wall_ms), "api": "RegistrationEngine.register(host pinned tensors) + R,t to host"},
+                "gpu_launches": eng.launches_per_step * args.steps, "launches_per_step": eng.launches_per_step,
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+
+
+def eng_layer_time(eng, reps=20):
+    """Average duration of ONE fused E_GCL layer launch (layer 1 of 3, all 2B clouds), CUDA events on
+    the launching stream, L2 flushed before each launch."""
+    import ctypes
+    from se3_equi_graph_registration_b200 import _lib, ops
+    lib = _lib.lib()
+    p = ops._ptr
+    layers, pin, pout = eng.model.egnn.packs()
+    G = 2 * eng.B * eng.N
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+    eng.use_graph = False
+    eng.run()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for r in range(reps + 3):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(lib.egspr_egcl_forward(p(eng.h[0]), p(eng.x4[0]), p(eng.P[0]), p(eng.Q[0]), p(eng.csr_ptr), p(eng.csr_row),
+                                          p(eng.csr_col), p(eng.csr_eid), None, 1.0, G, eng.N * eng.k, eng.N,
+                                          p(layers[0]), p(layers[1]), None, p(eng.h[1]), p(eng.x4[1]), None,
+                                          p(eng.P[1]), p(eng.Q[1]), int(eng.impl), ops._stream()), "egspr_egcl_forward")
+        b.record()
+        torch.cuda.synchronize()
+        if r >= 3:
+            tot += a.elapsed_time(b)
+    eng.use_graph = True
+    return tot / reps
+
+
+def load_traffic():
+    """dram bytes per launch of the layer kernel from the committed ncu --set full summary, if any."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "edge_kernel_traffic.json")))
+        return j.get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

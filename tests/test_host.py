@@ -1,0 +1,171 @@
+"""CPU: host-side mirror (module / parameter layout, checkpoint loading, packs), the C-ABI
+library's exported symbols, loud failure without a GPU, and the pair-sharding logic (gloo, 2 ranks)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import se3_equi_graph_registration_b200 as P
+from se3_equi_graph_registration_b200 import _lib, packing
+from oracle import egnn_oracle as O
+import pack_emulator as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "egspr_b200.h")).read()
+    declared = set(re.findall(r"\b(egspr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(handle, name) is not None
+    lib = _lib.lib()
+    assert lib.egspr_version() >= 100
+    assert lib.egspr_error_string(-2).decode().startswith("unsupported")
+    assert lib.egspr_csr_workspace_bytes(2048, 32768) >= 4 * (2048 + 32768)
+    # pack sizes in the header agree with the host packer
+    for macro, val in (("EGSPR_LAYER_PACK_FLOATS", packing.LAYER_PACK), ("EGSPR_EMBED_PACK_FLOATS", packing.EMBED_PACK),
+                       ("EGSPR_HEAD_PACK_FLOATS", packing.HEAD_PACK)):
+        assert int(re.search(macro + r"\s+(\d+)", hdr).group(1)) == val
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out), out
+
+
+@pytest.mark.parametrize("ck", ["checkpoint-3dmatch.pth", "checkpoint-3dmatch-no-encoder.pth"])
+def test_checkpoint_loads_unchanged(golden_dir, ck):
+    model = P.build_model(None, device="cpu")
+    ckpt, epoch = P.load_checkpoint(os.path.join(golden_dir, ck), None, model.egnn, model, device="cpu")   # strict
+    assert epoch == ckpt["epoch"] and epoch in (21, 58)
+    assert set(model.egnn.state_dict()) == set(ckpt["egnn_state_dict"])
+    assert set(model.state_dict()) == set(ckpt["cross_attention_state_dict"])
+    for k, v in ckpt["cross_attention_state_dict"].items():
+        assert tuple(model.state_dict()[k].shape) == tuple(v.shape), k
+    assert sum(p.numel() for p in model.parameters()) == 45742
+    # Adam state of the checkpoint maps onto the parameter order (97 params in one group)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt.load_state_dict(ckpt["optimizer_state_dict"])
+
+
+def test_checkpoint_round_trip(tmp_path, golden_dir):
+    model = P.build_model(os.path.join(golden_dir, "checkpoint-3dmatch.pth"), device="cpu")
+    path = P.save_checkpoint(str(tmp_path), 3, model.egnn, model, torch.optim.Adam(model.parameters()))
+    m2 = P.build_model(None, device="cpu")
+    _, ep = P.load_checkpoint(path, None, m2.egnn, m2, device="cpu")
+    assert ep == 3
+    for (k, a), (_, b) in zip(model.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(FileNotFoundError):
+        P.load_checkpoint(str(tmp_path / "nope.pth"), None, m2.egnn, m2, device="cpu")
+
+
+def test_reference_default_num_heads_would_not_load(golden_dir):
+    """with the reference's num_heads=1 default the shipped checkpoint does not load."""
+    egnn = P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=3, num_heads=1)
+    ck = torch.load(os.path.join(golden_dir, "checkpoint-3dmatch.pth"), map_location="cpu", weights_only=True)
+    with pytest.raises(RuntimeError):
+        egnn.load_state_dict(ck["egnn_state_dict"])
+
+
+@pytest.mark.parametrize("name", ["small_b2_n256", "kitti_b1_n1024"])
+def test_weight_packs_reproduce_the_reference(golden_dir, name):
+    """The packs the kernels read, pushed through a plain-torch emulation of the kernel algebra,
+    give the reference's outputs -> layout / transposes / P-Q split / bias folding are right."""
+    g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False, map_location="cpu")
+    model = P.build_model(os.path.join(golden_dir, "checkpoint-3dmatch.pth"), device="cpu")
+    layers, pin, pout = model.egnn.packs()
+    inp = g["inputs"]
+    row, col = O.edges_from_nbr(g["nbr_src"][0])
+    h, x = E.egnn(layers, pin, pout, inp["src_feat"][0], inp["src_pts"][0], row, col)
+    ref = g["eval_f32"]
+    assert float((h - ref["h_src"][0]).abs().max()) <= 2e-6 * float(ref["h_src"][0].abs().max())
+    assert float((x - ref["x_src"][0]).abs().max()) <= 1e-5 * max(1.0, float(ref["x_src"][0].abs().max()))
+    z = torch.randn(5, 64)
+    assert torch.allclose(E.head_mlp(model._pack_head.get(), z), model.mlp(z).squeeze(-1), atol=1e-5)
+
+
+def test_pack_cache_tracks_parameter_updates():
+    model = P.build_model(None, device="cpu")
+    gcl = model.egnn.gcl_0
+    a = gcl.layer_pack()
+    assert gcl.layer_pack() is a
+    with torch.no_grad():
+        gcl.layer_norm.weight.add_(1.0)
+    b = gcl.layer_pack()
+    assert b is not a and not torch.equal(a, b)
+    assert torch.allclose(b[packing.OFF["LNG"]:packing.OFF["LNG"] + 32], gcl.layer_norm.weight)
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=1, tanh=True).packs()
+    with pytest.raises(NotImplementedError):
+        P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=1, num_heads=2).packs()
+    with pytest.raises(NotImplementedError):
+        P.EGNN(33, 64, 33, in_edge_nf=1, device="cpu", n_layers=1).packs()
+
+
+def test_no_cpu_fallback():
+    model = P.build_model(None, device="cpu")
+    x = torch.rand(32, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.knn_graph(x, 16, loop=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.egnn(torch.rand(32, 32), x, [torch.zeros(4, dtype=torch.long)] * 2, torch.ones(4, 1))
+    with pytest.raises(RuntimeError):
+        P.RegistrationEngine(model, batch=1, n=32, device="cpu")
+    # the product never imports the oracle
+    pkg = os.path.join(ROOT, "se3-equi-graph-registration_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read(), fn
+
+
+def test_get_edges_batch_layout():
+    gi = torch.tensor([[1, 2, 0], [0, 0, 1]])
+    (row, col), ea = P.get_edges_batch(gi, 3, 1)
+    assert torch.equal(row, gi[0]) and torch.equal(col, gi[1]) and tuple(ea.shape) == (3, 1) and bool((ea == 1).all())
+    (row, col), ea = P.get_edges_batch(gi, 3, 2)
+    assert row.tolist() == [1, 2, 0, 4, 5, 3] and col.tolist() == [0, 0, 1, 3, 3, 4] and ea.shape[0] == 6
+
+
+def test_synthetic_pairs_follow_the_dataset_contract():
+    d = P.synthetic.make_pair(0, n=2048, dup_frac=0.3)
+    assert d["src_pts"].shape == (2048, 3) and d["src_feat"].shape == (2048, 32) and d["gt_pose"].shape == (4, 4)
+    assert np.allclose(np.linalg.norm(d["src_feat"], axis=1), 1, atol=1e-5)
+    R, t = d["gt_pose"][:3, :3], d["gt_pose"][:3, 3]
+    res = np.linalg.norm(d["src_pts"] @ R.T + t - d["tgt_pts"], axis=1)
+    assert (res[d["labels"] > 0] < 0.2).all() and abs(np.linalg.det(R) - 1) < 1e-5
+    assert len(np.unique(d["src_pts"], axis=0)) < 2048 * 0.8          # duplicate-heavy variant
+    assert np.array_equal(P.synthetic.make_pair(0, n=2048, dup_frac=0.3)["tgt_pts"], d["tgt_pts"])   # seeded
+
+
+def test_pair_sharding_two_ranks_gloo(tmp_path):
+    """bench.py's partition: contiguous slices of the pair batch per rank, no data-path collective;
+    throughput is aggregated with a MAX over ranks of the elapsed time."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "lo, hi = bench.shard_range(10, r, w)\n"
+        "t = torch.tensor([float(hi - lo)]); dist.all_reduce(t)\n"
+        "m = bench.max_over_ranks(1.0 + r, 'cpu')\n"
+        "assert t.item() == 10 and m == 2.0, (t, m)\n"
+        f"open(os.path.join({str(tmp_path)!r}, 'r%d.txt' % r), 'w').write('%d %d' % (lo, hi))\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert (tmp_path / "r0.txt").read_text() == "0 5" and (tmp_path / "r1.txt").read_text() == "5 10"

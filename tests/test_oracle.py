@@ -1,0 +1,138 @@
+"""CPU: the oracle (oracle/) pinned against the golden vectors produced by the reference's own
+classes (tests/golden/make_golden.py), and against the live reference when /root/reference exists."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import egnn_oracle as O
+from oracle import knn_oracle, ref_loader
+
+CASES = ["small_b2_n256", "dup_b2_n512", "full_b1_n2048", "kitti_b1_n1024", "noenc_b1_n512"]
+
+
+def load_case(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False, map_location="cpu")
+    ck = torch.load(os.path.join(golden_dir, g["meta"]["checkpoint"].split("/")[-1]), map_location="cpu", weights_only=True)
+    return g, ck["cross_attention_state_dict"]
+
+
+def edges_of(nbr):
+    return torch.stack([torch.stack(O.edges_from_nbr(n)) for n in nbr])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_eval_matches_reference_golden(golden_dir, name):
+    g, sd = load_case(golden_dir, name)
+    inp = g["inputs"]
+    out = O.forward_eval(sd, inp["src_feat"], inp["src_pts"], edges_of(g["nbr_src"]), inp["tgt_feat"], inp["tgt_pts"],
+                         edges_of(g["nbr_tgt"]), inp["labels"], inp["gt_pose"])
+    ref = g["eval_f32"]
+    # same torch ops in the same order as the reference -> essentially bit-identical
+    for i, key in ((4, "h_src"), (5, "x_src"), (6, "h_tgt"), (7, "x_tgt"), (0, "R"), (1, "t")):
+        assert torch.allclose(out[i], ref[key], rtol=0, atol=1e-6 * float(ref[key].abs().max())), key
+    assert out[2] is None
+    # the reference was called per pair (B=1); its loss is the per-pair loss
+    per_pair = torch.stack([O.forward_eval(sd, inp["src_feat"][b:b + 1], inp["src_pts"][b:b + 1], edges_of(g["nbr_src"][b:b + 1]),
+                                           inp["tgt_feat"][b:b + 1], inp["tgt_pts"][b:b + 1], edges_of(g["nbr_tgt"][b:b + 1]),
+                                           inp["labels"][b:b + 1], inp["gt_pose"][b:b + 1])[3] for b in range(inp["labels"].shape[0])])
+    assert torch.allclose(per_pair, ref["equi_loss"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["small_b2_n256", "dup_b2_n512", "noenc_b1_n512"])
+def test_oracle_train_matches_reference_golden(golden_dir, name):
+    g, sd = load_case(golden_dir, name)
+    inp = g["inputs"]
+    out = O.forward_train(sd, inp["src_feat"], inp["src_pts"], edges_of(g["nbr_src"]), inp["tgt_feat"], inp["tgt_pts"],
+                          edges_of(g["nbr_tgt"]), inp["labels"], inp["gt_pose"])
+    ref = g["train_f32"]
+    assert torch.allclose(out[4], ref["h_src"], rtol=0, atol=1e-6 * float(ref["h_src"].abs().max()))
+    assert torch.allclose(out[2], ref["slot2"].reshape(()), rtol=1e-6)
+    assert torch.allclose(out[3], ref["equi_loss"].reshape(()), rtol=1e-6)
+    assert torch.allclose(out[0], ref["R"], atol=1e-5) and torch.allclose(out[1], ref["t"], atol=1e-5)
+
+
+def test_oracle_per_layer_states(golden_dir):
+    g, sd = load_case(golden_dir, "small_b2_n256")
+    esd = {k[5:]: v for k, v in sd.items() if k.startswith("egnn.")}
+    inp = g["inputs"]
+    row, col = O.edges_from_nbr(g["nbr_src"][0])
+    ea = torch.ones(row.shape[0], 1)
+    h, x, layers = O.egnn_forward(esd, inp["src_feat"][0], inp["src_pts"][0], row, col, ea, return_layers=True)
+    ref = g["eval_f32"]["layers_src0"]
+    for i, (hl, xl) in enumerate(layers):
+        assert torch.allclose(hl, ref[i + 1][0], atol=1e-6 * float(ref[i + 1][0].abs().max()))
+        assert torch.allclose(xl, ref[i + 1][1], atol=1e-5)
+    m, _ = O.egcl_edge_messages(esd, "gcl_0.", torch.nn.functional.linear(inp["src_feat"][0], esd["embedding_in.weight"], esd["embedding_in.bias"]),
+                                inp["src_pts"][0], row, col, ea)
+    assert torch.allclose(m[: 64 * 16], g["eval_f32"]["layer0_messages"], atol=1e-5)
+
+
+def test_knn_c_oracle_matches_numpy_spec():
+    rng = np.random.default_rng(0)
+    for n, dup in ((64, 0), (300, 100), (1000, 0)):
+        x = (rng.random((n, 3)) * 3).astype(np.float32)
+        if dup:
+            x[-dup:] = x[:dup]
+        assert np.array_equal(knn_oracle.knn(x, 16), knn_oracle.knn_numpy(x, 16))
+    x = (rng.random((10, 3))).astype(np.float32)          # n < k: unfilled slots are -1
+    out = knn_oracle.knn(x, 16)
+    assert np.array_equal(out, knn_oracle.knn_numpy(x, 16)) and (out[:, 10:] == -1).all()
+    # nearest-first, self first on distinct points, ties -> lower index on exact duplicates
+    x = np.zeros((40, 3), np.float32)
+    assert np.array_equal(knn_oracle.knn(x, 16), np.tile(np.arange(16, dtype=np.int32), (40, 1)))
+
+
+def test_knn_golden_fixture_is_oracle_output(golden_dir):
+    g, _ = load_case(golden_dir, "dup_b2_n512")
+    assert np.array_equal(knn_oracle.knn(g["inputs"]["src_pts"].numpy(), 16), g["nbr_src"].numpy())
+
+
+def test_metrics_known_answers(golden_dir):
+    cases = torch.load(os.path.join(golden_dir, "metrics_kat.pt"), weights_only=False)
+    from se3_equi_graph_registration_b200 import metrics
+    for c in cases:
+        for impl in (O, metrics):
+            re, te = impl.calculate_pose_error(c["gt"], c["pred"])
+            rec, prec = impl.registration_recall(c["gt"], c["pred"], c["src"], c["tgt"])
+            assert np.isclose(re, c["re"], atol=1e-9) and np.isclose(te, c["te"], atol=1e-9)
+            assert np.isclose(rec, c["recall"]) and np.isclose(prec, c["precision"])
+
+
+def test_kabsch_oracle_recovers_known_pose_and_reflection_fix():
+    rng = np.random.default_rng(3)
+    from se3_equi_graph_registration_b200.synthetic import random_rotation
+    R = torch.tensor(random_rotation(rng), dtype=torch.float64)
+    t = torch.tensor(rng.random(3), dtype=torch.float64)
+    p = torch.tensor(rng.random((50, 3)), dtype=torch.float64)
+    q = p @ R.T + t
+    w = torch.full((50,), 1.0 / 50, dtype=torch.float64)
+    Rk, tk, _ = O.kabsch(p, q, w)
+    assert torch.allclose(Rk, R, atol=1e-5) and torch.allclose(tk, t, atol=1e-5)
+    # planar + mirrored target: det fix must still return a proper rotation
+    p[:, 2] = 0
+    q = p.clone(); q[:, 0] = -q[:, 0]
+    Rk, _, _ = O.kabsch(p, q, w)
+    assert abs(float(torch.det(Rk)) - 1.0) < 1e-6
+    Re, te, _ = O.kabsch(p[:0], q[:0], w[:0])
+    assert torch.equal(Re, torch.eye(3, dtype=torch.float64)) and float(te.abs().sum()) == 0.0
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="live reference only exists in the build container")
+def test_oracle_against_live_reference():
+    """Extra pin in the build container: run the reference classes right now on fresh inputs."""
+    from se3_equi_graph_registration_b200 import synthetic
+    data = synthetic.make_batch(99, 1, n=200)
+    nbr = torch.from_numpy(knn_oracle.knn(data["src_pts"].numpy(), 16))
+    nbt = torch.from_numpy(knn_oracle.knn(data["tgt_pts"].numpy(), 16))
+    es, et = edges_of(nbr), edges_of(nbt)
+    ns, egnn, head = ref_loader.build_reference_model("eval")
+    ea = torch.ones(1, es.shape[-1], 1)
+    with torch.no_grad():
+        ref = ref_loader.run_quiet(head, data["src_feat"], data["src_pts"], es, ea, data["tgt_feat"], data["tgt_pts"], et, ea,
+                                   data["corr"], data["labels"], data["gt_pose"])
+    out = O.forward_eval(head.state_dict(), data["src_feat"], data["src_pts"], es, data["tgt_feat"], data["tgt_pts"], et,
+                         data["labels"], data["gt_pose"])
+    for i in (0, 1, 4, 5, 6, 7):
+        assert torch.allclose(out[i], ref[i], rtol=0, atol=1e-6 * float(ref[i].abs().max()))
