@@ -136,7 +136,7 @@ def test_unsorted_segment_sum_matches_and_is_deterministic():
 # EGNN / E_GCL modules (a3-a11) vs the reference golden vectors
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_forward_eval_matches_reference_golden(golden_dir, name, impl):
     g, ck = load_case(golden_dir, name)
     model = P.build_model(ck, device=DEV, variant="eval")
