@@ -296,7 +296,7 @@ def eng_layer_time(eng, reps=20):
         _lib.check(lib.egspr_egcl_forward(p(eng.h[0]), p(eng.x4[0]), p(eng.P[0]), p(eng.Q[0]), p(eng.csr_ptr), p(eng.csr_row),
                                           p(eng.csr_col), p(eng.csr_eid), None, 1.0, G, eng.N * eng.k, eng.N,
                                           p(layers[0]), p(layers[1]), None, p(eng.h[1]), p(eng.x4[1]), None,
-                                          p(eng.P[1]), p(eng.Q[1]), int(eng.impl), ops._stream()), "egspr_egcl_forward")
+                                          p(eng.P[1]), p(eng.Q[1]), p(eng.agg_ws), int(eng.impl), ops._stream()), "egspr_egcl_forward")
         b.record()
         torch.cuda.synchronize()
         if r >= 3:

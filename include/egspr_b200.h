@@ -91,14 +91,17 @@ int egspr_node_embed(const float *feat, const float *x3, int64_t num_nodes, cons
  * the layer input).  edge_attr: optional [clouds*edges_per_cloud] per-edge scalar indexed through
  * csr_eid (NULL = constant edge_attr_const, the reference's ones, 3dm:387; a layer built with
  * edges_in_d=0 has a zero edge_attr column in its pack).
- * impl: 0 = fp32 CUDA-core path, 2 edges per thread; 1 = same, 1 edge per thread. */
+ * impl: 0 = auto (tensor-core path if agg_ws != NULL, else the fused CUDA-core kernel);
+ *       1 / 2 = fused fp32 CUDA-core kernel with 64 / 256 nodes per block;
+ *       3 = tensor-core path (tcgen05, 3xTF32 split: fp32-level accuracy) = edge kernel + node kernel,
+ *           needs agg_ws [num_nodes][32] floats of scratch. */
 int egspr_egcl_forward(const float *h, const float *x4, const float *P, const float *Q,
                        const int32_t *csr_ptr, const int32_t *csr_row, const int32_t *csr_col,
                        const int32_t *csr_eid, const float *edge_attr, float edge_attr_const,
                        int64_t num_nodes, int64_t edges_per_cloud, int n_per_cloud,
                        const float *layer_pack, const float *next_pack, const float *out_pack,
                        float *h_out, float *x4_out, float *x3_out, float *P_out, float *Q_out,
-                       int impl, void *stream);
+                       float *agg_ws, int impl, void *stream);
 
 /* ---- a15: weighted Kabsch / Procrustes block 3dm:726-758 (evl:786-818) --------------------------
  * One CTA per pair: centroids, H = sum w (p-cs)(q-ct)^T + 1e-6 I, 3x3 SVD (fp64 Jacobi), R = V U^T

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libegspr_b200.so")
-SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "head.cu"]
+SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_layer_tc.cu", "head.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -32,7 +32,7 @@ SIGNATURES = {
     "egspr_segment_sum": (_i, [_p, _i, _p, _p, _l, _p, _p]),
     "egspr_node_embed": (_i, [_p, _p, _l, _p, _p, _p, _p, _p, _p, _p]),
     "egspr_egcl_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _l, _l, _i, _p, _p, _p,
-                                _p, _p, _p, _p, _p, _i, _p]),
+                                _p, _p, _p, _p, _p, _p, _i, _p]),
     "egspr_kabsch": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "egspr_head_eval": (_i, [_p] * 11 + [_i, _i, _i] + [_p] * 6),
     "egspr_head_train": (_i, [_p] * 6 + [_i, _i] + [_p] * 7),
@@ -47,7 +47,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(_CSRC, "egspr_common.cuh"),
+    deps = sources() + [os.path.join(_CSRC, "egspr_common.cuh"), os.path.join(_CSRC, "egnn_layer.cuh"),
                         os.path.join(_HERE, "..", "include", "egspr_b200.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 

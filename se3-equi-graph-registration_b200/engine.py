@@ -48,6 +48,7 @@ class RegistrationEngine:
         self.h = [z(G, H), z(G, H)]; self.x4 = [z(G, 4), z(G, 4)]
         self.P = [z(G, H), z(G, H)]; self.Q = [z(G, H), z(G, H)]
         self.x_out = z(C, N, 3)
+        self.agg_ws = z(G, H)
         # outputs
         self.R = z(B, 3, 3); self.t = z(B, 3); self.Hm = z(B, 3, 3); self.w = z(B, N); self.loss_parts = z(B, 2)
         self.h_out = None
@@ -94,8 +95,9 @@ class RegistrationEngine:
                 p(self.csr_ptr), p(self.csr_row), p(self.csr_col), p(self.csr_eid), None, 1.0,
                 G, N * k, N, p(layers[i]), None if last else p(layers[i + 1]), p(pout) if last else None,
                 p(self.h[nxt]), p(self.x4[nxt]), p(self.x_out) if last else None,
-                None if last else p(self.P[nxt]), None if last else p(self.Q[nxt]), int(self.impl), st), "egspr_egcl_forward")
-            n_launch += 1
+                None if last else p(self.P[nxt]), None if last else p(self.Q[nxt]), p(self.agg_ws), int(self.impl), st),
+                "egspr_egcl_forward")
+            n_launch += 2 if self.impl in (0, 3) else 1
             cur = nxt
         self.h_out = self.h[cur].view(C, N, H)
         ho, xo = self.h_out, self.x_out

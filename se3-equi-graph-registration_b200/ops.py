@@ -132,6 +132,7 @@ def egnn_forward(feat, x, graph, layer_packs, embed_in_pack, embed_out_pack, edg
     pbuf = [torch.empty((G, H), dtype=torch.float32, device=dev) for _ in range(2)]
     qbuf = [torch.empty((G, H), dtype=torch.float32, device=dev) for _ in range(2)]
     x_out = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+    agg_ws = torch.empty((G, H), dtype=torch.float32, device=dev) if impl in (0, 3) else None
     layers = []
     with torch.cuda.device(dev):
         st = _stream()
@@ -151,7 +152,8 @@ def egnn_forward(feat, x, graph, layer_packs, embed_in_pack, embed_out_pack, edg
                 _ptr(layer_packs[i]), None if last else _ptr(layer_packs[i + 1]),
                 _ptr(embed_out_pack) if last else None,
                 _ptr(hbuf[nxt]), _ptr(xbuf[nxt]), _ptr(x3) if want_x3 else None,
-                None if last else _ptr(pbuf[nxt]), None if last else _ptr(qbuf[nxt]), int(impl), st), "egspr_egcl_forward")
+                None if last else _ptr(pbuf[nxt]), None if last else _ptr(qbuf[nxt]), _ptr(agg_ws), int(impl), st),
+                "egspr_egcl_forward")
             cur = nxt
             if return_layers and not last:
                 layers.append((hbuf[cur].view(C, N, H).clone(), x3))

@@ -136,7 +136,7 @@ def test_unsorted_segment_sum_matches_and_is_deterministic():
 # EGNN / E_GCL modules (a3-a11) vs the reference golden vectors
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_forward_eval_matches_reference_golden(golden_dir, name, impl):
     g, ck = load_case(golden_dir, name)
     model = P.build_model(ck, device=DEV, variant="eval")
@@ -209,6 +209,40 @@ def test_egnn_and_egcl_module_signatures(golden_dir, model):
     h1r, x1r, _ = O.egcl_forward(sd, "gcl_1.", hh, x_in, r2, c2, ea2)
     assert float((h1.cpu() - h1r).abs().max()) <= H_TOL * float(h1r.abs().max()) and float((x1.cpu() - x1r).abs().max()) <= X_TOL
     assert ea_out.shape == ea2.shape
+
+
+@pytest.mark.parametrize("impl", [1, 2, 3])
+def test_twin_points_stay_bit_identical(model, impl):
+    """Exact duplicate correspondences ("twins": same coordinates AND features, normal in the datasets,
+    datasets/ThreeDMatch.py:319,329) whose incoming-edge sets coincide must stay bit-identical through
+    every layer: the degenerate-frame rule (3dm:152-163) is discontinuous at x_i == x_j, so a
+    rounding-level split would change the messages by O(1).  Guaranteed by summing every node strictly
+    in ascending edge order (as scatter_add_ does) and by position-independent per-edge arithmetic."""
+    rng = np.random.default_rng(9)
+    n = 1000
+    x = (rng.random((n, 3)) * 3).astype(np.float32)
+    f = rng.standard_normal((n, 32)).astype(np.float32)
+    src = rng.integers(0, n // 2, 150); dst = rng.choice(np.arange(n // 2, n), 150, replace=False)
+    x[dst] = x[src]; f[dst] = f[src]
+    xt, ft = torch.from_numpy(x)[None].to(DEV), torch.from_numpy(f)[None].to(DEV)
+    nbr = ops.knn_build(xt, 16)
+    gr = ops.csr_from_nbr(nbr)
+    layers, pin, pout = model.egnn.packs()
+    h, xo = ops.egnn_forward(ft, xt, gr, layers, pin, pout, impl=impl)
+    row = nbr[0].cpu().long().reshape(-1); col = torch.arange(n).repeat_interleave(16)
+    insets = [set() for _ in range(n)]
+    for r, c in zip(row.tolist(), col.tolist()):
+        insets[r].add(c)
+    checked = 0
+    for s_, d_ in zip(src.tolist(), dst.tolist()):
+        if insets[s_] - {s_, d_} == insets[d_] - {s_, d_} and (s_ in insets[s_]) == (s_ in insets[d_]) and (d_ in insets[s_]) == (d_ in insets[d_]):
+            assert torch.equal(h[0, s_], h[0, d_]) and torch.equal(xo[0, s_], xo[0, d_])
+            checked += 1
+    assert checked > 20
+    sd = {k: v.cpu() for k, v in model.egnn.state_dict().items()}
+    href, xref = O.egnn_forward(sd, torch.from_numpy(f), torch.from_numpy(x), row, col, torch.ones(n * 16, 1))
+    assert float((h[0].cpu() - href).abs().max()) <= H_TOL * float(href.abs().max())
+    assert float((xo[0].cpu() - xref).abs().max()) <= X_TOL
 
 
 def test_forward_train_variant(golden_dir):

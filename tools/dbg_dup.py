@@ -9,7 +9,7 @@ g = torch.load(os.path.join(ROOT, "tests/golden/dup_b2_n512.pt"), weights_only=F
 model = P.build_model(os.path.join(ROOT, "tests/golden/checkpoint-3dmatch.pth"), device=dev)
 sd = {k: v.cpu() for k, v in model.egnn.state_dict().items()}
 inp = g["inputs"]
-for impl in (1, 2):
+for impl in (1, 3):
   for side in ("src", "tgt"):
     for b in range(2):
         nbr = g[f"nbr_{side}"][b:b+1]
