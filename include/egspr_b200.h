@@ -48,8 +48,12 @@ const char *egspr_error_string(int code);
 /* ---- a1: torch_cluster.knn_graph(x, k, loop=True) call sites 3dm:1005-1006, evl:1156-1157 ------
  * x [clouds][n][3] f32 -> nbr [clouds][n][k] i32: the k nearest points of the same cloud (self
  * included), ascending by (d2, index); d2 = fma(dz,dz,fma(dy,dy,dx*dx)) in fp32.  Slots that
- * cannot be filled (n < k) hold -1.  All clouds are processed by one launch. */
-int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t *nbr, void *stream);
+ * cannot be filled (n < k) hold -1.  All clouds are processed by one launch sequence.
+ * workspace (egspr_knn_workspace_bytes) selects the exact cell-grid search; workspace == NULL runs
+ * the brute-force scan.  Both return identical ids (the order (d2, index) is total). */
+size_t egspr_knn_workspace_bytes(int clouds, int n);
+int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t *nbr, void *workspace,
+                    size_t workspace_bytes, void *stream);
 
 /* ---- a2: get_edges_from_idx / get_edges_batch 3dm:372-403 -------------------------------------
  * nbr -> the reference's edge tensor edges[clouds][2][n*k] i64 (row = neighbour, col = centre,

@@ -24,7 +24,8 @@ _z = ctypes.c_size_t
 SIGNATURES = {
     "egspr_version": (_i, []),
     "egspr_error_string": (ctypes.c_char_p, [_i]),
-    "egspr_knn_build": (_i, [_p, _i, _i, _i, _p, _p]),
+    "egspr_knn_workspace_bytes": (_z, [_i, _i]),
+    "egspr_knn_build": (_i, [_p, _i, _i, _i, _p, _p, _z, _p]),
     "egspr_nbr_to_edges": (_i, [_p, _i, _i, _i, _p, _p]),
     "egspr_csr_workspace_bytes": (_z, [_l, _l]),
     "egspr_csr_from_nbr": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p, _p]),

@@ -66,6 +66,224 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_warp_select_kernel(
     if (active && lane < k) nbr[((size_t)cloud * n + qi) * k + lane] = bi;
 }
 
+// ================================================================================================
+// Cell-grid k-NN (exact): same result as the brute-force scan because the selection is defined by
+// the TOTAL order (d2, index) -- visiting order does not matter.
+//   build : one CTA per cloud: bounding box -> anisotropic cell grid (~4 points per cell, <= 4096
+//           cells) -> counting sort of the points by cell (x,y,z,index packed in a float4)
+//   query : one warp per query, in cell-sorted order (neighbouring warps touch neighbouring cells):
+//           scan the cubic shell of cells at Chebyshev radius L = 0,1,2,... around the query's cell
+//           (contiguous x-runs of cells = contiguous candidate ranges, one candidate per lane, the
+//           same ballot/shuffle insertion as above but with the lexicographic (d2, index) compare);
+//           stop when the k-th best distance is strictly inside the scanned block (margin test with
+//           1e-4 relative slack) or the block covers the whole grid.
+// ================================================================================================
+constexpr int GRID_MAXC = 4096;
+constexpr int GRID_BUILD_THREADS = 512;
+
+struct GridParams {        // per cloud, 16 floats
+    float mn[3];
+    float inv[3];          // 1 / cell size
+    float cs[3];           // cell size
+    int dims[3];
+    int pad[4];
+};
+
+__global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
+    const float *__restrict__ x, int n, float4 *__restrict__ sorted, int *__restrict__ cell_start,
+    GridParams *__restrict__ params) {
+    __shared__ int cnt[GRID_MAXC + 1];
+    __shared__ float red[6][GRID_BUILD_THREADS / 32];
+    __shared__ GridParams gp;
+    __shared__ int wtot[GRID_BUILD_THREADS / 32];
+    __shared__ int carry_s;
+    const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *xc = x + (size_t)cloud * n * 3;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = tid; i < n; i += GRID_BUILD_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = __ldg(xc + 3 * i + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    for (int i = tid; i <= GRID_MAXC; i += GRID_BUILD_THREADS) cnt[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        float mn[3], ext[3];
+        for (int a = 0; a < 3; ++a) {
+            float l = red[a][0], h = red[3 + a][0];
+            for (int w = 1; w < GRID_BUILD_THREADS / 32; ++w) { l = fminf(l, red[a][w]); h = fmaxf(h, red[3 + a][w]); }
+            mn[a] = l; ext[a] = h - l;
+        }
+        const float emax = fmaxf(fmaxf(ext[0], ext[1]), fmaxf(ext[2], 1e-30f));
+        // cells wanted: ~4 points per cell; degenerate (flat) axes get a single cell
+        float target = fmaxf(1.0f, (float)n * 0.25f);
+        if (target > (float)GRID_MAXC) target = (float)GRID_MAXC;
+        float e[3]; int live = 0; float vol = 1.0f;
+        for (int a = 0; a < 3; ++a) { e[a] = ext[a]; if (e[a] > 1e-4f * emax) { ++live; vol *= e[a]; } }
+        float c = live ? powf(vol / target, 1.0f / (float)live) : 1.0f;
+        int dims[3]; long long total = 1;
+        for (int a = 0; a < 3; ++a) {
+            int d = (e[a] > 1e-4f * emax) ? (int)(e[a] / c) + 1 : 1;
+            if (d > 64) d = 64;
+            if (d < 1) d = 1;
+            dims[a] = d; total *= d;
+        }
+        while (total > GRID_MAXC) {           // shrink the largest dimension until the grid fits
+            int am = 0;
+            for (int a = 1; a < 3; ++a) if (dims[a] > dims[am]) am = a;
+            total /= dims[am]; dims[am] -= 1; total *= dims[am];
+        }
+        for (int a = 0; a < 3; ++a) {
+            gp.mn[a] = mn[a]; gp.dims[a] = dims[a];
+            const float cs = (ext[a] > 0.f) ? ext[a] / (float)dims[a] : 1.0f;
+            gp.cs[a] = cs; gp.inv[a] = 1.0f / cs;
+        }
+        params[cloud] = gp;
+    }
+    __syncthreads();
+    const int nx = gp.dims[0], ny = gp.dims[1], nz = gp.dims[2];
+    const int ncell = nx * ny * nz;
+    auto cell_of = [&](float px, float py, float pz) {
+        int cx = min(nx - 1, max(0, (int)((px - gp.mn[0]) * gp.inv[0])));
+        int cy = min(ny - 1, max(0, (int)((py - gp.mn[1]) * gp.inv[1])));
+        int cz = min(nz - 1, max(0, (int)((pz - gp.mn[2]) * gp.inv[2])));
+        return (cz * ny + cy) * nx + cx;
+    };
+    for (int i = tid; i < n; i += GRID_BUILD_THREADS)
+        atomicAdd(&cnt[cell_of(__ldg(xc + 3 * i), __ldg(xc + 3 * i + 1), __ldg(xc + 3 * i + 2))], 1);
+    __syncthreads();
+    // exclusive scan of cnt[0..ncell) -> cell_start (global) and cursor (cnt reused)
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    int *cs_out = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    for (int base = 0; base < ncell; base += GRID_BUILD_THREADS) {
+        const int i = base + tid;
+        const int v = i < ncell ? cnt[i] : 0;
+        int sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+        if (lane == 31) wtot[warp] = sc;
+        __syncthreads();
+        if (warp == 0) {
+            int t = lane < GRID_BUILD_THREADS / 32 ? wtot[lane] : 0, u = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += w; }
+            if (lane < GRID_BUILD_THREADS / 32) wtot[lane] = u - t;
+        }
+        __syncthreads();
+        const int excl = carry_s + wtot[warp] + sc - v;
+        if (i < ncell) { cs_out[i] = excl; cnt[i] = excl; }
+        __syncthreads();
+        if (tid == GRID_BUILD_THREADS - 1) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) cs_out[ncell] = n;
+    float4 *so = sorted + (size_t)cloud * n;
+    for (int i = tid; i < n; i += GRID_BUILD_THREADS) {
+        const float px = __ldg(xc + 3 * i), py = __ldg(xc + 3 * i + 1), pz = __ldg(xc + 3 * i + 2);
+        const int pos = atomicAdd(&cnt[cell_of(px, py, pz)], 1);
+        so[pos] = make_float4(px, py, pz, __int_as_float(i));
+    }
+}
+
+constexpr int GQ_WARPS = 8;
+
+__global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_kernel(
+    const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
+    int n, int k, int32_t *__restrict__ nbr) {
+    const int cloud = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qs = blockIdx.x * GQ_WARPS + warp;          // query = qs-th point in cell-sorted order
+    if (qs >= n) return;
+    const float4 *so = sorted + (size_t)cloud * n;
+    const int *cs = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    const GridParams gp = params[cloud];
+    const float4 q = __ldg(so + qs);
+    const int qi = __float_as_int(q.w);
+    const int nx = gp.dims[0], ny = gp.dims[1], nz = gp.dims[2];
+    const int cx = min(nx - 1, max(0, (int)((q.x - gp.mn[0]) * gp.inv[0])));
+    const int cy = min(ny - 1, max(0, (int)((q.y - gp.mn[1]) * gp.inv[1])));
+    const int cz = min(nz - 1, max(0, (int)((q.z - gp.mn[2]) * gp.inv[2])));
+    float bd = 1e10f;
+    int bi = -1;
+    float thr_d = 1e10f;
+    int thr_i = -1;
+    const int Lmax = max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz));
+    for (int L = 0; L <= Lmax; ++L) {
+        // rows (dz, dy) of the shell at Chebyshev radius L
+        for (int dz = -L; dz <= L; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= nz) continue;
+            for (int dy = -L; dy <= L; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= ny) continue;
+                const bool outer = (dz == -L || dz == L || dy == -L || dy == L);
+                // outer rows: the full x-run [cx-L, cx+L]; inner rows: only the two end cells
+                const int nruns = (outer || L == 0) ? 1 : 2;
+                for (int run = 0; run < nruns; ++run) {
+                    int x0, x1;
+                    if (nruns == 1) { x0 = max(cx - L, 0); x1 = min(cx + L, nx - 1); }
+                    else { x0 = x1 = (run == 0) ? cx - L : cx + L; if (x0 < 0 || x0 >= nx) continue; }
+                    const int rowbase = (z * ny + y) * nx;
+                    const int s = __ldg(cs + rowbase + x0), e = __ldg(cs + rowbase + x1 + 1);
+                    for (int j0 = s; j0 < e; j0 += 32) {
+                        const int j = j0 + lane;
+                        float d = 3e38f;
+                        int idx = 0x7fffffff;
+                        if (j < e) {
+                            const float4 c = __ldg(so + j);
+                            const float dx = c.x - q.x, dy2 = c.y - q.y, dz2 = c.z - q.z;
+                            d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
+                            idx = __float_as_int(c.w);
+                        }
+                        unsigned m = __ballot_sync(0xffffffffu, d < thr_d || (d == thr_d && idx < thr_i));
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float dd = __shfl_sync(0xffffffffu, d, src);
+                            const int jj = __shfl_sync(0xffffffffu, idx, src);
+                            if (dd < thr_d || (dd == thr_d && jj < thr_i)) {
+                                const bool before = lane < k && (bd < dd || (bd == dd && bi < jj) );
+                                // empty slots are (1e10, -1): never "before" a real candidate (dd < 1e10)
+                                const int pos = __popc(__ballot_sync(0xffffffffu, before && bi >= 0));
+                                const float ubd = __shfl_up_sync(0xffffffffu, bd, 1);
+                                const int ubi = __shfl_up_sync(0xffffffffu, bi, 1);
+                                if (lane > pos) { bd = ubd; bi = ubi; }
+                                if (lane == pos) { bd = dd; bi = jj; }
+                                thr_d = __shfl_sync(0xffffffffu, bd, k - 1);
+                                thr_i = __shfl_sync(0xffffffffu, bi, k - 1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // done when the k-th best is strictly inside the scanned block (sides on the domain boundary
+        // have nothing beyond them)
+        float margin = 3e38f;
+        if (cx - L > 0) margin = fminf(margin, q.x - (gp.mn[0] + (float)(cx - L) * gp.cs[0]));
+        if (cx + L < nx - 1) margin = fminf(margin, (gp.mn[0] + (float)(cx + L + 1) * gp.cs[0]) - q.x);
+        if (cy - L > 0) margin = fminf(margin, q.y - (gp.mn[1] + (float)(cy - L) * gp.cs[1]));
+        if (cy + L < ny - 1) margin = fminf(margin, (gp.mn[1] + (float)(cy + L + 1) * gp.cs[1]) - q.y);
+        if (cz - L > 0) margin = fminf(margin, q.z - (gp.mn[2] + (float)(cz - L) * gp.cs[2]));
+        if (cz + L < nz - 1) margin = fminf(margin, (gp.mn[2] + (float)(cz + L + 1) * gp.cs[2]) - q.z);
+        if (margin > 1e37f) break;                              // block covers the whole grid
+        if (margin > 0.f) {
+            const float ms = margin * 0.9999f;
+            if (thr_i >= 0 && thr_d < ms * ms) break;
+        }
+    }
+    if (lane < k) nbr[((size_t)cloud * n + qi) * k + lane] = bi;
+}
+
 __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int k,
                                     int64_t *__restrict__ edges, int64_t per_cloud) {
     // edges[cloud][0][e] = nbr (row, neighbour); edges[cloud][1][e] = e / k (col, centre)
@@ -79,13 +297,32 @@ __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int 
 
 }  // namespace egspr
 
-extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t *nbr, void *stream) {
+extern "C" size_t egspr_knn_workspace_bytes(int clouds, int n) {
+    using namespace egspr;
+    return (size_t)clouds * ((size_t)n * sizeof(float4) + (GRID_MAXC + 1) * sizeof(int) + sizeof(GridParams)) + 256;
+}
+
+extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t *nbr, void *workspace,
+                               size_t workspace_bytes, void *stream) {
     using namespace egspr;
     if (!x || !nbr || clouds <= 0 || n <= 0) return EGSPR_E_INVALID;
     if (k <= 0 || k > EGSPR_MAX_K) return EGSPR_E_UNSUPPORTED;
     if (clouds > 65535) return EGSPR_E_UNSUPPORTED;
-    dim3 grid((n + KNN_WARPS - 1) / KNN_WARPS, clouds);
-    knn_warp_select_kernel<<<grid, KNN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, n, k, nbr);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!workspace) {                       // no scratch: brute-force scan
+        dim3 grid((n + KNN_WARPS - 1) / KNN_WARPS, clouds);
+        knn_warp_select_kernel<<<grid, KNN_WARPS * 32, 0, st>>>(x, n, k, nbr);
+        EGSPR_CHECK_LAUNCH();
+        return EGSPR_OK;
+    }
+    if (workspace_bytes < egspr_knn_workspace_bytes(clouds, n)) return EGSPR_E_WORKSPACE;
+    uint8_t *w = (uint8_t *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float4 *sorted = (float4 *)w;
+    int *cell_start = (int *)(w + (size_t)clouds * n * sizeof(float4));
+    GridParams *params = (GridParams *)(cell_start + (size_t)clouds * (GRID_MAXC + 1));
+    knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, 0, st>>>(x, n, sorted, cell_start, params);
+    dim3 grid((n + GQ_WARPS - 1) / GQ_WARPS, clouds);
+    knn_grid_query_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }

@@ -40,6 +40,9 @@ class RegistrationEngine:
         self.gt_pose = torch.eye(4, dtype=f32, device=dev).repeat(B, 1, 1).contiguous()
         # graph
         self.nbr = z(C, N, self.k, dt=i32)
+        self.knn_ws_bytes = _lib.lib().egspr_knn_workspace_bytes(C, N)
+        self.knn_ws = torch.empty(self.knn_ws_bytes, dtype=torch.uint8, device=dev)
+        self.knn_brute_force = False
         self.csr_ptr = z(G + 1, dt=i32); self.csr_row = z(E, dt=i32); self.csr_col = z(E, dt=i32); self.csr_eid = z(E, dt=i32)
         self.ws_bytes = _lib.lib().egspr_csr_workspace_bytes(G, E)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
@@ -79,7 +82,11 @@ class RegistrationEngine:
         head = self.model._pack_head.get()
         st = ops._stream()
         n_launch = 0
-        _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), st), "egspr_knn_build"); n_launch += 1
+        if self.knn_brute_force:
+            _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), None, 0, st), "egspr_knn_build"); n_launch += 1
+        else:
+            _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), p(self.knn_ws), self.knn_ws_bytes, st),
+                       "egspr_knn_build"); n_launch += 2
         _lib.check(lib.egspr_csr_from_nbr(p(self.nbr), C, N, k, p(self.csr_ptr), p(self.csr_row), p(self.csr_col),
                                           p(self.csr_eid), p(self.ws), self.ws_bytes, p(self.err), st), "egspr_csr_from_nbr")
         n_launch += 4

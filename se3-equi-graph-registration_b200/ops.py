@@ -29,8 +29,9 @@ def _req(t, name, dtype, ndim=None):
     return t.contiguous()
 
 
-def knn_build(x, k):
-    """x [C,N,3] f32 -> nbr [C,N,k] i32 (nearest first, ties -> lower index, self included)."""
+def knn_build(x, k, brute_force=False):
+    """x [C,N,3] f32 -> nbr [C,N,k] i32 (nearest first, ties -> lower index, self included).
+    brute_force=True runs the O(N^2) scan instead of the cell-grid search (identical output)."""
     x = _req(x, "x", torch.float32, 3)
     C, N, D = x.shape
     if D != 3:
@@ -38,8 +39,13 @@ def knn_build(x, k):
     nbr = torch.empty((C, N, k), dtype=torch.int32, device=x.device)
     if C * N == 0:
         return nbr
+    lib = _lib.lib()
+    ws, ws_bytes = None, 0
+    if not brute_force:
+        ws_bytes = lib.egspr_knn_workspace_bytes(C, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().egspr_knn_build(_ptr(x), C, N, k, _ptr(nbr), _stream()), "egspr_knn_build")
+        _lib.check(lib.egspr_knn_build(_ptr(x), C, N, k, _ptr(nbr), _ptr(ws), ws_bytes, _stream()), "egspr_knn_build")
     return nbr
 
 

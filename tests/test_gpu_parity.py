@@ -51,7 +51,8 @@ def edges_of(nbr):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,k,kind", [(16, 16, "uniform"), (17, 16, "uniform"), (33, 8, "uniform"), (257, 16, "dup"),
                                       (2048, 16, "uniform"), (2048, 16, "dup"), (2048, 32, "uniform"), (4096, 16, "kitti"),
-                                      (8192, 16, "kitti"), (5, 16, "uniform"), (3000, 16, "allsame")])
+                                      (8192, 16, "kitti"), (5, 16, "uniform"), (3000, 16, "allsame"), (2048, 16, "planar"),
+                                      (2048, 16, "clustered"), (20000, 16, "uniform"), (1, 1, "uniform")])
 def test_knn_bit_exact(n, k, kind):
     rng = np.random.default_rng(n * 7 + k)
     C = 3
@@ -65,9 +66,16 @@ def test_knn_bit_exact(n, k, kind):
             x[c, rng.choice(n, n // 3, replace=False)] = x[c, idx[c]]
     if kind == "allsame":
         x[:] = 1.25
-    got = ops.knn_build(torch.from_numpy(x).to(DEV), k).cpu().numpy()
+    if kind == "planar":
+        x[:, :, 2] = 0.75                     # flat cloud: one degenerate grid axis
+    if kind == "clustered":                   # a few tight clusters far apart + exact duplicates across clusters
+        centres = rng.random((C, 8, 3)) * 50
+        x = (centres[:, rng.integers(0, 8, n)][np.arange(C)[:, None], np.arange(n)[None] % 1, :] if False else
+             np.stack([centres[c][rng.integers(0, 8, n)] + rng.standard_normal((n, 3)) * 0.01 for c in range(C)])).astype(np.float32)
     ref = knn_oracle.knn(x, k)
-    assert np.array_equal(got, ref)
+    for brute in (False, True):              # cell-grid search and brute-force scan: identical ids
+        got = ops.knn_build(torch.from_numpy(x).to(DEV), k, brute_force=brute).cpu().numpy()
+        assert np.array_equal(got, ref), ("brute" if brute else "grid")
     if n >= k and kind == "uniform":
         assert (got[:, :, 0] == np.arange(n)[None]).all()       # self is the nearest (loop=True)
 

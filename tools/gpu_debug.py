@@ -133,7 +133,8 @@ def main():
         for _ in range(n): fn()
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
-    print("knn      ms", timeit(lambda: ops.knn_build(eng.x, K)))
+    print("knn grid ms", timeit(lambda: ops.knn_build(eng.x, K)))
+    print("knn brute ms", timeit(lambda: ops.knn_build(eng.x, K, brute_force=True)))
     print("csr      ms", timeit(lambda: ops.csr_from_nbr(eng.nbr)))
     layers, pin, pout = model.egnn.packs()
     gr = ops.csr_from_nbr(eng.nbr)
