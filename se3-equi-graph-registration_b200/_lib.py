@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libegspr_b200.so")
-SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_layer_tc.cu", "head.cu"]
+SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_layer_tc.cu", "egnn_edge_mma.cu", "head.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -48,7 +48,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(_CSRC, "egspr_common.cuh"), os.path.join(_CSRC, "egnn_layer.cuh"),
+    deps = sources() + [os.path.join(_CSRC, "egspr_common.cuh"), os.path.join(_CSRC, "egnn_layer.cuh"), os.path.join(_CSRC, "tcgen05.cuh"),
                         os.path.join(_HERE, "..", "include", "egspr_b200.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 

@@ -168,6 +168,7 @@ static int launch_layer(const LayerArgs &a, cudaStream_t st) {
 }
 
 int launch_layer_tc(const LayerArgs &a, float *agg_ws, cudaStream_t st);   // egnn_layer_tc.cu
+int launch_layer_mma(const LayerArgs &a, float *agg_ws, cudaStream_t st);  // egnn_edge_mma.cu
 
 }  // namespace egspr
 
@@ -203,13 +204,16 @@ extern "C" int egspr_egcl_forward(const float *h, const float *x4, const float *
     const bool big = num_nodes >= (int64_t)256 * 2 * sm_count();
     switch (impl) {
         case 0:
-            if (agg_ws) return launch_layer_tc(a, agg_ws, (cudaStream_t)stream);
+            if (agg_ws) return launch_layer_mma(a, agg_ws, (cudaStream_t)stream);
             return big ? launch_layer<256>(a, (cudaStream_t)stream) : launch_layer<64>(a, (cudaStream_t)stream);
         case 1: return launch_layer<64>(a, (cudaStream_t)stream);
         case 2: return launch_layer<256>(a, (cudaStream_t)stream);
         case 3:
             if (!agg_ws) return EGSPR_E_WORKSPACE;
             return launch_layer_tc(a, agg_ws, (cudaStream_t)stream);
+        case 4:
+            if (!agg_ws) return EGSPR_E_WORKSPACE;
+            return launch_layer_mma(a, agg_ws, (cudaStream_t)stream);
         default: return EGSPR_E_UNSUPPORTED;
     }
 }

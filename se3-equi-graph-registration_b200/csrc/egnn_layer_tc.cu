@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "egnn_layer.cuh"
+#include "tcgen05.cuh"
 
 namespace egspr {
 
@@ -36,87 +37,10 @@ constexpr int TS_SACC = TS_DXS + T_TILE * 16, TS_SPTR = TS_SACC + T_NB * L_ROW *
 constexpr int TS_MBAR = ((TS_SPTR + (T_NB + 4) * 4 + 7) / 8) * 8, TS_TMEM = TS_MBAR + 8, TS_END = TS_TMEM + 8;
 constexpr size_t T_SMEM_BYTES = TS_END + 1024;   // + slack for the manual 1024-byte alignment
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ---- PTX wrappers (sm_100a) --------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // bounded spin: a descriptor / protocol bug must trap, not hang the GPU
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes = 32 tf32, 8-row groups
-// 1024 bytes apart).  Field layout as in CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);          // start address            bits [0,14)
-    d |= (uint64_t)1 << 16;                                // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset       bits [32,46)
-    d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B
-    return d;
-}
-// instruction descriptor: D=f32, A=B=tf32, both K-major, N=32, M=128 (InstrDescriptor bit layout)
-constexpr uint32_t T_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-
-// byte offset of element (row, k) inside a 128B-swizzled K-major tile
-__device__ __forceinline__ int sw128_off(int row, int k) { return row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2)); }
-
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+using namespace tc;
+constexpr uint32_t T_IDESC = IDESC_TF32_M128_N32;
+__device__ __forceinline__ void tc_fence_before() { fence_before_sync(); }
+__device__ __forceinline__ void tc_fence_after() { fence_after_sync(); }
 
 __global__ void __launch_bounds__(T_THREADS, 3) egcl_edge_tc_kernel(const LayerArgs a, float *__restrict__ agg_out) {
     extern __shared__ uint8_t smem_raw[];
@@ -285,6 +209,19 @@ __global__ void __launch_bounds__(N_THREADS) egcl_node_kernel(const LayerArgs a,
         }
         node_update(a, g, hrow, arow, sw);
     }
+}
+
+static int g_node_ctas = 0;
+void launch_node_kernel(const LayerArgs &a, const float *agg, cudaStream_t st) {
+    if (g_node_ctas == 0) {
+        int n = 1;
+        cudaFuncSetAttribute(egcl_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)N_SMEM_BYTES);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, egcl_node_kernel, N_THREADS, N_SMEM_BYTES) != cudaSuccess || n < 1) n = 1;
+        g_node_ctas = n;
+    }
+    int64_t ngrid = (a.num_nodes + N_THREADS - 1) / N_THREADS;
+    if (ngrid > (int64_t)sm_count() * g_node_ctas) ngrid = (int64_t)sm_count() * g_node_ctas;
+    egcl_node_kernel<<<(unsigned)ngrid, N_THREADS, N_SMEM_BYTES, st>>>(a, agg);
 }
 
 int launch_layer_tc(const LayerArgs &a, float *agg_ws, cudaStream_t st) {
