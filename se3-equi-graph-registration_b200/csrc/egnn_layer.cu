@@ -169,6 +169,7 @@ static int launch_layer(const LayerArgs &a, cudaStream_t st) {
 
 int launch_layer_tc(const LayerArgs &a, float *agg_ws, cudaStream_t st);   // egnn_layer_tc.cu
 int launch_layer_mma(const LayerArgs &a, float *agg_ws, cudaStream_t st);  // egnn_edge_mma.cu
+int launch_layer_ts(const LayerArgs &a, float *agg_ws, cudaStream_t st);   // egnn_edge_ts.cu
 
 }  // namespace egspr
 
@@ -214,6 +215,9 @@ extern "C" int egspr_egcl_forward(const float *h, const float *x4, const float *
         case 4:
             if (!agg_ws) return EGSPR_E_WORKSPACE;
             return launch_layer_mma(a, agg_ws, (cudaStream_t)stream);
+        case 5:
+            if (!agg_ws) return EGSPR_E_WORKSPACE;
+            return launch_layer_ts(a, agg_ws, (cudaStream_t)stream);
         default: return EGSPR_E_UNSUPPORTED;
     }
 }

@@ -144,7 +144,7 @@ def test_unsorted_segment_sum_matches_and_is_deterministic():
 # EGNN / E_GCL modules (a3-a11) vs the reference golden vectors
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4, 5])
 def test_forward_eval_matches_reference_golden(golden_dir, name, impl):
     g, ck = load_case(golden_dir, name)
     model = P.build_model(ck, device=DEV, variant="eval")
@@ -219,7 +219,7 @@ def test_egnn_and_egcl_module_signatures(golden_dir, model):
     assert ea_out.shape == ea2.shape
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3, 4])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5])
 def test_twin_points_stay_bit_identical(model, impl):
     """Exact duplicate correspondences ("twins": same coordinates AND features, normal in the datasets,
     datasets/ThreeDMatch.py:319,329) whose incoming-edge sets coincide must stay bit-identical through
