@@ -40,14 +40,26 @@ constexpr int VS_W = 0;                               // X1 | W2hi | W2lo | W3hi
 constexpr int VS_PAR = VS_W + 5 * 4096;               // b2, ln gamma, ln beta, bc1, wc2 (32 floats each)
 constexpr int VS_GRP = VS_PAR + 5 * 128;
 constexpr int VG_MT = 0;                              // float[128][36]  messages of the tile
-constexpr int VG_DXS = VG_MT + 128 * V_MROW * 4;      // float4[128]     coord_diff * s of the tile
-constexpr int VG_CARRY = VG_DXS + 128 * 16;           // float[2][36]    running sums of a row that spans tiles
-constexpr int VG_RLAST = VG_CARRY + 2 * 36 * 4;       // int             aggregation row of the tile's last edge
+constexpr int V_SPTR = 256;           // csr_ptr entries of a tile's rows staged in shared memory
+constexpr int VG_DXS = VG_MT + 128 * V_MROW * 4;      // float4[2][128]  coord_diff * s of the tile (by tile parity)
+constexpr int VG_CARRY = VG_DXS + 2 * 128 * 16;       // float[2][36]    running sums of a row that spans tiles
+constexpr int VG_SPTR = VG_CARRY + 2 * 36 * 4;        // int[2][V_SPTR]  csr_ptr[nstart ...] of the tile (by tile parity)
+constexpr int VG_RLAST = VG_SPTR + 2 * V_SPTR * 4;    // int             aggregation row of the tile's last edge
 constexpr int VG_MBAR = VG_RLAST + 8;
 constexpr int VG_SIZE = ((VG_MBAR + 8 + 127) / 128) * 128;
 constexpr int VS_TMEM = VS_GRP + V_GROUPS * VG_SIZE;
 constexpr int VS_END = VS_TMEM + 16;
 constexpr size_t V_SMEM_BYTES = VS_END + 1024;        // + slack for the manual 1024-byte alignment
+
+#ifdef EGSPR_TS_TIMING
+__device__ long long g_ts_dbg[4 * 64 * 12];
+#define TS_MARK(slot)                                                                                     \
+    do {                                                                                                  \
+        if (blockIdx.x == 7 && lane == 0 && tile_no < 64) g_ts_dbg[(hw * 64 + tile_no) * 12 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define TS_MARK(slot)
+#endif
 
 __device__ __forceinline__ float silu_fast(float v) {
     // v * sigmoid(v) = v * rcp(1 + 2^(-v log2 e)); MUFU.EX2 + MUFU.RCP, no range fix-ups
@@ -87,8 +99,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     const float *slng = sb2 + 32, *slnb = sb2 + 64, *sbc1 = sb2 + 96, *swc2 = sb2 + 128;
     uint8_t *gb = base + VS_GRP + grp * VG_SIZE;
     float *mt = reinterpret_cast<float *>(gb + VG_MT);
-    float4 *dxs = reinterpret_cast<float4 *>(gb + VG_DXS);
+    float4 *dxs2 = reinterpret_cast<float4 *>(gb + VG_DXS);
     float *carry = reinterpret_cast<float *>(gb + VG_CARRY);
+    int *sptr2 = reinterpret_cast<int *>(gb + VG_SPTR);
     int *s_rlast = reinterpret_cast<int *>(gb + VG_RLAST);
     const uint32_t mbar = smem_u32(gb + VG_MBAR);
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(base + VS_TMEM);
@@ -146,19 +159,87 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     const int nA = (int)(G * gi / NG), nB = (int)(G * (gi + 1) / NG);
     const int pbeg = __ldg(a.csr_ptr + nA), pend = __ldg(a.csr_ptr + nB);
     int nstart = nA;                 // first row whose sums have not been written out yet
-    int par = 0;                     // carry buffer read by this tile (the other one is written)
+    int par = 0;                     // tile parity: selects the dxs / sptr / carry buffers
+    // csr_ptr[n] for a row of the tile whose first staged row is `nbase` (rows beyond the staged window: global)
+    auto ptr_at = [&](const int *sp, int nbase, int n) -> int {
+        const int i = n - nbase;
+        return (i < V_SPTR) ? sp[i] : __ldg(a.csr_ptr + n);
+    };
+    // coordinate segment sums of one finished tile: thread (slot = ht/4, component = ht%4) per row
+    auto coord_pass = [&](int tpar, int tp0, int tend_, int nfirst, int nlast, float x_pre) {
+        const int comp = ht & 3;
+        bool first = true;
+        const float *dx_t = reinterpret_cast<const float *>(dxs2 + tpar * 128);
+        const int *sp = sptr2 + tpar * V_SPTR;
+        for (int n = nfirst + (ht >> 2); n <= nlast; n += 32) {
+            const float x_old = first ? x_pre : ((comp < 3) ? __ldg(a.x4 + (int64_t)n * 4 + comp) : 0.f);
+            first = false;
+            const int b0 = ptr_at(sp, nfirst, n), b1 = ptr_at(sp, nfirst, n + 1);
+            const int lo = max(b0, tp0) - tp0, hi = min(b1, tend_) - tp0;
+            float s1 = (b0 < tp0) ? carry[tpar * 36 + 32 + comp] : 0.f;
+            int q = lo;
+            for (; q + 4 <= hi; q += 4) {
+                const float d0 = dx_t[4 * q + comp], d1 = dx_t[4 * q + 4 + comp], d2 = dx_t[4 * q + 8 + comp], d3 = dx_t[4 * q + 12 + comp];
+                s1 += d0; s1 += d1; s1 += d2; s1 += d3;
+            }
+            for (; q < hi; ++q) s1 += dx_t[4 * q + comp];
+            if (b1 <= tend_) {
+                const float xv = (comp < 3) ? x_old + s1 : 0.f;                                   // coord + agg  :267
+                a.x4_out[(int64_t)n * 4 + comp] = xv;
+                if (a.x3_out && comp < 3) a.x3_out[(int64_t)n * 3 + comp] = xv;
+            } else {
+                carry[(tpar ^ 1) * 36 + 32 + comp] = s1;
+            }
+        }
+    };
+    int prev_p0 = 0, prev_tend = 0, prev_nstart = 0, prev_rlast = -1;     // the tile whose coordinate pass is pending
 
+    int rn = 0, cn = 0;              // endpoints of this thread's edge in the NEXT tile (loaded one tile ahead)
+    float xrn0 = 0.f, xrn1 = 0.f, xrn2 = 0.f, xcn0 = 0.f, xcn1 = 0.f, xcn2 = 0.f;   // ... and their coordinates
+    if (pbeg < pend) {
+        const int p = min(pbeg + ht, pend - 1);
+        rn = __ldg(a.csr_row + p); cn = __ldg(a.csr_col + p);
+        const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
+        xrn0 = t0.x; xrn1 = t0.y; xrn2 = t0.z; xcn0 = t1.x; xcn1 = t1.y; xcn2 = t1.z;
+    }
+#ifdef EGSPR_TS_TIMING
+    int tile_no = -1;
+#endif
     for (int p0 = pbeg; p0 < pend; p0 += 128, par ^= 1) {
+#ifdef EGSPR_TS_TIMING
+        ++tile_no;
+        if (grp != 1) tile_no = 1000;
+#endif
+        TS_MARK(0);
         const int tend = min(p0 + 128, pend);
         int p = p0 + ht;
         if (p >= pend) p = pend - 1;               // idle slot: recompute the last edge, never reduced
-        const int r = __ldg(a.csr_row + p), c = __ldg(a.csr_col + p);
-        if (ht == tend - 1 - p0) *s_rlast = r;
+        const int r = rn, c = cn;
+        const float3 xr = make_float3(xrn0, xrn1, xrn2), xc = make_float3(xcn0, xcn1, xcn2);
+        {
+            const int pn = min(p + 128, pend - 1);
+            rn = __ldg(a.csr_row + pn); cn = __ldg(a.csr_col + pn);
+        }
+        // old coordinate of the row this thread finishes in the pending coordinate pass (previous tile)
+        float x_pre = 0.f;
+        {
+            const int n = prev_nstart + (ht >> 2);
+            if (n <= prev_rlast && (ht & 3) < 3) x_pre = __ldg(a.x4 + (int64_t)n * 4 + (ht & 3));
+        }
+        // csr_ptr window of this tile's rows (staged into shared memory after the first barrier)
+        const int pt0 = __ldg(a.csr_ptr + min((int64_t)nstart + ht, G)), pt1 = __ldg(a.csr_ptr + min((int64_t)nstart + 128 + ht, G));
+        // first edge Linear, node halves (bias in Q): issued now, consumed after the stage-1 MMA
+        float4 pv[8], qv[8];
+        {
+            const float *Pr = a.P + (int64_t)r * H, *Qc = a.Q + (int64_t)c * H;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { pv[i] = ldg4(Pr + 4 * i); qv[i] = ldg4(Qc + 4 * i); }
+        }
+        if (ht == tend - 1 - p0) s_rlast[0] = r;
         float dx, dy, dz;
         // ---------------- stage 1 operand: geometry (:271-278, :128-181) ----------------
         {
             float geo[16];
-            const float4 xr = ldg4(a.x4 + (int64_t)r * 4), xc = ldg4(a.x4 + (int64_t)c * 4);
             float ea = a.edge_attr_const;
             if (a.edge_attr) {
                 const int64_t cloud = r / a.n_per_cloud;
@@ -192,7 +273,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         }
         tmem_wait_st();
         fence_before_sync();
+        TS_MARK(1);
         bar_sync(bar_id, 128);
+        TS_MARK(2);
         if (ht == 0) {
             fence_after_sync();
             umma_tf32_ts(tD, tAhi + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
@@ -203,43 +286,50 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             umma_tf32_ts(tD, tAhi + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
             umma_commit(mbar);
         }
+        // stage csr_ptr[nstart ...] of this tile's rows for the segment sums (visible after barriers 2, 3)
+        const int rlast = s_rlast[0];
+        int *sp = sptr2 + par * V_SPTR;
+        sp[ht] = pt0; sp[ht + 128] = pt1;
         float v[32];
-        {   // P[row] + Q[col] while the tensor core works  (first edge Linear, node halves; bias in Q)
-            const float *Pr = a.P + (int64_t)r * H, *Qc = a.Q + (int64_t)c * H;
-            float pq[32];
+        TS_MARK(3);
+        mbar_wait(mbar, phase); phase ^= 1;
+        TS_MARK(4);
+        fence_after_sync();
+        tmem_ld32(tmem_w, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 pv = ldg4(Pr + 4 * i), qv = ldg4(Qc + 4 * i);
-                pq[4 * i] = pv.x + qv.x; pq[4 * i + 1] = pv.y + qv.y; pq[4 * i + 2] = pv.z + qv.z; pq[4 * i + 3] = pv.w + qv.w;
-            }
-            mbar_wait(mbar, phase); phase ^= 1;
-            fence_after_sync();
-            tmem_ld32(tmem_w, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i] + pq[i]);                 // :203-206 act
+        for (int i = 0; i < 8; ++i) {   // + P[row] + Q[col], SiLU  (:203-206)
+            v[4 * i] = silu_fast(v[4 * i] + (pv[i].x + qv[i].x)); v[4 * i + 1] = silu_fast(v[4 * i + 1] + (pv[i].y + qv[i].y));
+            v[4 * i + 2] = silu_fast(v[4 * i + 2] + (pv[i].z + qv[i].z)); v[4 * i + 3] = silu_fast(v[4 * i + 3] + (pv[i].w + qv[i].w));
         }
         // ---------------- stage 2: per-head second Linear (block-diagonal) ----------------
         store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
         tmem_wait_st();
         fence_before_sync();
+        TS_MARK(5);
         bar_sync(bar_id, 128);
+        TS_MARK(6);
         if (ht == 0) {
             fence_after_sync();
             issue_3xtf32_ts(tD, tAhi, tAlo, dW2hi, dW2lo);
             umma_commit(mbar);
         }
+        {   // the next tile's endpoint coordinates travel while stages 2 and 3 run
+            const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
+            xrn0 = t0.x; xrn1 = t0.y; xrn2 = t0.z; xcn0 = t1.x; xcn1 = t1.y; xcn2 = t1.z;
+        }
         mbar_wait(mbar, phase); phase ^= 1;
+        TS_MARK(7);
         fence_after_sync();
         tmem_ld32(tmem_w, v);
-        {   // + b2, LayerNorm(32), eps 1e-5, biased variance (:209,:249)
-            float mean = 0.f;
+        {   // + b2, LayerNorm(32), eps 1e-5, biased variance (:209,:249); 4 partial sums for ILP
+            float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] += sb2[j]; mean += v[j]; }
-            mean *= (1.0f / 32.0f);
-            float var = 0.f;
+            for (int j = 0; j < 32; ++j) { v[j] += sb2[j]; m4[j & 3] += v[j]; }
+            const float mean = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (1.0f / 32.0f);
+            float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] -= mean; var = fmaf(v[j], v[j], var); }
-            const float rstd = rsqrtf(var * (1.0f / 32.0f) + 1e-5f);
+            for (int j = 0; j < 32; ++j) { v[j] -= mean; q4[j & 3] = fmaf(v[j], v[j], q4[j & 3]); }
+            const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / 32.0f) + 1e-5f);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] * rstd, slng[j], slnb[j]);
         }
@@ -250,55 +340,64 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             *reinterpret_cast<float4 *>(mt + ht * V_MROW + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         tmem_wait_st();
         fence_before_sync();
+        TS_MARK(8);
         bar_sync(bar_id, 128);
+        TS_MARK(9);
         if (ht == 0) {
             fence_after_sync();
             issue_3xtf32_ts(tD, tAhi, tAlo, dW3hi, dW3lo);
             umma_commit(mbar);
         }
-        // ---- feature segment sums while the tensor core works ----
-        const int rlast = *s_rlast;
-        for (int n = nstart + hw; n <= rlast; n += 4) {
-            const int b0 = __ldg(a.csr_ptr + n), b1 = __ldg(a.csr_ptr + n + 1);
-            const int lo = max(b0, p0) - p0, hi = min(b1, tend) - p0;
-            float s0 = (b0 < p0) ? carry[par * 36 + lane] : 0.f;     // row continues from the previous tile
-            int q = lo;
-            for (; q + 4 <= hi; q += 4) {                             // strictly sequential edge order (twin stability)
-                const float m0 = mt[q * V_MROW + lane], m1 = mt[(q + 1) * V_MROW + lane];
-                const float m2 = mt[(q + 2) * V_MROW + lane], m3 = mt[(q + 3) * V_MROW + lane];
-                s0 += m0; s0 += m1; s0 += m2; s0 += m3;
+        // ---- feature segment sums while the tensor core works: 8 threads per aggregation row (4 features
+        // each), up to 16 rows of the tile in parallel; every thread adds its row's edges in ascending order ----
+        {
+            const int fq = 4 * (ht & 7);
+            for (int n = nstart + (ht >> 3); n <= rlast; n += 16) {
+                const int b0 = ptr_at(sp, nstart, n), b1 = ptr_at(sp, nstart, n + 1);
+                const int lo = max(b0, p0) - p0, hi = min(b1, tend) - p0;
+                float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b0 < p0) s0 = *reinterpret_cast<const float4 *>(carry + par * 36 + fq);     // row continues from the previous tile
+                int q = lo;
+                for (; q + 4 <= hi; q += 4) {                         // strictly sequential edge order (twin stability)
+                    const float4 m0 = *reinterpret_cast<const float4 *>(mt + q * V_MROW + fq);
+                    const float4 m1 = *reinterpret_cast<const float4 *>(mt + (q + 1) * V_MROW + fq);
+                    const float4 m2 = *reinterpret_cast<const float4 *>(mt + (q + 2) * V_MROW + fq);
+                    const float4 m3 = *reinterpret_cast<const float4 *>(mt + (q + 3) * V_MROW + fq);
+                    s0.x += m0.x; s0.y += m0.y; s0.z += m0.z; s0.w += m0.w;
+                    s0.x += m1.x; s0.y += m1.y; s0.z += m1.z; s0.w += m1.w;
+                    s0.x += m2.x; s0.y += m2.y; s0.z += m2.z; s0.w += m2.w;
+                    s0.x += m3.x; s0.y += m3.y; s0.z += m3.z; s0.w += m3.w;
+                }
+                for (; q < hi; ++q) {
+                    const float4 m0 = *reinterpret_cast<const float4 *>(mt + q * V_MROW + fq);
+                    s0.x += m0.x; s0.y += m0.y; s0.z += m0.z; s0.w += m0.w;
+                }
+                if (b1 <= tend) *reinterpret_cast<float4 *>(agg_out + (int64_t)n * H + fq) = s0;      // row complete: out it goes
+                else *reinterpret_cast<float4 *>(carry + (par ^ 1) * 36 + fq) = s0;
             }
-            for (; q < hi; ++q) s0 += mt[q * V_MROW + lane];
-            if (b1 <= tend) agg_out[(int64_t)n * H + lane] = s0;      // row complete: out it goes
-            else carry[(par ^ 1) * 36 + lane] = s0;
         }
         // ---- accumulator -> registers, SiLU + wc2 epilogue (:219-229, :264) ----
+        TS_MARK(10);
         mbar_wait(mbar, phase); phase ^= 1;
+        TS_MARK(11);
         fence_after_sync();
         tmem_ld32(tmem_w, v);
-        float s = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int o = 0; o < 32; ++o) s = fmaf(swc2[o], silu_fast(v[o] + sbc1[o]), s);
-        dxs[ht] = make_float4(dx * s, dy * s, dz * s, 0.f);                               // trans = coord_diff * s
+        for (int o = 0; o < 32; ++o) s4[o & 3] = fmaf(swc2[o], silu_fast(v[o] + sbc1[o]), s4[o & 3]);
+        const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        // the previous tile's coordinate pass (its dxs were completed before this tile's barriers)
+        if (prev_rlast >= 0) coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast, x_pre);
+        dxs2[par * 128 + ht] = make_float4(dx * s, dy * s, dz * s, 0.f);                  // trans = coord_diff * s
+        prev_p0 = p0; prev_tend = tend; prev_nstart = nstart; prev_rlast = rlast;
+        nstart = (ptr_at(sp, nstart, rlast + 1) <= tend) ? rlast + 1 : rlast;
+    }
+    if (prev_rlast >= 0) {
         fence_before_sync();
-        bar_sync(bar_id, 128);      // dxs complete; every thread is done with the message tile and the accumulator
-        {   // coordinate segment sums: thread (slot = ht/4, component = ht%4)
-            const int comp = ht & 3;
-            for (int n = nstart + (ht >> 2); n <= rlast; n += 32) {
-                const int b0 = __ldg(a.csr_ptr + n), b1 = __ldg(a.csr_ptr + n + 1);
-                const int lo = max(b0, p0) - p0, hi = min(b1, tend) - p0;
-                float s1 = (b0 < p0) ? carry[par * 36 + 32 + comp] : 0.f;
-                for (int q = lo; q < hi; ++q) s1 += reinterpret_cast<const float *>(dxs + q)[comp];
-                if (b1 <= tend) {
-                    const float xv = (comp < 3) ? __ldg(a.x4 + (int64_t)n * 4 + comp) + s1 : 0.f;   // coord + agg  :267
-                    a.x4_out[(int64_t)n * 4 + comp] = xv;
-                    if (a.x3_out && comp < 3) a.x3_out[(int64_t)n * 3 + comp] = xv;
-                } else {
-                    carry[(par ^ 1) * 36 + 32 + comp] = s1;
-                }
-            }
-        }
-        nstart = (__ldg(a.csr_ptr + rlast + 1) <= tend) ? rlast + 1 : rlast;
+        bar_sync(bar_id, 128);      // the last tile's dxs are complete
+        const int n = prev_nstart + (ht >> 2);
+        coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast,
+                   (n <= prev_rlast && (ht & 3) < 3) ? __ldg(a.x4 + (int64_t)n * 4 + (ht & 3)) : 0.f);
     }
     // rows after the last edge of the range have no edges at all: zero aggregate, unchanged coordinates
     for (int n = nstart + hw; n < nB; n += 4) {
@@ -315,6 +414,12 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
 }
 
 void launch_node_kernel(const LayerArgs &a, const float *agg, cudaStream_t st);   // egnn_layer_tc.cu
+
+#ifdef EGSPR_TS_TIMING
+extern "C" int egspr_debug_read_ts(long long *host_dst) {
+    return cudaMemcpyFromSymbol(host_dst, g_ts_dbg, sizeof(long long) * 4 * 64 * 12) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 int launch_layer_ts(const LayerArgs &a, float *agg_ws, cudaStream_t st) {
     static bool configured = false;

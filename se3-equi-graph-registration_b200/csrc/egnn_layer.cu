@@ -205,7 +205,7 @@ extern "C" int egspr_egcl_forward(const float *h, const float *x4, const float *
     const bool big = num_nodes >= (int64_t)256 * 2 * sm_count();
     switch (impl) {
         case 0:
-            if (agg_ws) return launch_layer_mma(a, agg_ws, (cudaStream_t)stream);
+            if (agg_ws) return launch_layer_ts(a, agg_ws, (cudaStream_t)stream);
             return big ? launch_layer<256>(a, (cudaStream_t)stream) : launch_layer<64>(a, (cudaStream_t)stream);
         case 1: return launch_layer<64>(a, (cudaStream_t)stream);
         case 2: return launch_layer<256>(a, (cudaStream_t)stream);

@@ -1,0 +1,17 @@
+"""Developer script (gpurun): CUDA-event time of one E_GCL layer launch sequence per impl at the bench shape."""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import se3_equi_graph_registration_b200 as P
+import bench
+impls = [int(x) for x in os.environ.get("EGSPR_IMPLS", "3,4,5").split(",")]
+B = int(os.environ.get("EGSPR_B", "64")); N = int(os.environ.get("EGSPR_N", "2048"))
+model = P.build_model(bench.CKPT, device="cuda:0")
+data = P.synthetic.make_batch(5, B, n=N)
+eng = P.RegistrationEngine(model, batch=B, n=N, k=16, use_graph=False)
+eng.load(*[data[k] for k in ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "labels", "gt_pose")])
+for impl in impls:
+    eng.impl = impl
+    ms = bench.eng_layer_time(eng, reps=20)
+    eng.use_graph = False
+    print(f"impl {impl}: layer (edge+node kernels) {ms*1e3:.1f} us")
