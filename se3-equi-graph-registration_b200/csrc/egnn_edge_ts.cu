@@ -61,14 +61,6 @@ __device__ long long g_ts_dbg[4 * 64 * 12];
 #define TS_MARK(slot)
 #endif
 
-__device__ __forceinline__ float silu_fast(float v) {
-    // v * sigmoid(v) = v * rcp(1 + 2^(-v log2 e)); MUFU.EX2 + MUFU.RCP, no range fix-ups
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return v * r;
-}
-
 // this thread's 32 values -> hi / lo halves of the A operand in TMEM (columns [0,32) of each)
 __device__ __forceinline__ void store_hilo_tmem(uint32_t t_hi, uint32_t t_lo, const float (&v)[32]) {
 #pragma unroll
@@ -298,8 +290,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         tmem_ld32(tmem_w, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {   // + P[row] + Q[col], SiLU  (:203-206)
-            v[4 * i] = silu_fast(v[4 * i] + (pv[i].x + qv[i].x)); v[4 * i + 1] = silu_fast(v[4 * i + 1] + (pv[i].y + qv[i].y));
-            v[4 * i + 2] = silu_fast(v[4 * i + 2] + (pv[i].z + qv[i].z)); v[4 * i + 3] = silu_fast(v[4 * i + 3] + (pv[i].w + qv[i].w));
+            v[4 * i] = silu(v[4 * i] + (pv[i].x + qv[i].x)); v[4 * i + 1] = silu(v[4 * i + 1] + (pv[i].y + qv[i].y));
+            v[4 * i + 2] = silu(v[4 * i + 2] + (pv[i].z + qv[i].z)); v[4 * i + 3] = silu(v[4 * i + 3] + (pv[i].w + qv[i].w));
         }
         // ---------------- stage 2: per-head second Linear (block-diagonal) ----------------
         store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
@@ -384,7 +376,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         tmem_ld32(tmem_w, v);
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int o = 0; o < 32; ++o) s4[o & 3] = fmaf(swc2[o], silu_fast(v[o] + sbc1[o]), s4[o & 3]);
+        for (int o = 0; o < 32; ++o) s4[o & 3] = fmaf(swc2[o], silu(v[o] + sbc1[o]), s4[o & 3]);
         const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         // the previous tile's coordinate pass (its dxs were completed before this tile's barriers)
         if (prev_rlast >= 0) coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast, x_pre);
@@ -413,7 +405,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     if (tid < 32) tmem_dealloc(*tmem_holder, 512);
 }
 
-void launch_node_kernel(const LayerArgs &a, const float *agg, cudaStream_t st);   // egnn_layer_tc.cu
+int launch_node_update_ts(const LayerArgs &a, const float *agg, cudaStream_t st);   // egnn_node_ts.cu
 
 #ifdef EGSPR_TS_TIMING
 extern "C" int egspr_debug_read_ts(long long *host_dst) {
@@ -434,9 +426,7 @@ int launch_layer_ts(const LayerArgs &a, float *agg_ws, cudaStream_t st) {
     if (grid > need) grid = need;
     egcl_edge_ts_kernel<<<(unsigned)grid, V_THREADS, V_SMEM_BYTES, st>>>(a, agg_ws);
     if (cudaGetLastError() != cudaSuccess) return EGSPR_E_LAUNCH;
-    launch_node_kernel(a, agg_ws, st);
-    if (cudaGetLastError() != cudaSuccess) return EGSPR_E_LAUNCH;
-    return EGSPR_OK;
+    return launch_node_update_ts(a, agg_ws, st);
 }
 
 }  // namespace egspr

@@ -12,6 +12,8 @@
 //   node phase   : node MLP + residual (:252-260), coordinate update (:267), then the NEXT layer's
 //                  P/Q halves (or embedding_out :337 after the last layer) while h' is in registers
 // so per layer the only HBM/L2 traffic is the gathers and one write of h', x', P', Q'.
+#include <cstdlib>
+
 #include "egnn_layer.cuh"
 
 namespace egspr {
@@ -170,6 +172,8 @@ static int launch_layer(const LayerArgs &a, cudaStream_t st) {
 int launch_layer_tc(const LayerArgs &a, float *agg_ws, cudaStream_t st);   // egnn_layer_tc.cu
 int launch_layer_mma(const LayerArgs &a, float *agg_ws, cudaStream_t st);  // egnn_edge_mma.cu
 int launch_layer_ts(const LayerArgs &a, float *agg_ws, cudaStream_t st);   // egnn_edge_ts.cu
+int launch_node_embed_ts(const float *feat, const float *x3, int64_t G, const float *embed_pack, const float *layer0_pack,
+                         float *h, float *x4, float *P, float *Q, cudaStream_t st);   // egnn_node_ts.cu
 
 }  // namespace egspr
 
@@ -178,6 +182,8 @@ extern "C" int egspr_node_embed(const float *feat, const float *x3, int64_t num_
     using namespace egspr;
     if (!feat || !layer0_pack || !h || !P || !Q || num_nodes <= 0) return EGSPR_E_INVALID;
     if (x4 && !x3) return EGSPR_E_INVALID;
+    static const bool simt = getenv("EGSPR_EMBED_SIMT") != nullptr;     // developer switch: CUDA-core embed kernel
+    if (!simt) return launch_node_embed_ts(feat, x3, num_nodes, embed_pack, layer0_pack, h, x4, P, Q, (cudaStream_t)stream);
     int64_t grid = (num_nodes + 127) / 128;
     if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     node_embed_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(feat, x3, num_nodes, embed_pack, layer0_pack, h, x4, P, Q);

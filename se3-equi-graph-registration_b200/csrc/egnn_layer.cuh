@@ -57,10 +57,8 @@ __device__ __forceinline__ void matvec32_smem(float (&acc)[32], const float *__r
 #pragma unroll
         for (int o4 = 0; o4 < 8; ++o4) {
             const float4 w = *reinterpret_cast<const float4 *>(wt + 32 * i + 4 * o4);
-            acc[4 * o4 + 0] = fmaf(w.x, v, acc[4 * o4 + 0]);
-            acc[4 * o4 + 1] = fmaf(w.y, v, acc[4 * o4 + 1]);
-            acc[4 * o4 + 2] = fmaf(w.z, v, acc[4 * o4 + 2]);
-            acc[4 * o4 + 3] = fmaf(w.w, v, acc[4 * o4 + 3]);
+            ffma2(acc[4 * o4 + 0], acc[4 * o4 + 1], w.x, w.y, v, v);
+            ffma2(acc[4 * o4 + 2], acc[4 * o4 + 3], w.z, w.w, v, v);
         }
     }
 }

@@ -43,8 +43,12 @@ constexpr int HOFF_W0T = 0, HOFF_B0 = 2048, HOFF_W1T = 2080, HOFF_B1 = 2592, HOF
 constexpr int HEAD_PACK = EGSPR_HEAD_PACK_FLOATS;
 
 __device__ __forceinline__ float silu(float v) {
-    // v * sigmoid(v) with MUFU.EX2 / MUFU.RCP (each within ~2 ulp, far inside the 1e-4 parity budget)
-    return __fdividef(v, 1.0f + __expf(-v));
+    // v * sigmoid(v) = v * rcp(1 + 2^(-v log2 e)): MUFU.EX2 + MUFU.RCP (each within ~2 ulp, far inside the
+    // 1e-4 parity budget), no range fix-ups: v -> -inf gives v * rcp(inf) = -0
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
 }
 __device__ __forceinline__ float fast_sqrt(float v) {
     float r;
@@ -55,6 +59,15 @@ __device__ __forceinline__ float fast_rcp(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+}
+
+// packed fp32 pair FMA (sm_100 FFMA2): (d0, d1) = (a0, a1) * (b0, b1) + (d0, d1), each lane rounded like fmaf --
+// one issue slot for two FMAs
+__device__ __forceinline__ void ffma2(float &d0, float &d1, float a0, float a1, float b0, float b1) {
+    asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rd, {%0, %1};\n"
+        "fma.rn.f32x2 rd, ra, rb, rd;\nmov.b64 {%0, %1}, rd;\n}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
