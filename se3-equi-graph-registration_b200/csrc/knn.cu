@@ -10,6 +10,8 @@
 // (SoA, coalesced loads); each lane scores one candidate per step; the running top-k lives one
 // entry per lane (k <= 32), kept sorted; candidates beating the current k-th distance are
 // inserted with a ballot + shuffle-up (no local memory, no divergence across queries).
+#include <cstdlib>
+
 #include "egspr_common.cuh"
 
 namespace egspr {
@@ -86,7 +88,8 @@ struct GridParams {        // per cloud, 16 floats
     float inv[3];          // 1 / cell size
     float cs[3];           // cell size
     int dims[3];
-    int pad[4];
+    float slack;           // absolute slack of the stopping rule: rounding of the point -> cell assignment
+    int pad[3];
 };
 
 __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
@@ -146,6 +149,9 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
             const float cs = (ext[a] > 0.f) ? ext[a] / (float)dims[a] : 1.0f;
             gp.cs[a] = cs; gp.inv[a] = 1.0f / cs;
         }
+        // a point may be assigned to the cell next to its geometric one when (p - mn) * inv rounds across an
+        // integer: the error is a few ulp of the coordinate magnitude
+        gp.slack = 8.0f * 1.1920929e-7f * (fmaxf(fmaxf(fabsf(mn[0]), fabsf(mn[1])), fabsf(mn[2])) + emax);
         params[cloud] = gp;
     }
     __syncthreads();
@@ -277,11 +283,326 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_kernel(
         if (cz + L < nz - 1) margin = fminf(margin, (gp.mn[2] + (float)(cz + L + 1) * gp.cs[2]) - q.z);
         if (margin > 1e37f) break;                              // block covers the whole grid
         if (margin > 0.f) {
-            const float ms = margin * 0.9999f;
-            if (thr_i >= 0 && thr_d < ms * ms) break;
+            const float ms = margin * 0.9999f - gp.slack;
+            if (thr_i >= 0 && ms > 0.f && thr_d < ms * ms) break;
         }
     }
     if (lane < k) nbr[((size_t)cloud * n + qi) * k + lane] = bi;
+}
+
+// ---- flattened variant of the query kernel -------------------------------------------------------
+// Same search (shells of cells at Chebyshev radius L around the query's cell, same (d2, index) total
+// order, same stopping rule), but the cells of a shell are not walked by nested loops: every lane
+// describes ONE contiguous run of cells (a "segment": start, length in the cell-sorted point array),
+// a warp scan turns the lengths into offsets, and the lanes then sweep the concatenated candidate list
+// 32 at a time (segment found by a 5-step shuffle binary search).  Removes the loop / branch overhead
+// that dominated the nested version (ncu: 27 % ISETP+BRA, 10 % BSSY/BSYNC) and keeps lanes busy on
+// short runs.
+__device__ __forceinline__ void knn_insert_batch(float d, int idx, int k, int lane, float &bd, int &bi, float &thr_d, int &thr_i) {
+    unsigned m = __ballot_sync(0xffffffffu, d < thr_d || (d == thr_d && idx < thr_i));
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float dd = __shfl_sync(0xffffffffu, d, src);
+        const int jj = __shfl_sync(0xffffffffu, idx, src);
+        if (dd < thr_d || (dd == thr_d && jj < thr_i)) {
+            const bool before = lane < k && (bd < dd || (bd == dd && bi < jj));
+            // empty slots are (1e10, -1): never "before" a real candidate (dd < 1e10)
+            const int pos = __popc(__ballot_sync(0xffffffffu, before && bi >= 0));
+            const float ubd = __shfl_up_sync(0xffffffffu, bd, 1);
+            const int ubi = __shfl_up_sync(0xffffffffu, bi, 1);
+            if (lane > pos) { bd = ubd; bi = ubi; }
+            if (lane == pos) { bd = dd; bi = jj; }
+            thr_d = __shfl_sync(0xffffffffu, bd, k - 1);
+            thr_i = __shfl_sync(0xffffffffu, bi, k - 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_flat_kernel(
+    const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
+    int n, int k, int32_t *__restrict__ nbr) {
+    const int cloud = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qs = blockIdx.x * GQ_WARPS + warp;          // query = qs-th point in cell-sorted order
+    if (qs >= n) return;
+    const float4 *so = sorted + (size_t)cloud * n;
+    const int *cs = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    const GridParams gp = params[cloud];
+    const float4 q = __ldg(so + qs);
+    const int qi = __float_as_int(q.w);
+    const int nx = gp.dims[0], ny = gp.dims[1], nz = gp.dims[2];
+    const int cx = min(nx - 1, max(0, (int)((q.x - gp.mn[0]) * gp.inv[0])));
+    const int cy = min(ny - 1, max(0, (int)((q.y - gp.mn[1]) * gp.inv[1])));
+    const int cz = min(nz - 1, max(0, (int)((q.z - gp.mn[2]) * gp.inv[2])));
+    float bd = 1e10f;
+    int bi = -1;
+    float thr_d = 1e10f;
+    int thr_i = -1;
+    const int Lmax = max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz));
+    for (int L = 1; L <= max(Lmax, 1); ++L) {
+        // segments of this step: L == 1: the 9 rows of the 3x3x3 block (shells 0 and 1 together);
+        // L >= 2: 8L outer rows (full x-run) + (2L-1)^2 inner rows x 2 end cells
+        const int w = 2 * L - 1;
+        const int nseg = (L == 1) ? 9 : 8 * L + 2 * w * w;
+        for (int s0 = 0; s0 < nseg; s0 += 32) {
+            const int s = s0 + lane;
+            int start = 0, len = 0;
+            if (s < nseg) {
+                int dz, dy, x0, x1;
+                if (L == 1) {
+                    dz = s / 3 - 1; dy = s % 3 - 1; x0 = cx - 1; x1 = cx + 1;
+                } else if (s < 8 * L) {
+                    x0 = cx - L; x1 = cx + L;
+                    if (s < 2 * L + 1) { dz = -L; dy = s - L; }
+                    else if (s < 2 * (2 * L + 1)) { dz = L; dy = s - (2 * L + 1) - L; }
+                    else { const int t = s - 2 * (2 * L + 1); dy = (t >= w) ? L : -L; dz = (t >= w ? t - w : t) - (L - 1); }
+                } else {
+                    const int t = s - 8 * L, rr = t >> 1;
+                    dz = rr / w - (L - 1); dy = rr % w - (L - 1);
+                    x0 = x1 = (t & 1) ? cx + L : cx - L;
+                }
+                const int z = cz + dz, y = cy + dy;
+                x0 = max(x0, 0); x1 = min(x1, nx - 1);
+                if (z >= 0 && z < nz && y >= 0 && y < ny && x0 <= x1) {
+                    const int rowbase = (z * ny + y) * nx;
+                    start = __ldg(cs + rowbase + x0);
+                    len = __ldg(cs + rowbase + x1 + 1) - start;
+                }
+            }
+            // exclusive scan of the segment lengths
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int excl = incl - len;
+            const int T = __shfl_sync(0xffffffffu, incl, 31);
+            for (int t0 = 0; t0 < T; t0 += 32) {
+                const int t = t0 + lane;
+                // segment of candidate t: the last lane whose exclusive offset is <= t (empty segments share
+                // an offset with their successor, so "last" lands on the non-empty one)
+                int lo = 0;
+#pragma unroll
+                for (int h = 16; h > 0; h >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, excl, lo + h);
+                    if (v <= t) lo += h;
+                }
+                const int sstart = __shfl_sync(0xffffffffu, start, lo), sbase = __shfl_sync(0xffffffffu, excl, lo);
+                float d = 3e38f;
+                int idx = 0x7fffffff;
+                if (t < T) {
+                    const float4 c = __ldg(so + sstart + (t - sbase));
+                    const float dx = c.x - q.x, dy2 = c.y - q.y, dz2 = c.z - q.z;
+                    d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
+                    idx = __float_as_int(c.w);
+                }
+                knn_insert_batch(d, idx, k, lane, bd, bi, thr_d, thr_i);
+            }
+        }
+        // done when the k-th best is strictly inside the scanned block (sides on the domain boundary
+        // have nothing beyond them)
+        float margin = 3e38f;
+        if (cx - L > 0) margin = fminf(margin, q.x - (gp.mn[0] + (float)(cx - L) * gp.cs[0]));
+        if (cx + L < nx - 1) margin = fminf(margin, (gp.mn[0] + (float)(cx + L + 1) * gp.cs[0]) - q.x);
+        if (cy - L > 0) margin = fminf(margin, q.y - (gp.mn[1] + (float)(cy - L) * gp.cs[1]));
+        if (cy + L < ny - 1) margin = fminf(margin, (gp.mn[1] + (float)(cy + L + 1) * gp.cs[1]) - q.y);
+        if (cz - L > 0) margin = fminf(margin, q.z - (gp.mn[2] + (float)(cz - L) * gp.cs[2]));
+        if (cz + L < nz - 1) margin = fminf(margin, (gp.mn[2] + (float)(cz + L + 1) * gp.cs[2]) - q.z);
+        if (margin > 1e37f) break;                              // block covers the whole grid
+        if (margin > 0.f) {
+            const float ms = margin * 0.9999f - gp.slack;
+            if (thr_i >= 0 && ms > 0.f && thr_d < ms * ms) break;
+        }
+    }
+    if (lane < k) nbr[((size_t)cloud * n + qi) * k + lane] = bi;
+}
+
+// ---- sub-warp variant (k <= 16): 32/W queries per warp, W lanes each ---------------------------------
+// The per-iteration instruction cost of the flat kernel (segment search, candidate scoring, the
+// serial insertion loop) is paid once per warp, so sharing a warp between 32/W neighbouring queries
+// (cell-sorted order: same or adjacent cells, similar trip counts) divides the cost per query.  The
+// sorted top-k list of a query lives E = 16/W entries per lane (position = lane_in_group * E + j).
+// Identical selection rule: total order (d2, index), same stopping test.
+template <int W>
+__global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
+    const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
+    int n, int k, int32_t *__restrict__ nbr, int merge_min) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int E = 16 / W;                      // list entries per lane
+    constexpr int QPW = 32 / W;                    // queries per warp
+    constexpr unsigned GMASK = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
+    const int cloud = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / W, sl = lane % W, sh = W * sub;
+    const int qs = (blockIdx.x * GQ_WARPS + warp) * QPW + sub;      // query = qs-th point in cell-sorted order
+    const bool valid = qs < n;
+    const float4 *so = sorted + (size_t)cloud * n;
+    const int *cs = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    const GridParams gp = params[cloud];
+    const float4 q = __ldg(so + (valid ? qs : n - 1));
+    const int qi = __float_as_int(q.w);
+    const int nx = gp.dims[0], ny = gp.dims[1], nz = gp.dims[2];
+    const int cx = min(nx - 1, max(0, (int)((q.x - gp.mn[0]) * gp.inv[0])));
+    const int cy = min(ny - 1, max(0, (int)((q.y - gp.mn[1]) * gp.inv[1])));
+    const int cz = min(nz - 1, max(0, (int)((q.z - gp.mn[2]) * gp.inv[2])));
+    float bd[E];
+    int bi[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) { bd[j] = 1e10f; bi[j] = -1; }
+    float thr_d = 1e10f;
+    int thr_i = -1;
+    const int kl = (k - 1) / E, kj = (k - 1) % E;          // lane / slot of the k-th entry
+    const int Lmax = max(max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz)), 1);
+    bool done = !valid;
+    for (int L = 1; !__all_sync(FULL, done); ++L) {
+        const int w = 2 * L - 1;
+        const int nseg = done ? 0 : ((L == 1) ? 9 : 8 * L + 2 * w * w);
+        for (int s0 = 0; __any_sync(FULL, s0 < nseg); s0 += W) {
+            const int s = s0 + sl;
+            int start = 0, len = 0;
+            if (s < nseg) {
+                int dz, dy, x0, x1;
+                if (L == 1) {
+                    dz = s / 3 - 1; dy = s % 3 - 1; x0 = cx - 1; x1 = cx + 1;
+                } else if (s < 8 * L) {
+                    x0 = cx - L; x1 = cx + L;
+                    if (s < 2 * L + 1) { dz = -L; dy = s - L; }
+                    else if (s < 2 * (2 * L + 1)) { dz = L; dy = s - (2 * L + 1) - L; }
+                    else { const int t = s - 2 * (2 * L + 1); dy = (t >= w) ? L : -L; dz = (t >= w ? t - w : t) - (L - 1); }
+                } else {
+                    const int t = s - 8 * L, rr = t >> 1;
+                    dz = rr / w - (L - 1); dy = rr % w - (L - 1);
+                    x0 = x1 = (t & 1) ? cx + L : cx - L;
+                }
+                const int z = cz + dz, y = cy + dy;
+                x0 = max(x0, 0); x1 = min(x1, nx - 1);
+                if (z >= 0 && z < nz && y >= 0 && y < ny && x0 <= x1) {
+                    const int rowbase = (z * ny + y) * nx;
+                    start = __ldg(cs + rowbase + x0);
+                    len = __ldg(cs + rowbase + x1 + 1) - start;
+                }
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < W; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o, W); if (sl >= o) incl += t; }
+            const int excl = incl - len;
+            const int T = __shfl_sync(FULL, incl, W - 1, W);
+            for (int t0 = 0; __any_sync(FULL, t0 < T); t0 += W) {
+                const int t = t0 + sl;
+                int lo = 0;
+#pragma unroll
+                for (int h = W / 2; h > 0; h >>= 1) {
+                    const int v = __shfl_sync(FULL, excl, lo + h, W);
+                    if (v <= t) lo += h;
+                }
+                const int sstart = __shfl_sync(FULL, start, lo, W), sbase = __shfl_sync(FULL, excl, lo, W);
+                float d = 3e38f;
+                int idx = 0x7fffffff;
+                if (t < T) {
+                    const float4 c = __ldg(so + sstart + (t - sbase));
+                    const float dx = c.x - q.x, dy2 = c.y - q.y, dz2 = c.z - q.z;
+                    d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
+                    idx = __float_as_int(c.w);
+                }
+                unsigned m = (__ballot_sync(FULL, d < thr_d || (d == thr_d && idx < thr_i)) >> sh) & GMASK;
+                if constexpr (W == 16) {
+                    // many candidates beat the k-th best (the first batches of a query): sort the batch with a
+                    // bitonic network and merge it into the list in one go instead of inserting one by one
+                    if (__any_sync(FULL, __popc(m) >= merge_min)) {
+                        float sd = ((m >> sl) & 1u) ? d : 3e38f;          // non-passers cannot enter the list
+                        int si = ((m >> sl) & 1u) ? idx : 0x7fffffff;
+#pragma unroll
+                        for (int size = 2; size <= 16; size <<= 1) {
+#pragma unroll
+                            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                                const float pd = __shfl_xor_sync(FULL, sd, stride, 16);
+                                const int pi = __shfl_xor_sync(FULL, si, stride, 16);
+                                const bool plt = pd < sd || (pd == sd && pi < si);           // partner sorts first
+                                const bool up = ((sl & size) == 0);                           // ascending block
+                                const bool lower = ((sl & stride) == 0);
+                                if (plt == (up == lower)) { sd = pd; si = pi; }               // keep min in the lower lane of an ascending pair
+                            }
+                        }
+                        // lowest 16 of (list, batch): elementwise min against the reversed batch is bitonic -> 4 merge stages
+                        {
+                            const float rd = __shfl_sync(FULL, sd, 15 - sl, 16);
+                            const int ri = __shfl_sync(FULL, si, 15 - sl, 16);
+                            if (rd < bd[0] || (rd == bd[0] && ri < bi[0])) { bd[0] = rd; bi[0] = ri; }
+                        }
+#pragma unroll
+                        for (int stride = 8; stride > 0; stride >>= 1) {
+                            const float pd = __shfl_xor_sync(FULL, bd[0], stride, 16);
+                            const int pi = __shfl_xor_sync(FULL, bi[0], stride, 16);
+                            const bool plt = pd < bd[0] || (pd == bd[0] && pi < bi[0]);
+                            const bool lower = ((sl & stride) == 0);
+                            if (plt == lower) { bd[0] = pd; bi[0] = pi; }
+                        }
+                        thr_d = __shfl_sync(FULL, bd[0], k - 1, 16);
+                        thr_i = __shfl_sync(FULL, bi[0], k - 1, 16);
+                        m = 0;
+                    }
+                }
+                // serial insertion of the candidates that beat the current k-th best, each group on its own list
+                while (__any_sync(FULL, m != 0)) {
+                    const bool act = m != 0;
+                    const int src = act ? __ffs(m) - 1 : 0;
+                    m &= m - 1;
+                    const float dd = __shfl_sync(FULL, d, src, W);
+                    const int jj = __shfl_sync(FULL, idx, src, W);
+                    const bool ins = act && (dd < thr_d || (dd == thr_d && jj < thr_i));   // thr may have dropped since the ballot
+                    // position = number of kept entries that sort before the candidate (empty slots never do)
+                    int pos = 0;
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const bool before = (sl * E + j) < k && bi[j] >= 0 && (bd[j] < dd || (bd[j] == dd && bi[j] < jj));
+                        pos += __popc((__ballot_sync(FULL, before) >> sh) & GMASK);
+                    }
+                    const float ubd = __shfl_up_sync(FULL, bd[E - 1], 1, W);
+                    const int ubi = __shfl_up_sync(FULL, bi[E - 1], 1, W);
+                    if (ins) {
+#pragma unroll
+                        for (int j = E - 1; j >= 0; --j) {
+                            const int p = sl * E + j;
+                            const float pd = (j == 0) ? ubd : bd[j - 1];
+                            const int pi = (j == 0) ? ubi : bi[j - 1];
+                            if (p > pos) { bd[j] = pd; bi[j] = pi; }
+                            else if (p == pos) { bd[j] = dd; bi[j] = jj; }
+                        }
+                    }
+                    float td = bd[0]; int ti = bi[0];
+#pragma unroll
+                    for (int j = 1; j < E; ++j) if (kj == j) { td = bd[j]; ti = bi[j]; }
+                    thr_d = __shfl_sync(FULL, td, kl, W);
+                    thr_i = __shfl_sync(FULL, ti, kl, W);
+                }
+            }
+        }
+        if (!done) {
+            float margin = 3e38f;
+            if (cx - L > 0) margin = fminf(margin, q.x - (gp.mn[0] + (float)(cx - L) * gp.cs[0]));
+            if (cx + L < nx - 1) margin = fminf(margin, (gp.mn[0] + (float)(cx + L + 1) * gp.cs[0]) - q.x);
+            if (cy - L > 0) margin = fminf(margin, q.y - (gp.mn[1] + (float)(cy - L) * gp.cs[1]));
+            if (cy + L < ny - 1) margin = fminf(margin, (gp.mn[1] + (float)(cy + L + 1) * gp.cs[1]) - q.y);
+            if (cz - L > 0) margin = fminf(margin, q.z - (gp.mn[2] + (float)(cz - L) * gp.cs[2]));
+            if (cz + L < nz - 1) margin = fminf(margin, (gp.mn[2] + (float)(cz + L + 1) * gp.cs[2]) - q.z);
+            const float ms = margin * 0.9999f - gp.slack;
+            if (margin > 1e37f || L >= Lmax) done = true;                     // block covers the whole grid
+            else if (thr_i >= 0 && ms > 0.f && thr_d < ms * ms) done = true;  // k-th best strictly inside the block
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < E; ++j)
+            if (sl * E + j < k) nbr[((size_t)cloud * n + qi) * k + sl * E + j] = bi[j];
+    }
+}
+
+template <int W>
+static void launch_knn_sub(const float4 *sorted, const int *cell_start, const GridParams *params, int clouds, int n, int k,
+                           int32_t *nbr, cudaStream_t st) {
+    constexpr int QPB = GQ_WARPS * (32 / W);
+    dim3 grid((n + QPB - 1) / QPB, clouds);
+    static const int merge_min = getenv("EGSPR_KNN_MERGE_MIN") ? atoi(getenv("EGSPR_KNN_MERGE_MIN")) : 5;
+    knn_grid_query_sub_kernel<W><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min);
 }
 
 __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int k,
@@ -322,7 +643,14 @@ extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t
     GridParams *params = (GridParams *)(cell_start + (size_t)clouds * (GRID_MAXC + 1));
     knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, 0, st>>>(x, n, sorted, cell_start, params);
     dim3 grid((n + GQ_WARPS - 1) / GQ_WARPS, clouds);
-    knn_grid_query_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr);
+    static const bool nested = getenv("EGSPR_KNN_NESTED") != nullptr;    // developer switch: the nested-loop query kernel
+    static const bool flat32 = getenv("EGSPR_KNN_FLAT32") != nullptr;    // developer switch: one query per warp even for k <= 16
+    if (nested) knn_grid_query_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr);
+    else if (k <= 16 && !flat32) {
+        static const int wsel = getenv("EGSPR_KNN_W") ? atoi(getenv("EGSPR_KNN_W")) : 16;   // lanes per query
+        if (wsel == 8) launch_knn_sub<8>(sorted, cell_start, params, clouds, n, k, nbr, st);
+        else launch_knn_sub<16>(sorted, cell_start, params, clouds, n, k, nbr, st);
+    } else knn_grid_query_flat_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
