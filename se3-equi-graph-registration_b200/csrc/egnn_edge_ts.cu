@@ -67,7 +67,11 @@ __device__ __forceinline__ void store_hilo_tmem(uint32_t t_hi, uint32_t t_lo, co
     for (int b = 0; b < 2; ++b) {
         float hi[16], lo[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { hi[i] = tf32_hi(v[16 * b + i]); lo[i] = v[16 * b + i] - hi[i]; }
+        for (int i = 0; i < 16; i += 2) {
+            hi[i] = tf32_hi(v[16 * b + i]); hi[i + 1] = tf32_hi(v[16 * b + i + 1]);
+            lo[i] = v[16 * b + i]; lo[i + 1] = v[16 * b + i + 1];
+            fadd2(lo[i], lo[i + 1], -hi[i], -hi[i + 1]);             // lo = v - hi (exact)
+        }
         tmem_st16(t_hi + 16 * b, hi);
         tmem_st16(t_lo + 16 * b, lo);
     }
@@ -290,8 +294,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         tmem_ld32(tmem_w, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {   // + P[row] + Q[col], SiLU  (:203-206)
-            v[4 * i] = silu(v[4 * i] + (pv[i].x + qv[i].x)); v[4 * i + 1] = silu(v[4 * i + 1] + (pv[i].y + qv[i].y));
-            v[4 * i + 2] = silu(v[4 * i + 2] + (pv[i].z + qv[i].z)); v[4 * i + 3] = silu(v[4 * i + 3] + (pv[i].w + qv[i].w));
+            fadd2(pv[i].x, pv[i].y, qv[i].x, qv[i].y); fadd2(pv[i].z, pv[i].w, qv[i].z, qv[i].w);
+            fadd2(v[4 * i], v[4 * i + 1], pv[i].x, pv[i].y); fadd2(v[4 * i + 2], v[4 * i + 3], pv[i].z, pv[i].w);
+            silu2(v[4 * i], v[4 * i + 1]); silu2(v[4 * i + 2], v[4 * i + 3]);
         }
         // ---------------- stage 2: per-head second Linear (block-diagonal) ----------------
         store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
@@ -316,14 +321,27 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         {   // + b2, LayerNorm(32), eps 1e-5, biased variance (:209,:249); 4 partial sums for ILP
             float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] += sb2[j]; m4[j & 3] += v[j]; }
-            const float mean = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (1.0f / 32.0f);
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4 *>(sb2 + j);
+                fadd2(v[j], v[j + 1], b.x, b.y); fadd2(v[j + 2], v[j + 3], b.z, b.w);
+                fadd2(m4[0], m4[1], v[j], v[j + 1]); fadd2(m4[2], m4[3], v[j + 2], v[j + 3]);
+            }
+            const float nmean = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (-1.0f / 32.0f);
             float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] -= mean; q4[j & 3] = fmaf(v[j], v[j], q4[j & 3]); }
+            for (int j = 0; j < 32; j += 4) {
+                fadd2(v[j], v[j + 1], nmean, nmean); fadd2(v[j + 2], v[j + 3], nmean, nmean);
+                ffma2(q4[0], q4[1], v[j], v[j + 1], v[j], v[j + 1]); ffma2(q4[2], q4[3], v[j + 2], v[j + 3], v[j + 2], v[j + 3]);
+            }
             const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / 32.0f) + 1e-5f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] * rstd, slng[j], slnb[j]);
+            for (int j = 0; j < 32; j += 4) {
+                const float4 gm = *reinterpret_cast<const float4 *>(slng + j), bt = *reinterpret_cast<const float4 *>(slnb + j);
+                fmul2(v[j], v[j + 1], rstd, rstd); fmul2(v[j + 2], v[j + 3], rstd, rstd);
+                float o0 = bt.x, o1 = bt.y, o2 = bt.z, o3 = bt.w;
+                ffma2(o0, o1, v[j], v[j + 1], gm.x, gm.y); ffma2(o2, o3, v[j + 2], v[j + 3], gm.z, gm.w);
+                v[j] = o0; v[j + 1] = o1; v[j + 2] = o2; v[j + 3] = o3;
+            }
         }
         // ---------------- stage 3: coord_mlp.0; messages also to shared memory ----------------
         store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
@@ -376,7 +394,12 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         tmem_ld32(tmem_w, v);
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int o = 0; o < 32; ++o) s4[o & 3] = fmaf(swc2[o], silu(v[o] + sbc1[o]), s4[o & 3]);
+        for (int o = 0; o < 32; o += 4) {
+            const float4 b = *reinterpret_cast<const float4 *>(sbc1 + o), wc = *reinterpret_cast<const float4 *>(swc2 + o);
+            fadd2(v[o], v[o + 1], b.x, b.y); fadd2(v[o + 2], v[o + 3], b.z, b.w);
+            silu2(v[o], v[o + 1]); silu2(v[o + 2], v[o + 3]);
+            ffma2(s4[0], s4[1], v[o], v[o + 1], wc.x, wc.y); ffma2(s4[2], s4[3], v[o + 2], v[o + 3], wc.z, wc.w);
+        }
         const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         // the previous tile's coordinate pass (its dxs were completed before this tile's barriers)
         if (prev_rlast >= 0) coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast, x_pre);

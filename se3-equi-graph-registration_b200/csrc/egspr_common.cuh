@@ -70,6 +70,26 @@ __device__ __forceinline__ void ffma2(float &d0, float &d1, float a0, float a1, 
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+__device__ __forceinline__ void fadd2(float &d0, float &d1, float b0, float b1) {        // (d0,d1) += (b0,b1), FADD2
+    asm("{\n.reg .b64 ra, rb;\nmov.b64 ra, {%0, %1};\nmov.b64 rb, {%2, %3};\nadd.rn.f32x2 ra, ra, rb;\nmov.b64 {%0, %1}, ra;\n}"
+        : "+f"(d0), "+f"(d1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float &d0, float &d1, float b0, float b1) {        // (d0,d1) *= (b0,b1), FMUL2
+    asm("{\n.reg .b64 ra, rb;\nmov.b64 ra, {%0, %1};\nmov.b64 rb, {%2, %3};\nmul.rn.f32x2 ra, ra, rb;\nmov.b64 {%0, %1}, ra;\n}"
+        : "+f"(d0), "+f"(d1) : "f"(b0), "f"(b1));
+}
+// SiLU on a pair: the multiplies / add run packed (FMUL2, FADD2), the two MUFU pairs stay scalar
+__device__ __forceinline__ void silu2(float &x0, float &x1) {
+    float t0 = x0, t1 = x1;
+    fmul2(t0, t1, -1.4426950408889634f, -1.4426950408889634f);
+    asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(t1));
+    fadd2(t0, t1, 1.0f, 1.0f);
+    asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(t0));
+    asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(t1));
+    fmul2(x0, x1, t0, t1);
+}
+
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
