@@ -95,12 +95,16 @@ int egspr_node_embed(const float *feat, const float *x3, int64_t num_nodes, cons
  * the layer input).  edge_attr: optional [clouds*edges_per_cloud] per-edge scalar indexed through
  * csr_eid (NULL = constant edge_attr_const, the reference's ones, 3dm:387; a layer built with
  * edges_in_d=0 has a zero edge_attr column in its pack).
- * impl: 0 = auto (impl 4 if agg_ws != NULL, else the fused CUDA-core kernel);
- *       1 / 2 = fused fp32 CUDA-core kernel with 64 / 256 nodes per block;
- *       3 = tensor-core path, coord_mlp.0 only on tcgen05 (3xTF32 split: fp32-level accuracy) = edge
- *           kernel + node kernel, needs agg_ws [num_nodes][32] floats of scratch;
- *       4 = tensor-core path with all three per-edge contractions (first edge Linear's geometry
- *           block, the heads' second Linear, coord_mlp.0) on tcgen05, 3xTF32; needs agg_ws. */
+ * impl: 0 = auto (the tensor-core path if agg_ws != NULL, else the fused CUDA-core kernel);
+ *       1 / 2 = fused fp32 CUDA-core kernel with 64 / 256 nodes per block (edge, reduce and node phases
+ *           in one launch);
+ *       3 = tensor-core path: edge kernel (first edge Linear's geometry block, the heads' second Linear
+ *           and coord_mlp.0 on tcgen05 with the A operand handed over through tensor memory, 3xTF32 =
+ *           fp32-level accuracy; streaming in-order segment sums) + node kernel (node MLP, residual, next
+ *           layer's P/Q or embedding_out, also tcgen05); needs agg_ws [num_nodes][32] floats of scratch.
+ *       3 | EGSPR_IMPL_EDGE_ONLY = the edge kernel of impl 3 alone (writes agg_ws, x4_out, x3_out; no node
+ *           update) -- for benchmarks and profiling of that kernel. */
+#define EGSPR_IMPL_EDGE_ONLY 0x100
 int egspr_egcl_forward(const float *h, const float *x4, const float *P, const float *Q,
                        const int32_t *csr_ptr, const int32_t *csr_row, const int32_t *csr_col,
                        const int32_t *csr_eid, const float *edge_attr, float edge_attr_const,

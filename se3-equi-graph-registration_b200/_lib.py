@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("EGSPR_LIB_PATH") or os.path.join(_HERE, "libegspr_b200.so")   # override: developer A/B builds
-SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_layer_tc.cu", "egnn_edge_mma.cu", "egnn_edge_ts.cu", "egnn_node_ts.cu", "head.cu"]
+SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_edge_ts.cu", "egnn_node_ts.cu", "head.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1,4 +1,4 @@
-// E_GCL edge kernel, impl 5: all three per-edge contractions on tcgen05 with the A operand handed
+// E_GCL edge kernel of the tensor-core path (impl 3): all three per-edge contractions on tcgen05 with the A operand handed
 // to the tensor core THROUGH TENSOR MEMORY (tcgen05.st -> tcgen05.mma [d], [a_tmem], b_desc), and a
 // streaming segment reduction that writes finished aggregation rows straight to global memory.
 //
@@ -436,7 +436,7 @@ extern "C" int egspr_debug_read_ts(long long *host_dst) {
 }
 #endif
 
-int launch_layer_ts(const LayerArgs &a, float *agg_ws, cudaStream_t st) {
+int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(egcl_edge_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM_BYTES) != cudaSuccess)
@@ -449,6 +449,7 @@ int launch_layer_ts(const LayerArgs &a, float *agg_ws, cudaStream_t st) {
     if (grid > need) grid = need;
     egcl_edge_ts_kernel<<<(unsigned)grid, V_THREADS, V_SMEM_BYTES, st>>>(a, agg_ws);
     if (cudaGetLastError() != cudaSuccess) return EGSPR_E_LAUNCH;
+    if (edge_only) return EGSPR_OK;      // bench / profiling: the edge stage alone (agg_ws, x4_out written)
     return launch_node_update_ts(a, agg_ws, st);
 }
 

@@ -34,10 +34,16 @@ class RegistrationEngine:
         G, E = C * N, C * N * self.k
         f32, i32 = torch.float32, torch.int32
         z = lambda *s, dt=f32: torch.empty(s, dtype=dt, device=dev)
-        # inputs (clouds-major)
-        self.feat = z(C, N, H); self.x = z(C, N, 3)
-        self.labels = torch.zeros(B, N, dtype=f32, device=dev)
-        self.gt_pose = torch.eye(4, dtype=f32, device=dev).repeat(B, 1, 1).contiguous()
+        # inputs (clouds-major), two sets: set 0 is the one register()/load()/run() use; submit() alternates
+        # between them so the next batch's host->device copy overlaps the current batch's kernels
+        self._in = [dict(feat=z(C, N, H), x=z(C, N, 3), labels=torch.zeros(B, N, dtype=f32, device=dev),
+                         gt_pose=torch.eye(4, dtype=f32, device=dev).repeat(B, 1, 1).contiguous()) for _ in range(2)]
+        self._set = 0
+        self._bind_inputs(0)
+        self._copy_stream = None
+        self._set_free = [None, None]        # event: the kernels that read input set s have finished
+        self._host_out = None
+        self._tickets = 0
         # graph
         self.nbr = z(C, N, self.k, dt=i32)
         self.knn_ws_bytes = _lib.lib().egspr_knn_workspace_bytes(C, N)
@@ -55,10 +61,15 @@ class RegistrationEngine:
         # outputs
         self.R = z(B, 3, 3); self.t = z(B, 3); self.Hm = z(B, 3, 3); self.w = z(B, N); self.loss_parts = z(B, 2)
         self.h_out = None
-        self._graph = None
-        self._graph_key = None
+        self._graph = [None, None]
+        self._graph_key = [None, None]
         self.impl = 0
         self.launches_per_step = 0
+
+    def _bind_inputs(self, s):
+        self._set = s
+        d = self._in[s]
+        self.feat, self.x, self.labels, self.gt_pose = d["feat"], d["x"], d["labels"], d["gt_pose"]
 
     # ---- input staging -----------------------------------------------------------------------
     def load(self, src_feat, src_pts, tgt_feat, tgt_pts, labels=None, gt_pose=None):
@@ -104,7 +115,7 @@ class RegistrationEngine:
                 p(self.h[nxt]), p(self.x4[nxt]), p(self.x_out) if last else None,
                 None if last else p(self.P[nxt]), None if last else p(self.Q[nxt]), p(self.agg_ws), int(self.impl), st),
                 "egspr_egcl_forward")
-            n_launch += 2 if self.impl in (0, 3, 4, 5) else 1
+            n_launch += 2 if self.impl in (0, 3) else 1
             cur = nxt
         self.h_out = self.h[cur].view(C, N, H)
         ho, xo = self.h_out, self.x_out
@@ -123,20 +134,61 @@ class RegistrationEngine:
             packs = self.model.egnn.packs()
             key = tuple(t.data_ptr() for t in packs[0]) + (packs[1].data_ptr(), packs[2].data_ptr(),
                                                            self.model._pack_head.get().data_ptr(), self.impl)
-            if self._graph is None or key != self._graph_key:
+            s = self._set
+            if self._graph[s] is None or key != self._graph_key[s]:
                 self._enqueue()                      # warm-up outside capture (function attributes, lazy init)
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue()
-                self._graph, self._graph_key = g, key
-            self._graph.replay()
+                self._graph[s], self._graph_key[s] = g, key
+            self._graph[s].replay()
 
     def register(self, src_feat, src_pts, tgt_feat, tgt_pts, labels=None, gt_pose=None):
         """Full step: stage inputs, run, return (R [B,3,3], t [B,3]) device tensors."""
+        self._bind_inputs(0)
         self.load(src_feat, src_pts, tgt_feat, tgt_pts, labels, gt_pose)
         self.run()
         return self.R, self.t
+
+    # ---- pipelined host-to-host path ------------------------------------------------------------
+    def submit(self, src_feat, src_pts, tgt_feat, tgt_pts, labels=None, gt_pose=None):
+        """Enqueue one batch given as HOST (pinned) tensors: H2D on a copy stream into the free input set,
+        the hot path on the current stream, (R, t) back to pinned host buffers.  Returns a ticket for
+        collect().  Up to two batches are in flight, so batch i+1's upload overlaps batch i's kernels
+        (the reference's loop uploads, computes and downloads strictly in turn, evl:1126-1250)."""
+        with torch.cuda.device(self.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._host_out = [(torch.empty((self.B, 3, 3), dtype=torch.float32).pin_memory(),
+                                   torch.empty((self.B, 3), dtype=torch.float32).pin_memory()) for _ in range(2)]
+            s = self._tickets & 1
+            self._tickets += 1
+            cur = torch.cuda.current_stream()
+            cs = self._copy_stream
+            if self._set_free[s] is not None:
+                cs.wait_event(self._set_free[s])      # the kernels that read this input set two batches ago are done
+            self._bind_inputs(s)
+            with torch.cuda.stream(cs):
+                self.load(src_feat, src_pts, tgt_feat, tgt_pts, labels, gt_pose)
+                uploaded = torch.cuda.Event()
+                uploaded.record(cs)
+            cur.wait_event(uploaded)
+            self.run()
+            Rh, th = self._host_out[s]
+            Rh.copy_(self.R, non_blocking=True)
+            th.copy_(self.t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+            self._set_free[s] = done
+            return (s, done)
+
+    def collect(self, ticket):
+        """Wait for a submitted batch; returns its (R [B,3,3], t [B,3]) pinned HOST tensors (valid until the
+        second-next submit())."""
+        s, done = ticket
+        done.synchronize()
+        return self._host_out[s]
 
     def outputs(self):
         B = self.B

@@ -144,7 +144,7 @@ def test_unsorted_segment_sum_matches_and_is_deterministic():
 # EGNN / E_GCL modules (a3-a11) vs the reference golden vectors
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_forward_eval_matches_reference_golden(golden_dir, name, impl):
     g, ck = load_case(golden_dir, name)
     model = P.build_model(ck, device=DEV, variant="eval")
@@ -221,7 +221,7 @@ def test_egnn_and_egcl_module_signatures(golden_dir, model):
     assert ea_out.shape == ea2.shape
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 def test_twin_points_stay_bit_identical(model, impl):
     """Exact duplicate correspondences ("twins": same coordinates AND features, normal in the datasets,
     datasets/ThreeDMatch.py:319,329) whose incoming-edge sets coincide must stay bit-identical through
@@ -395,3 +395,27 @@ def test_full_batch_properties(model):
     e1 = P.RegistrationEngine(model, batch=1, n=N, k=16, use_graph=False)
     e1.register(*[data[k][7:8] for k in keys])
     assert torch.equal(e1.R[0], R1[7]) and torch.equal(e1.t[0], t1[7])
+
+
+def test_engine_submit_collect_pipeline_matches_register(model):
+    """Pipelined host-to-host path (two input sets, upload on a copy stream) == the plain register() call,
+    batch after batch, in order."""
+    B, N = 3, 1024
+    keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "labels", "gt_pose")
+    batches = [P.synthetic.make_batch(40 + i, B, n=N, pin=True) for i in range(5)]
+    ref_eng = P.RegistrationEngine(model, batch=B, n=N, k=16, use_graph=False)
+    want = []
+    for b in batches:
+        R, t = ref_eng.register(*[b[k] for k in keys])
+        want.append((R.cpu().clone(), t.cpu().clone()))
+    eng = P.RegistrationEngine(model, batch=B, n=N, k=16, use_graph=True)
+    got, tk = [], eng.submit(*[batches[0][k] for k in keys])
+    for b in batches[1:]:
+        nxt = eng.submit(*[b[k] for k in keys])
+        R, t = eng.collect(tk)
+        got.append((R.clone(), t.clone()))
+        tk = nxt
+    R, t = eng.collect(tk)
+    got.append((R.clone(), t.clone()))
+    for (Rw, tw), (Rg, tg) in zip(want, got):
+        assert torch.equal(Rw, Rg) and torch.equal(tw, tg)

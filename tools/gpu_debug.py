@@ -97,7 +97,7 @@ def main():
     B, N, K = 64, 2048, 16
     model = P.build_model(os.path.join(G, "checkpoint-3dmatch.pth"), device=dev)
     data = P.synthetic.make_batch(5, B, n=N, pin=True)
-    for impl in (3, 4, 5):
+    for impl in (1, 3):
         eng = P.RegistrationEngine(model, batch=B, n=N, k=K, use_graph=False)
         eng.impl = impl
         eng.load(data["src_feat"], data["src_pts"], data["tgt_feat"], data["tgt_pts"], data["labels"], data["gt_pose"])
@@ -138,7 +138,7 @@ def main():
     print("csr      ms", timeit(lambda: ops.csr_from_nbr(eng.nbr)))
     layers, pin, pout = model.egnn.packs()
     gr = ops.csr_from_nbr(eng.nbr)
-    for impl in (3, 4, 5):
+    for impl in (1, 3):
         print(f"egnn impl={impl} (embed+3 layers) ms", timeit(lambda: ops.egnn_forward(eng.feat, eng.x, gr, layers, pin, pout, impl=impl)))
     ho, xo = ops.egnn_forward(eng.feat, eng.x, gr, layers, pin, pout)
     print("head     ms", timeit(lambda: ops.head_eval(eng.feat[:B], eng.feat[B:], eng.x[:B], eng.x[B:], ho[:B], ho[B:], xo[:B], xo[B:],

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import se3_equi_graph_registration_b200 as P
 import bench
-impls = [int(x) for x in os.environ.get("EGSPR_IMPLS", "3,4,5").split(",")]
+impls = [int(x) for x in os.environ.get("EGSPR_IMPLS", "1,3").split(",")]
 B = int(os.environ.get("EGSPR_B", "64")); N = int(os.environ.get("EGSPR_N", "2048"))
 model = P.build_model(bench.CKPT, device="cuda:0")
 data = P.synthetic.make_batch(5, B, n=N)

@@ -9,7 +9,7 @@ import bench
 model = P.build_model(bench.CKPT, device="cuda:0")
 data = P.synthetic.make_batch(5, 64, n=2048)
 eng = P.RegistrationEngine(model, batch=64, n=2048, k=16, use_graph=False)
-eng.impl = 5
+eng.impl = 3
 for _ in range(3):
     eng.register(*[data[k] for k in ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "labels", "gt_pose")])
 torch.cuda.synchronize()
