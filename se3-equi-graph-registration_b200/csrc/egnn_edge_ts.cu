@@ -31,7 +31,10 @@
 namespace egspr {
 using namespace tc;
 
-constexpr int V_GROUPS = 4;
+#ifndef EGSPR_V_GROUPS
+#define EGSPR_V_GROUPS 4            // 512 threads x 128 registers; 5 groups (96 registers) measured 10 % slower (spills)
+#endif
+constexpr int V_GROUPS = EGSPR_V_GROUPS;
 constexpr int V_THREADS = 128 * V_GROUPS;
 constexpr int V_MROW = 36;            // floats per row of the message tile (144 B: conflict-free STS.128)
 
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem_g = *tmem_holder + 128u * grp;                  // this group's 128 columns
+    const uint32_t tmem_g = *tmem_holder + 96u * grp;                   // this group's 96 columns (D | A_hi | A_lo)
     const uint32_t tmem_w = tmem_g + ((uint32_t)(hw * 32) << 16);       // ... at this warp's 32 lanes
     const uint32_t tD = tmem_g, tAhi = tmem_g + 32, tAlo = tmem_g + 64;
     const uint64_t dX1 = make_desc_sw128(smem_u32(base + VS_W));
