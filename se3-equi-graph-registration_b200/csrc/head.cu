@@ -11,6 +11,7 @@
 namespace egspr {
 
 constexpr int HD_THREADS = 256;
+constexpr int HD_MAX_N = 48 * 1024;   // n floats of dynamic shared memory (<= 192 KB); larger clouds stage in w_out
 constexpr int HD_WARPS = HD_THREADS / 32;
 
 struct BlockScratch {
@@ -236,9 +237,10 @@ struct HeadEvalArgs {
 __global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
-    float *ssim = dyn;            // [n] sim0, later the weights
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t nb = (size_t)b * n;
+    // [n] sim0, later the weights: shared memory, or (n > HD_MAX_N) this pair's row of w_out in global memory
+    float *ssim = (n > HD_MAX_N) ? a.w_out + nb : dyn;
     // 1. input-feature similarity (evl:691)
     unsigned long long best = 0ull;
     for (int i = tid; i < n; i += HD_THREADS) {
@@ -365,9 +367,9 @@ struct HeadTrainArgs {
 __global__ void __launch_bounds__(HD_THREADS) head_train_kernel(const HeadTrainArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
-    float *ssim = dyn;
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
     const size_t nb = (size_t)b * n;
+    float *ssim = (n > HD_MAX_N) ? a.w_out + nb : dyn;
     float mx = -3.4e38f;
     float cnt[1] = {0.f};
     for (int i = tid; i < n; i += HD_THREADS) {
@@ -422,8 +424,6 @@ __global__ void __launch_bounds__(HD_THREADS) kabsch_kernel(const float *__restr
                  Hout ? Hout + b * 9 : nullptr, sc);
 }
 
-constexpr int HD_MAX_N = 48 * 1024;   // n floats of dynamic shared memory (<= 192 KB)
-
 template <class K>
 static int ensure_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -457,8 +457,8 @@ extern "C" int egspr_head_eval(const float *feat_src, const float *feat_tgt, con
         n <= 0 || top_k <= 0)
         return EGSPR_E_INVALID;
     if (loss_parts && (!x_out_src || !x_out_tgt || !labels || !gt_pose)) return EGSPR_E_INVALID;
-    if (n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
-    const size_t smem = sizeof(float) * (size_t)n;
+    if (n > HD_MAX_N && !w_out) return EGSPR_E_WORKSPACE;      // large clouds: the weights row doubles as scratch
+    const size_t smem = n > HD_MAX_N ? 0 : sizeof(float) * (size_t)n;
     if (int e = ensure_smem(head_eval_kernel, smem)) return e;
     HeadEvalArgs a{feat_src, feat_tgt, x_src, x_tgt, h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose,
                    head_pack, n, top_k, w_out, R, t, Hout, loss_parts};
@@ -475,8 +475,8 @@ extern "C" int egspr_head_train(const float *h_out_src, const float *h_out_tgt, 
     if (!h_out_src || !h_out_tgt || !x_out_src || !x_out_tgt || !labels || !R || !t || pairs <= 0 || n <= 0)
         return EGSPR_E_INVALID;
     if (loss_parts && !gt_pose) return EGSPR_E_INVALID;
-    if (n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
-    const size_t smem = sizeof(float) * (size_t)n;
+    if (n > HD_MAX_N && !w_out) return EGSPR_E_WORKSPACE;
+    const size_t smem = n > HD_MAX_N ? 0 : sizeof(float) * (size_t)n;
     if (int e = ensure_smem(head_train_kernel, smem)) return e;
     HeadTrainArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose, n, w_out, sim_out, R, t, Hout, loss_parts};
     head_train_kernel<<<pairs, HD_THREADS, smem, (cudaStream_t)stream>>>(a);
