@@ -102,6 +102,9 @@ int egspr_node_embed(const float *feat, const float *x3, int64_t num_nodes, cons
  *           and coord_mlp.0 on tcgen05 with the A operand handed over through tensor memory, 3xTF32 =
  *           fp32-level accuracy; streaming in-order segment sums) + node kernel (node MLP, residual, next
  *           layer's P/Q or embedding_out, also tcgen05); needs agg_ws [num_nodes][32] floats of scratch.
+ *       4 = impl 3 with the edge kernel in reduced precision (BASELINE config 2's "looser bound" edge MLP):
+ *           single-pass TF32 operands (10-bit mantissa, round to nearest) and SiLU through MUFU.TANH;
+ *           segment sums, node kernel and everything else as in impl 3.
  *       3 | EGSPR_IMPL_EDGE_ONLY = the edge kernel of impl 3 alone (writes agg_ws, x4_out, x3_out; no node
  *           update) -- for benchmarks and profiling of that kernel. */
 #define EGSPR_IMPL_EDGE_ONLY 0x100

@@ -80,6 +80,40 @@ __device__ __forceinline__ void store_hilo_tmem(uint32_t t_hi, uint32_t t_lo, co
     }
 }
 
+// ---- reduced-precision mode (FAST): single-pass TF32 (operands rounded to nearest, 10-bit mantissa) and
+// SiLU through MUFU.TANH (rel. error 2^-11, the same order as the operand rounding) ----
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void store_tf32_tmem(uint32_t t_hi, const float (&v)[32]) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        float hi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hi[i] = tf32_rna(v[16 * b + i]);
+        tmem_st16(t_hi + 16 * b, hi);
+    }
+}
+__device__ __forceinline__ void silu2_tanh(float &x0, float &x1) {
+    // x * sigmoid(x) = h + h * tanh(h), h = x / 2
+    fmul2(x0, x1, 0.5f, 0.5f);
+    float t0, t1;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(x0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(x1));
+    ffma2(x0, x1, x0, x1, t0, t1);
+}
+template <bool FAST>
+__device__ __forceinline__ void silu_pair(float &x0, float &x1) {
+    if constexpr (FAST) silu2_tanh(x0, x1);
+    else silu2(x0, x1);
+}
+__device__ __forceinline__ void issue_1xtf32_ts(uint32_t d, uint32_t ahi, uint64_t whi) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_tf32_ts(d, ahi + 8 * k, whi + 2 * k, IDESC_TF32_M128_N32, k > 0);
+}
+
 // D = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T over K = 32 (4 K-blocks of 8 columns)
 __device__ __forceinline__ void issue_3xtf32_ts(uint32_t d, uint32_t ahi, uint32_t alo, uint64_t whi, uint64_t wlo) {
 #pragma unroll
@@ -90,6 +124,7 @@ __device__ __forceinline__ void issue_3xtf32_ts(uint32_t d, uint32_t ahi, uint32
     for (int k = 0; k < 4; ++k) umma_tf32_ts(d, ahi + 8 * k, wlo + 2 * k, IDESC_TF32_M128_N32, 1);
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerArgs a, float *__restrict__ agg_out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -114,18 +149,18 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             float w = 0.f;
             if (kk < 12) w = __ldg(a.layer_pack + OFF_WG + 32 * kk + o);
             else if (kk == 12) w = __ldg(a.layer_pack + OFF_WEA + o);
-            const float hi = tf32_hi(w);
+            const float hi = FAST ? tf32_rna(w) : tf32_hi(w);
             *reinterpret_cast<float *>(base + VS_W + sw128_off(o, k)) = (k < 16) ? hi : (w - hi);
         }
         {   // stage 2: block-diagonal of the heads' second Linear, pack layout [head][in][out]
             const float w = ((o >> 3) == (k >> 3)) ? __ldg(a.layer_pack + OFF_W2P + 64 * (o >> 3) + 8 * (k & 7) + (o & 7)) : 0.f;
-            const float hi = tf32_hi(w);
+            const float hi = FAST ? tf32_rna(w) : tf32_hi(w);
             *reinterpret_cast<float *>(base + VS_W + 4096 + sw128_off(o, k)) = hi;
             *reinterpret_cast<float *>(base + VS_W + 8192 + sw128_off(o, k)) = w - hi;
         }
         {   // stage 3: coord_mlp.0.weight [out][in]
             const float w = __ldg(a.layer_pack + OFF_WC1 + i);
-            const float hi = tf32_hi(w);
+            const float hi = FAST ? tf32_rna(w) : tf32_hi(w);
             *reinterpret_cast<float *>(base + VS_W + 12288 + sw128_off(o, k)) = hi;
             *reinterpret_cast<float *>(base + VS_W + 16384 + sw128_off(o, k)) = w - hi;
         }
@@ -265,10 +300,16 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             geo[9] = az; geo[10] = bz; geo[11] = ez;
             geo[12] = ea; geo[13] = 0.f; geo[14] = 0.f; geo[15] = 0.f;
             float hi[16], lo[16];
+            if constexpr (FAST) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { hi[i] = tf32_hi(geo[i]); lo[i] = geo[i] - hi[i]; }
-            tmem_st16(tmem_w + 32, hi);          // A_hi columns 0..15  = hi(geo)
-            tmem_st16(tmem_w + 48, lo);          // A_hi columns 16..31 = lo(geo)
+                for (int i = 0; i < 16; ++i) hi[i] = tf32_rna(geo[i]);
+                tmem_st16(tmem_w + 32, hi);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { hi[i] = tf32_hi(geo[i]); lo[i] = geo[i] - hi[i]; }
+                tmem_st16(tmem_w + 32, hi);          // A_hi columns 0..15  = hi(geo)
+                tmem_st16(tmem_w + 48, lo);          // A_hi columns 16..31 = lo(geo)
+            }
         }
         tmem_wait_st();
         fence_before_sync();
@@ -279,10 +320,12 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             fence_after_sync();
             umma_tf32_ts(tD, tAhi + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
             umma_tf32_ts(tD, tAhi + 8, dX1 + 2, IDESC_TF32_M128_N32, 1);
-            umma_tf32_ts(tD, tAhi + 16, dX1 + 0, IDESC_TF32_M128_N32, 1);     // lo x Whi
-            umma_tf32_ts(tD, tAhi + 24, dX1 + 2, IDESC_TF32_M128_N32, 1);
-            umma_tf32_ts(tD, tAhi + 0, dX1 + 4, IDESC_TF32_M128_N32, 1);      // hi x Wlo
-            umma_tf32_ts(tD, tAhi + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
+            if constexpr (!FAST) {
+                umma_tf32_ts(tD, tAhi + 16, dX1 + 0, IDESC_TF32_M128_N32, 1);     // lo x Whi
+                umma_tf32_ts(tD, tAhi + 24, dX1 + 2, IDESC_TF32_M128_N32, 1);
+                umma_tf32_ts(tD, tAhi + 0, dX1 + 4, IDESC_TF32_M128_N32, 1);      // hi x Wlo
+                umma_tf32_ts(tD, tAhi + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
+            }
             umma_commit(mbar);
         }
         // stage csr_ptr[nstart ...] of this tile's rows for the segment sums (visible after barriers 2, 3)
@@ -299,10 +342,11 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         for (int i = 0; i < 8; ++i) {   // + P[row] + Q[col], SiLU  (:203-206)
             fadd2(pv[i].x, pv[i].y, qv[i].x, qv[i].y); fadd2(pv[i].z, pv[i].w, qv[i].z, qv[i].w);
             fadd2(v[4 * i], v[4 * i + 1], pv[i].x, pv[i].y); fadd2(v[4 * i + 2], v[4 * i + 3], pv[i].z, pv[i].w);
-            silu2(v[4 * i], v[4 * i + 1]); silu2(v[4 * i + 2], v[4 * i + 3]);
+            silu_pair<FAST>(v[4 * i], v[4 * i + 1]); silu_pair<FAST>(v[4 * i + 2], v[4 * i + 3]);
         }
         // ---------------- stage 2: per-head second Linear (block-diagonal) ----------------
-        store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
+        if constexpr (FAST) store_tf32_tmem(tmem_w + 32, v);
+        else store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
         tmem_wait_st();
         fence_before_sync();
         TS_MARK(5);
@@ -310,7 +354,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(6);
         if (ht == 0) {
             fence_after_sync();
-            issue_3xtf32_ts(tD, tAhi, tAlo, dW2hi, dW2lo);
+            if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW2hi);
+            else issue_3xtf32_ts(tD, tAhi, tAlo, dW2hi, dW2lo);
             umma_commit(mbar);
         }
         {   // the next tile's endpoint coordinates travel while stages 2 and 3 run
@@ -347,7 +392,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             }
         }
         // ---------------- stage 3: coord_mlp.0; messages also to shared memory ----------------
-        store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
+        if constexpr (FAST) store_tf32_tmem(tmem_w + 32, v);
+        else store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4 *>(mt + ht * V_MROW + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -358,7 +404,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(9);
         if (ht == 0) {
             fence_after_sync();
-            issue_3xtf32_ts(tD, tAhi, tAlo, dW3hi, dW3lo);
+            if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW3hi);
+            else issue_3xtf32_ts(tD, tAhi, tAlo, dW3hi, dW3lo);
             umma_commit(mbar);
         }
         // ---- feature segment sums while the tensor core works: 8 threads per aggregation row (4 features
@@ -400,7 +447,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         for (int o = 0; o < 32; o += 4) {
             const float4 b = *reinterpret_cast<const float4 *>(sbc1 + o), wc = *reinterpret_cast<const float4 *>(swc2 + o);
             fadd2(v[o], v[o + 1], b.x, b.y); fadd2(v[o + 2], v[o + 3], b.z, b.w);
-            silu2(v[o], v[o + 1]); silu2(v[o + 2], v[o + 3]);
+            silu_pair<FAST>(v[o], v[o + 1]); silu_pair<FAST>(v[o + 2], v[o + 3]);
             ffma2(s4[0], s4[1], v[o], v[o + 1], wc.x, wc.y); ffma2(s4[2], s4[3], v[o + 2], v[o + 3], wc.z, wc.w);
         }
         const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
@@ -439,10 +486,11 @@ extern "C" int egspr_debug_read_ts(long long *host_dst) {
 }
 #endif
 
-int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, cudaStream_t st) {
+int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, bool fast, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(egcl_edge_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(egcl_edge_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(egcl_edge_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM_BYTES) != cudaSuccess)
             return EGSPR_E_LAUNCH;
         configured = true;
     }
@@ -450,7 +498,8 @@ int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, cudaStrea
     int64_t grid = sm_count();
     const int64_t need = (a.num_nodes + 63) / 64;
     if (grid > need) grid = need;
-    egcl_edge_ts_kernel<<<(unsigned)grid, V_THREADS, V_SMEM_BYTES, st>>>(a, agg_ws);
+    if (fast) egcl_edge_ts_kernel<true><<<(unsigned)grid, V_THREADS, V_SMEM_BYTES, st>>>(a, agg_ws);
+    else egcl_edge_ts_kernel<false><<<(unsigned)grid, V_THREADS, V_SMEM_BYTES, st>>>(a, agg_ws);
     if (cudaGetLastError() != cudaSuccess) return EGSPR_E_LAUNCH;
     if (edge_only) return EGSPR_OK;      // bench / profiling: the edge stage alone (agg_ws, x4_out written)
     return launch_node_update_ts(a, agg_ws, st);

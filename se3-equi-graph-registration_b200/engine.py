@@ -115,7 +115,7 @@ class RegistrationEngine:
                 p(self.h[nxt]), p(self.x4[nxt]), p(self.x_out) if last else None,
                 None if last else p(self.P[nxt]), None if last else p(self.Q[nxt]), p(self.agg_ws), int(self.impl), st),
                 "egspr_egcl_forward")
-            n_launch += 2 if self.impl in (0, 3) else 1
+            n_launch += 2 if self.impl in (0, 3, 4) else 1
             cur = nxt
         self.h_out = self.h[cur].view(C, N, H)
         ho, xo = self.h_out, self.x_out
