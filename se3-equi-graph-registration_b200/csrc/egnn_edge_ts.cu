@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     const uint32_t mbar = smem_u32(gb + VG_MBAR);
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(base + VS_TMEM);
     const int bar_id = 1 + grp;
+    pdl_trigger();                  // the next kernel's prologue may overlap this kernel's tail
 
     // ---- one-time setup: swizzled hi/lo weight tiles (B operands: row = output o, K = input) ----
     for (int i = tid; i < 1024; i += V_THREADS) {
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    pdl_wait();                     // everything above touched only static weights / on-chip state
     const uint32_t tmem_g = *tmem_holder + 96u * grp;                   // this group's 96 columns (D | A_hi | A_lo)
     const uint32_t tmem_w = tmem_g + ((uint32_t)(hw * 32) << 16);       // ... at this warp's 32 lanes
     const uint32_t tD = tmem_g, tAhi = tmem_g + 32, tAlo = tmem_g + 64;
@@ -498,9 +500,9 @@ int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, bool fast
     int64_t grid = sm_count();
     const int64_t need = (a.num_nodes + 63) / 64;
     if (grid > need) grid = need;
-    if (fast) egcl_edge_ts_kernel<true><<<(unsigned)grid, V_THREADS, V_SMEM_BYTES, st>>>(a, agg_ws);
-    else egcl_edge_ts_kernel<false><<<(unsigned)grid, V_THREADS, V_SMEM_BYTES, st>>>(a, agg_ws);
-    if (cudaGetLastError() != cudaSuccess) return EGSPR_E_LAUNCH;
+    const cudaError_t le = fast ? launch_pdl(egcl_edge_ts_kernel<true>, dim3((unsigned)grid), dim3(V_THREADS), V_SMEM_BYTES, st, a, agg_ws)
+                                : launch_pdl(egcl_edge_ts_kernel<false>, dim3((unsigned)grid), dim3(V_THREADS), V_SMEM_BYTES, st, a, agg_ws);
+    if (le != cudaSuccess || cudaGetLastError() != cudaSuccess) return EGSPR_E_LAUNCH;
     if (edge_only) return EGSPR_OK;      // bench / profiling: the edge stage alone (agg_ws, x4_out written)
     return launch_node_update_ts(a, agg_ws, st);
 }

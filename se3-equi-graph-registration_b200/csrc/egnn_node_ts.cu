@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(base + NS_TMEM);
     const bool do_s1 = a.agg != nullptr, do_s2 = a.w2t != nullptr;
     const int n3 = a.w3pt ? (a.w3qt ? 64 : 32) : 0;
+    pdl_trigger();                  // the next kernel's prologue may overlap this kernel's tail
 
     // ---- weight tiles (hi / lo, swizzled) ----
     if (do_s1) {
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    pdl_wait();                     // everything above touched only static weights / on-chip state
     const uint32_t tg = *tmem_holder + NT_COLS * grp;
     const uint32_t tw = tg + ((uint32_t)(hw * 32) << 16);
     const uint64_t dW1Ahi = make_desc_sw128(smem_u32(base + NS_W1A)), dW1Alo = make_desc_sw128(smem_u32(base + NS_W1A + 4096));
@@ -219,8 +221,8 @@ static int launch_node_ts(const NodeTsArgs &a, cudaStream_t st) {
     const int64_t tiles = (a.G + 127) / 128;
     int64_t grid = (tiles + NT_GROUPS - 1) / NT_GROUPS;
     if (grid > sm_count()) grid = sm_count();
-    egnn_node_ts_kernel<<<(unsigned)grid, NT_THREADS, NT_SMEM_BYTES, st>>>(a);
-    return cudaGetLastError() == cudaSuccess ? EGSPR_OK : EGSPR_E_LAUNCH;
+    const cudaError_t le = launch_pdl(egnn_node_ts_kernel, dim3((unsigned)grid), dim3(NT_THREADS), NT_SMEM_BYTES, st, a);
+    return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? EGSPR_OK : EGSPR_E_LAUNCH;
 }
 
 // node MLP + residual + next P/Q (or embedding_out) after the edge kernel of a layer

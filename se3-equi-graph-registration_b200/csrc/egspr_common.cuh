@@ -103,6 +103,25 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl may start its CTAs as soon as
+// every CTA of the kernel before it in the stream has called pdl_trigger() (or exited); it must call
+// pdl_wait() -- which returns once that kernel has COMPLETED and flushed -- before it touches any global
+// memory another kernel of the chain produces or consumes.  What runs before pdl_wait() (weight tiles,
+// TMEM allocation, barrier init) overlaps the tail of the previous kernel, SM by SM.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {
