@@ -6,13 +6,17 @@
 //   train variant src/3dmatch_train_egnn_with_batch.py:696-758 (softmax of output-feature similarity
 //                 over the GT inliers, Kabsch on the EGNN coords)
 // and the cuSOLVER launch + `if det<0` host sync per pair (:741-751) with an in-kernel fp64 Jacobi SVD.
+#include <cstdlib>
+
 #include "egspr_common.cuh"
 
 namespace egspr {
 
-constexpr int HD_THREADS = 256;
+constexpr int HD_THREADS = 256;       // CTA size for clouds up to HD_BIG_N points
+constexpr int HD_THREADS_BIG = 1024;  // ... and beyond (one CTA still owns a pair; every loop strides by blockDim.x)
+constexpr int HD_BIG_N = 8192;
 constexpr int HD_MAX_N = 48 * 1024;   // n floats of dynamic shared memory (<= 192 KB); larger clouds stage in w_out
-constexpr int HD_WARPS = HD_THREADS / 32;
+constexpr int HD_WARPS = HD_THREADS_BIG / 32;     // scratch is sized for the largest CTA
 
 struct BlockScratch {
     float red[HD_WARPS][16];
@@ -36,7 +40,7 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], BlockScratch &sc) {
     if (threadIdx.x < NV) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < HD_WARPS; ++w) s += sc.red[w][threadIdx.x];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sc.red[w][threadIdx.x];
         sc.bc[threadIdx.x] = s;
     }
     __syncthreads();
@@ -52,7 +56,7 @@ __device__ __forceinline__ float block_max(float v, BlockScratch &sc) {
     __syncthreads();
     float m = sc.red[0][0];
 #pragma unroll
-    for (int w = 1; w < HD_WARPS; ++w) m = fmaxf(m, sc.red[w][0]);
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sc.red[w][0]);
     return m;
 }
 
@@ -143,7 +147,7 @@ __device__ void block_kabsch(const float *__restrict__ p, const float *__restric
                              const float *w, int n, int count, float *__restrict__ R, float *__restrict__ t,
                              float *__restrict__ Hout, BlockScratch &sc) {
     float c[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float wi = w[i];
         if (wi != 0.f) {
             c[0] = fmaf(wi, p[i * stride], c[0]); c[1] = fmaf(wi, p[i * stride + 1], c[1]); c[2] = fmaf(wi, p[i * stride + 2], c[2]);
@@ -152,7 +156,7 @@ __device__ void block_kabsch(const float *__restrict__ p, const float *__restric
     }
     block_sum<6>(c, sc);
     float hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float wi = w[i];
         if (wi != 0.f) {
             const float a0 = wi * (p[i * stride] - c[0]), a1 = wi * (p[i * stride + 1] - c[1]), a2 = wi * (p[i * stride + 2] - c[2]);
@@ -202,7 +206,7 @@ __device__ void block_equi_loss(const float *__restrict__ hs, const float *__res
         g[9 + i] = __ldg(gt + 4 * i + 3);
     }
     float acc[2] = {0.f, 0.f};
-    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float lab = __ldg(labels + i);
         const float x0 = xs[3 * i], x1 = xs[3 * i + 1], x2 = xs[3 * i + 2];
         float ch = 0.f;
@@ -234,7 +238,7 @@ struct HeadEvalArgs {
     float *w_out, *R, *t, *Hout, *loss_parts;
 };
 
-__global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArgs a) {
+__global__ void __launch_bounds__(HD_THREADS_BIG) head_eval_kernel(const HeadEvalArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArg
     float *ssim = (n > HD_MAX_N) ? a.w_out + nb : dyn;
     // 1. input-feature similarity (evl:691)
     unsigned long long best = 0ull;
-    for (int i = tid; i < n; i += HD_THREADS) {
+    for (int i = tid; i < n; i += blockDim.x) {
         const float s = dot32(a.feat_src + (nb + i) * H, a.feat_tgt + (nb + i) * H);
         ssim[i] = s;
         const unsigned long long cand = ((unsigned long long)order_key(s) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArg
     __syncthreads();
     if (tid == 0) {
         unsigned long long m = sc.red64[0];
-        for (int w = 1; w < HD_WARPS; ++w) m = sc.red64[w] > m ? sc.red64[w] : m;
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = sc.red64[w] > m ? sc.red64[w] : m;
         sc.u[0] = 0xffffffffu - (unsigned)(m & 0xffffffffull);   // i0
     }
     // 3. k-th largest key by 4-pass radix select (evl:694 topk, k=128)
@@ -268,9 +272,9 @@ __global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArg
     int want = kk;                 // rank (1-based, from the top) still to locate inside the prefix class
     for (int shift = 24; shift >= 0; shift -= 8) {
         __syncthreads();
-        sc.hist[tid] = 0;          // HD_THREADS == 256 bins
+        if (tid < 256) sc.hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += HD_THREADS) {
+        for (int i = tid; i < n; i += blockDim.x) {
             const unsigned key = order_key(ssim[i]);
             if ((key & pmask) == prefix) atomicAdd(&sc.hist[(key >> shift) & 0xffu], 1u);
         }
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArg
     // 5. final weights: members of the top-k set take p0 when the (quirky) conditions hold (evl:761-768)
     float part[1] = {0.f};
     unsigned eq_carry = 0;       // equals seen in earlier index chunks
-    for (int base = 0; base < n; base += HD_THREADS) {
+    for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + tid;
         float s = 0.f;
         unsigned key = 0;
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArg
         if (lane == 0) sc.hist[warp] = __popc(bal);
         __syncthreads();
         unsigned before = eq_carry, total = 0;
-        for (int w = 0; w < HD_WARPS; ++w) { const unsigned c = sc.hist[w]; if (w < warp) before += c; total += c; }
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const unsigned c = sc.hist[w]; if (w < warp) before += c; total += c; }
         before += __popc(bal & ((1u << lane) - 1u));
         eq_carry += total;
         const bool member = (i < n) && (key > kth_key || (is_eq && (int)before < want));
@@ -333,17 +337,17 @@ __global__ void __launch_bounds__(HD_THREADS) head_eval_kernel(const HeadEvalArg
     block_sum<1>(part, sc);
     const float inv_s = 1.0f / (part[0] + 1e-6f);                                  // evl:771
     float mx = -3.4e38f;
-    for (int i = tid; i < n; i += HD_THREADS) { const float f = ssim[i] * inv_s; ssim[i] = f; mx = fmaxf(mx, f); }
+    for (int i = tid; i < n; i += blockDim.x) { const float f = ssim[i] * inv_s; ssim[i] = f; mx = fmaxf(mx, f); }
     mx = block_max(mx, sc);
     float z[1] = {0.f};
-    for (int i = tid; i < n; i += HD_THREADS) { const float e = expf(ssim[i] - mx); ssim[i] = e; z[0] += e; }   // softmax evl:774
+    for (int i = tid; i < n; i += blockDim.x) { const float e = expf(ssim[i] - mx); ssim[i] = e; z[0] += e; }   // softmax evl:774
     block_sum<1>(z, sc);
     const float inv_z = 1.0f / z[0];
     float sw[1] = {0.f};
-    for (int i = tid; i < n; i += HD_THREADS) { const float w = ssim[i] * inv_z; ssim[i] = w; sw[0] += w; }
+    for (int i = tid; i < n; i += blockDim.x) { const float w = ssim[i] * inv_z; ssim[i] = w; sw[0] += w; }
     block_sum<1>(sw, sc);
     const float inv_w = 1.0f / (sw[0] + 1e-6f);                                    // evl:783
-    for (int i = tid; i < n; i += HD_THREADS) {
+    for (int i = tid; i < n; i += blockDim.x) {
         const float w = ssim[i] * inv_w;
         ssim[i] = w;
         if (a.w_out) a.w_out[nb + i] = w;
@@ -364,7 +368,7 @@ struct HeadTrainArgs {
     float *w_out, *sim_out, *R, *t, *Hout, *loss_parts;
 };
 
-__global__ void __launch_bounds__(HD_THREADS) head_train_kernel(const HeadTrainArgs a) {
+__global__ void __launch_bounds__(HD_THREADS_BIG) head_train_kernel(const HeadTrainArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_train_kernel(const HeadTrainA
     float *ssim = (n > HD_MAX_N) ? a.w_out + nb : dyn;
     float mx = -3.4e38f;
     float cnt[1] = {0.f};
-    for (int i = tid; i < n; i += HD_THREADS) {
+    for (int i = tid; i < n; i += blockDim.x) {
         const float s = dot32(a.h_out_src + (nb + i) * H, a.h_out_tgt + (nb + i) * H);   // 3dm:681, 717
         if (a.sim_out) a.sim_out[nb + i] = s;
         const bool valid = __ldg(a.labels + nb + i) != 0.f;                              // 3dm:696
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_train_kernel(const HeadTrainA
     mx = block_max(mx, sc);
     block_sum<1>(cnt, sc);
     float z[1] = {0.f};
-    for (int i = tid; i < n; i += HD_THREADS) {
+    for (int i = tid; i < n; i += blockDim.x) {
         const float v = ssim[i];
         const float e = v > -3.0e38f ? expf(v - mx) : 0.f;                               // softmax over the valid set 3dm:718
         ssim[i] = e; z[0] += e;
@@ -390,10 +394,10 @@ __global__ void __launch_bounds__(HD_THREADS) head_train_kernel(const HeadTrainA
     block_sum<1>(z, sc);
     const float inv_z = z[0] > 0.f ? 1.0f / z[0] : 0.f;
     float sw[1] = {0.f};
-    for (int i = tid; i < n; i += HD_THREADS) { const float w = ssim[i] * inv_z; ssim[i] = w; sw[0] += w; }
+    for (int i = tid; i < n; i += blockDim.x) { const float w = ssim[i] * inv_z; ssim[i] = w; sw[0] += w; }
     block_sum<1>(sw, sc);
     const float inv_w = 1.0f / (sw[0] + 1e-6f);                                          // 3dm:724
-    for (int i = tid; i < n; i += HD_THREADS) {
+    for (int i = tid; i < n; i += blockDim.x) {
         const float w = ssim[i] * inv_w;
         ssim[i] = w;
         if (a.w_out) a.w_out[nb + i] = w;
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_train_kernel(const HeadTrainA
                         a.labels + nb, a.gt_pose + b * 16, n, a.loss_parts + b * 2, sc);
 }
 
-__global__ void __launch_bounds__(HD_THREADS) kabsch_kernel(const float *__restrict__ p, const float *__restrict__ q,
+__global__ void __launch_bounds__(HD_THREADS_BIG) kabsch_kernel(const float *__restrict__ p, const float *__restrict__ q,
                                                             const float *__restrict__ w, const float *__restrict__ mask,
                                                             int n, float *R, float *t, float *Hout) {
     extern __shared__ __align__(16) float dyn[];
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(HD_THREADS) kabsch_kernel(const float *__restr
     const int b = blockIdx.x;
     const size_t nb = (size_t)b * n;
     float cnt[1] = {0.f};
-    for (int i = threadIdx.x; i < n; i += HD_THREADS) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const bool inc = !mask || __ldg(mask + nb + i) != 0.f;
         dyn[i] = inc ? __ldg(w + nb + i) : 0.f;
         if (inc) cnt[0] += 1.f;
@@ -422,6 +426,12 @@ __global__ void __launch_bounds__(HD_THREADS) kabsch_kernel(const float *__restr
     block_sum<1>(cnt, sc);
     block_kabsch(p + nb * 3, q + nb * 3, 3, dyn, n, (int)(cnt[0] + 0.5f), R + b * 9, t + b * 3,
                  Hout ? Hout + b * 9 : nullptr, sc);
+}
+
+static int head_threads(int n) {
+    static const int forced = getenv("EGSPR_HEAD_THREADS") ? atoi(getenv("EGSPR_HEAD_THREADS")) : 0;   // developer switch
+    if (forced == 256 || forced == 512 || forced == 1024) return forced;
+    return n > HD_BIG_N ? HD_THREADS_BIG : HD_THREADS;
 }
 
 template <class K>
@@ -442,7 +452,7 @@ extern "C" int egspr_kabsch(const float *p, const float *q, const float *w, cons
     if (n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
     const size_t smem = sizeof(float) * (size_t)(n > 0 ? n : 1);
     if (int e = ensure_smem(kabsch_kernel, smem)) return e;
-    kabsch_kernel<<<pairs, HD_THREADS, smem, (cudaStream_t)stream>>>(p, q, w, mask, n, R, t, Hout);
+    kabsch_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(p, q, w, mask, n, R, t, Hout);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
@@ -462,7 +472,7 @@ extern "C" int egspr_head_eval(const float *feat_src, const float *feat_tgt, con
     if (int e = ensure_smem(head_eval_kernel, smem)) return e;
     HeadEvalArgs a{feat_src, feat_tgt, x_src, x_tgt, h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose,
                    head_pack, n, top_k, w_out, R, t, Hout, loss_parts};
-    head_eval_kernel<<<pairs, HD_THREADS, smem, (cudaStream_t)stream>>>(a);
+    head_eval_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
@@ -479,7 +489,7 @@ extern "C" int egspr_head_train(const float *h_out_src, const float *h_out_tgt, 
     const size_t smem = n > HD_MAX_N ? 0 : sizeof(float) * (size_t)n;
     if (int e = ensure_smem(head_train_kernel, smem)) return e;
     HeadTrainArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose, n, w_out, sim_out, R, t, Hout, loss_parts};
-    head_train_kernel<<<pairs, HD_THREADS, smem, (cudaStream_t)stream>>>(a);
+    head_train_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }

@@ -80,7 +80,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_warp_select_kernel(
 //           stop when the k-th best distance is strictly inside the scanned block (margin test with
 //           1e-4 relative slack) or the block covers the whole grid.
 // ================================================================================================
-constexpr int GRID_MAXC = 4096;
+constexpr int GRID_MAXC = 32768;      // upper bound of cells per cloud (shared-memory counters of the build CTA)
+// cell capacity reserved per cloud: the grid aims at ~4 points per cell (n/4 cells; the per-axis rounding can
+// overshoot, the build shrinks the grid until it fits)
+static inline int grid_capacity(int n) { return n < 1024 ? 1024 : (n > GRID_MAXC ? GRID_MAXC : n); }
 constexpr int GRID_BUILD_THREADS = 512;
 
 struct GridParams {        // per cloud, 16 floats
@@ -94,8 +97,8 @@ struct GridParams {        // per cloud, 16 floats
 
 __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
     const float *__restrict__ x, int n, float4 *__restrict__ sorted, int *__restrict__ cell_start,
-    GridParams *__restrict__ params) {
-    __shared__ int cnt[GRID_MAXC + 1];
+    GridParams *__restrict__ params, int maxc) {
+    extern __shared__ int cnt[];          // [maxc + 1]
     __shared__ float red[6][GRID_BUILD_THREADS / 32];
     __shared__ GridParams gp;
     __shared__ int wtot[GRID_BUILD_THREADS / 32];
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
         }
         if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
     }
-    for (int i = tid; i <= GRID_MAXC; i += GRID_BUILD_THREADS) cnt[i] = 0;
+    for (int i = tid; i <= maxc; i += GRID_BUILD_THREADS) cnt[i] = 0;
     __syncthreads();
     if (tid == 0) {
         float mn[3], ext[3];
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
         const float emax = fmaxf(fmaxf(ext[0], ext[1]), fmaxf(ext[2], 1e-30f));
         // cells wanted: ~4 points per cell; degenerate (flat) axes get a single cell
         float target = fmaxf(1.0f, (float)n * 0.25f);
-        if (target > (float)GRID_MAXC) target = (float)GRID_MAXC;
+        if (target > (float)maxc) target = (float)maxc;
         float e[3]; int live = 0; float vol = 1.0f;
         for (int a = 0; a < 3; ++a) { e[a] = ext[a]; if (e[a] > 1e-4f * emax) { ++live; vol *= e[a]; } }
         float c = live ? powf(vol / target, 1.0f / (float)live) : 1.0f;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
             if (d < 1) d = 1;
             dims[a] = d; total *= d;
         }
-        while (total > GRID_MAXC) {           // shrink the largest dimension until the grid fits
+        while (total > maxc) {           // shrink the largest dimension until the grid fits
             int am = 0;
             for (int a = 1; a < 3; ++a) if (dims[a] > dims[am]) am = a;
             total /= dims[am]; dims[am] -= 1; total *= dims[am];
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
     // exclusive scan of cnt[0..ncell) -> cell_start (global) and cursor (cnt reused)
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    int *cs_out = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    int *cs_out = cell_start + (size_t)cloud * (maxc + 1);
     for (int base = 0; base < ncell; base += GRID_BUILD_THREADS) {
         const int i = base + tid;
         const int v = i < ncell ? cnt[i] : 0;
@@ -204,13 +207,13 @@ constexpr int GQ_WARPS = 8;
 
 __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_kernel(
     const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
-    int n, int k, int32_t *__restrict__ nbr) {
+    int n, int k, int32_t *__restrict__ nbr, int maxc) {
     const int cloud = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qs = blockIdx.x * GQ_WARPS + warp;          // query = qs-th point in cell-sorted order
     if (qs >= n) return;
     const float4 *so = sorted + (size_t)cloud * n;
-    const int *cs = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    const int *cs = cell_start + (size_t)cloud * (maxc + 1);
     const GridParams gp = params[cloud];
     const float4 q = __ldg(so + qs);
     const int qi = __float_as_int(q.w);
@@ -321,13 +324,13 @@ __device__ __forceinline__ void knn_insert_batch(float d, int idx, int k, int la
 
 __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_flat_kernel(
     const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
-    int n, int k, int32_t *__restrict__ nbr) {
+    int n, int k, int32_t *__restrict__ nbr, int maxc) {
     const int cloud = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qs = blockIdx.x * GQ_WARPS + warp;          // query = qs-th point in cell-sorted order
     if (qs >= n) return;
     const float4 *so = sorted + (size_t)cloud * n;
-    const int *cs = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    const int *cs = cell_start + (size_t)cloud * (maxc + 1);
     const GridParams gp = params[cloud];
     const float4 q = __ldg(so + qs);
     const int qi = __float_as_int(q.w);
@@ -422,12 +425,12 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_flat_kernel(
 // (cell-sorted order: same or adjacent cells, similar trip counts) divides the cost per query.  The
 // sorted top-k list of a query lives E = 16/W entries per lane (position = lane_in_group * E + j).
 // Identical selection rule: total order (d2, index), same stopping test.
-template <int W>
+template <int W, int E>
 __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
-    int n, int k, int32_t *__restrict__ nbr, int merge_min) {
+    int n, int k, int32_t *__restrict__ nbr, int merge_min, int maxc) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int E = 16 / W;                      // list entries per lane
+    // E = list entries per lane: the list holds W * E >= k entries
     constexpr int QPW = 32 / W;                    // queries per warp
     constexpr unsigned GMASK = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
     const int cloud = blockIdx.y;
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     const int qs = (blockIdx.x * GQ_WARPS + warp) * QPW + sub;      // query = qs-th point in cell-sorted order
     const bool valid = qs < n;
     const float4 *so = sorted + (size_t)cloud * n;
-    const int *cs = cell_start + (size_t)cloud * (GRID_MAXC + 1);
+    const int *cs = cell_start + (size_t)cloud * (maxc + 1);
     const GridParams gp = params[cloud];
     const float4 q = __ldg(so + (valid ? qs : n - 1));
     const int qi = __float_as_int(q.w);
@@ -504,40 +507,40 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
                     idx = __float_as_int(c.w);
                 }
                 unsigned m = (__ballot_sync(FULL, d < thr_d || (d == thr_d && idx < thr_i)) >> sh) & GMASK;
-                if constexpr (W == 16) {
+                if constexpr (E == 1) {
                     // many candidates beat the k-th best (the first batches of a query): sort the batch with a
                     // bitonic network and merge it into the list in one go instead of inserting one by one
                     if (__any_sync(FULL, __popc(m) >= merge_min)) {
                         float sd = ((m >> sl) & 1u) ? d : 3e38f;          // non-passers cannot enter the list
                         int si = ((m >> sl) & 1u) ? idx : 0x7fffffff;
 #pragma unroll
-                        for (int size = 2; size <= 16; size <<= 1) {
+                        for (int size = 2; size <= W; size <<= 1) {
 #pragma unroll
                             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                                const float pd = __shfl_xor_sync(FULL, sd, stride, 16);
-                                const int pi = __shfl_xor_sync(FULL, si, stride, 16);
+                                const float pd = __shfl_xor_sync(FULL, sd, stride, W);
+                                const int pi = __shfl_xor_sync(FULL, si, stride, W);
                                 const bool plt = pd < sd || (pd == sd && pi < si);           // partner sorts first
                                 const bool up = ((sl & size) == 0);                           // ascending block
                                 const bool lower = ((sl & stride) == 0);
                                 if (plt == (up == lower)) { sd = pd; si = pi; }               // keep min in the lower lane of an ascending pair
                             }
                         }
-                        // lowest 16 of (list, batch): elementwise min against the reversed batch is bitonic -> 4 merge stages
+                        // lowest W of (list, batch): elementwise min against the reversed batch is bitonic -> log2(W) merge stages
                         {
-                            const float rd = __shfl_sync(FULL, sd, 15 - sl, 16);
-                            const int ri = __shfl_sync(FULL, si, 15 - sl, 16);
+                            const float rd = __shfl_sync(FULL, sd, W - 1 - sl, W);
+                            const int ri = __shfl_sync(FULL, si, W - 1 - sl, W);
                             if (rd < bd[0] || (rd == bd[0] && ri < bi[0])) { bd[0] = rd; bi[0] = ri; }
                         }
 #pragma unroll
-                        for (int stride = 8; stride > 0; stride >>= 1) {
-                            const float pd = __shfl_xor_sync(FULL, bd[0], stride, 16);
-                            const int pi = __shfl_xor_sync(FULL, bi[0], stride, 16);
+                        for (int stride = W / 2; stride > 0; stride >>= 1) {
+                            const float pd = __shfl_xor_sync(FULL, bd[0], stride, W);
+                            const int pi = __shfl_xor_sync(FULL, bi[0], stride, W);
                             const bool plt = pd < bd[0] || (pd == bd[0] && pi < bi[0]);
                             const bool lower = ((sl & stride) == 0);
                             if (plt == lower) { bd[0] = pd; bi[0] = pi; }
                         }
-                        thr_d = __shfl_sync(FULL, bd[0], k - 1, 16);
-                        thr_i = __shfl_sync(FULL, bi[0], k - 1, 16);
+                        thr_d = __shfl_sync(FULL, bd[0], k - 1, W);
+                        thr_i = __shfl_sync(FULL, bi[0], k - 1, W);
                         m = 0;
                     }
                 }
@@ -596,13 +599,13 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     }
 }
 
-template <int W>
+template <int W, int E>
 static void launch_knn_sub(const float4 *sorted, const int *cell_start, const GridParams *params, int clouds, int n, int k,
-                           int32_t *nbr, cudaStream_t st) {
+                           int32_t *nbr, int maxc, cudaStream_t st) {
     constexpr int QPB = GQ_WARPS * (32 / W);
     dim3 grid((n + QPB - 1) / QPB, clouds);
     static const int merge_min = getenv("EGSPR_KNN_MERGE_MIN") ? atoi(getenv("EGSPR_KNN_MERGE_MIN")) : 5;
-    knn_grid_query_sub_kernel<W><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min);
+    knn_grid_query_sub_kernel<W, E><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min, maxc);
 }
 
 __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int k,
@@ -620,7 +623,7 @@ __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int 
 
 extern "C" size_t egspr_knn_workspace_bytes(int clouds, int n) {
     using namespace egspr;
-    return (size_t)clouds * ((size_t)n * sizeof(float4) + (GRID_MAXC + 1) * sizeof(int) + sizeof(GridParams)) + 256;
+    return (size_t)clouds * ((size_t)n * sizeof(float4) + (size_t)(grid_capacity(n) + 1) * sizeof(int) + sizeof(GridParams)) + 256;
 }
 
 extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t *nbr, void *workspace,
@@ -640,17 +643,23 @@ extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t
     uint8_t *w = (uint8_t *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float4 *sorted = (float4 *)w;
     int *cell_start = (int *)(w + (size_t)clouds * n * sizeof(float4));
-    GridParams *params = (GridParams *)(cell_start + (size_t)clouds * (GRID_MAXC + 1));
-    knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, 0, st>>>(x, n, sorted, cell_start, params);
+    const int maxc = grid_capacity(n);
+    GridParams *params = (GridParams *)(cell_start + (size_t)clouds * (maxc + 1));
+    const size_t build_smem = (size_t)(maxc + 1) * sizeof(int);
+    if (build_smem > 48 * 1024 &&
+        cudaFuncSetAttribute(knn_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem) != cudaSuccess)
+        return EGSPR_E_LAUNCH;
+    knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, build_smem, st>>>(x, n, sorted, cell_start, params, maxc);
     dim3 grid((n + GQ_WARPS - 1) / GQ_WARPS, clouds);
     static const bool nested = getenv("EGSPR_KNN_NESTED") != nullptr;    // developer switch: the nested-loop query kernel
     static const bool flat32 = getenv("EGSPR_KNN_FLAT32") != nullptr;    // developer switch: one query per warp even for k <= 16
-    if (nested) knn_grid_query_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr);
+    if (nested) knn_grid_query_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, maxc);
     else if (k <= 16 && !flat32) {
         static const int wsel = getenv("EGSPR_KNN_W") ? atoi(getenv("EGSPR_KNN_W")) : 16;   // lanes per query
-        if (wsel == 8) launch_knn_sub<8>(sorted, cell_start, params, clouds, n, k, nbr, st);
-        else launch_knn_sub<16>(sorted, cell_start, params, clouds, n, k, nbr, st);
-    } else knn_grid_query_flat_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr);
+        if (wsel == 8) launch_knn_sub<8, 2>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);
+        else launch_knn_sub<16, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);
+    } else if (!flat32) launch_knn_sub<32, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);   // 16 < k <= 32
+    else knn_grid_query_flat_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, maxc);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
