@@ -6,6 +6,8 @@
 // scatter-add atomics per layer, the edge list is transposed once: a counting sort by row
 // (integer atomics only decide slots; a per-row rank pass then restores ascending edge order, so
 // the result is deterministic and sums run in the same order as scatter_add_ on CPU).
+#include <cstdlib>
+
 #include "egspr_common.cuh"
 
 namespace egspr {
@@ -134,6 +136,122 @@ __global__ void __launch_bounds__(256) csr_emit_kernel(Src src, int n, int64_t e
     }
 }
 
+// ---- fused build for small clouds: ONE CTA per cloud does count -> scan -> fill -> rank/emit with the
+// degree counters, row offsets and the unsorted edge list all in shared memory (one launch instead of a
+// memset + four kernels, no global atomics).  Same output as the generic path.
+constexpr int CF_THREADS = 1024;
+constexpr size_t CF_MAX_SMEM = 200 * 1024;
+
+template <class Src>
+__global__ void __launch_bounds__(CF_THREADS) csr_fused_kernel(Src src, int n, int64_t epc, int clouds,
+                                                               int32_t *__restrict__ csr_ptr, int32_t *__restrict__ csr_row,
+                                                               int32_t *__restrict__ csr_col, int32_t *__restrict__ csr_eid,
+                                                               int32_t *__restrict__ err_flag) {
+    extern __shared__ int32_t cf_smem[];
+    int32_t *deg = cf_smem;                 // [n]      degree, later the fill cursor
+    int32_t *off = deg + n;                 // [n + 1]  exclusive offsets inside the cloud
+    int32_t *tmp = off + n + 1;             // [epc]    edge ids grouped by row, unsorted inside a row
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = (int)epc;
+    for (int i = tid; i < n; i += CF_THREADS) deg[i] = 0;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int e0 = tid; e0 < E; e0 += 8 * CF_THREADS) {        // 8 edges per thread in flight (the loads are independent)
+        int r[8], c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * CF_THREADS;
+            r[u] = 0; c[u] = 0;
+            if (e < E) src.get(cloud, e, epc, r[u], c[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (e0 + u * CF_THREADS < E) {
+                bool bad = fix_range(r[u], n);
+                bad |= fix_range(c[u], n);
+                if (bad && err_flag) *err_flag = 1;
+                atomicAdd(&deg[r[u]], 1);
+            }
+        }
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += CF_THREADS) {        // exclusive scan of deg -> off; deg becomes the cursor
+        const int i = base + tid;
+        const int v = i < n ? deg[i] : 0;
+        int sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+        if (lane == 31) warp_tot[warp] = sc;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane], u = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += w; }
+            warp_tot[lane] = u - t;
+        }
+        __syncthreads();
+        const int excl = carry_s + warp_tot[warp] + sc - v;
+        if (i < n) {
+            off[i] = excl; deg[i] = excl;
+            csr_ptr[(int64_t)cloud * n + i] = (int32_t)(cloud * epc) + excl;
+        }
+        __syncthreads();
+        if (tid == CF_THREADS - 1) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        off[n] = E;
+        if (cloud == clouds - 1) csr_ptr[(int64_t)clouds * n] = (int32_t)(clouds * epc);
+    }
+    for (int e0 = tid; e0 < E; e0 += 8 * CF_THREADS) {
+        int r[8], c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * CF_THREADS;
+            r[u] = 0; c[u] = 0;
+            if (e < E) src.get(cloud, e, epc, r[u], c[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * CF_THREADS;
+            if (e < E) { fix_range(r[u], n); tmp[atomicAdd(&deg[r[u]], 1)] = e; }
+        }
+    }
+    __syncthreads();
+    const int64_t gbase = (int64_t)cloud * epc;
+    for (int i = warp; i < n; i += CF_THREADS / 32) {          // warp per row: rank restores ascending edge order
+        const int base = off[i], d = off[i + 1] - base;
+        const int32_t g = cloud * n + i;
+        if (d <= 32) {
+            const int e = lane < d ? tmp[base + lane] : 0x7fffffff;
+            int rank = 0;
+            for (int j = 0; j < d; ++j) rank += (__shfl_sync(0xffffffffu, e, j) < e);
+            if (lane < d) {
+                int r, c;
+                src.get(cloud, e, epc, r, c);
+                fix_range(c, n);
+                csr_eid[gbase + base + rank] = e;
+                csr_row[gbase + base + rank] = g;
+                csr_col[gbase + base + rank] = cloud * n + c;
+            }
+        } else {
+            for (int q = lane; q < d; q += 32) {
+                const int e = tmp[base + q];
+                int rank = 0;
+                for (int j = 0; j < d; ++j) rank += (tmp[base + j] < e);
+                int r, c;
+                src.get(cloud, e, epc, r, c);
+                fix_range(c, n);
+                csr_eid[gbase + base + rank] = e;
+                csr_row[gbase + base + rank] = g;
+                csr_col[gbase + base + rank] = cloud * n + c;
+            }
+        }
+    }
+}
+
 template <class Src>
 static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, int32_t *csr_row,
                      int32_t *csr_col, int32_t *csr_eid, void *ws, size_t ws_bytes, int32_t *err_flag,
@@ -141,6 +259,21 @@ static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, 
     const int64_t G = (int64_t)clouds * n, E = (int64_t)clouds * epc;
     if (clouds > 65535 || E >= (int64_t)0x7fffffff || G >= (int64_t)0x7fffffff) return EGSPR_E_UNSUPPORTED;
     if (ws_bytes < egspr_csr_workspace_bytes(G, E)) return EGSPR_E_WORKSPACE;
+    {   // small clouds, enough of them to fill the GPU: fused single-launch build in shared memory
+        static const bool generic = getenv("EGSPR_CSR_GENERIC") != nullptr;     // developer switch
+        const size_t smem = sizeof(int32_t) * (size_t)(2 * (int64_t)n + 1 + epc);
+        if (!generic && smem <= CF_MAX_SMEM && clouds >= 16) {
+            static bool configured = false;
+            if (!configured) {
+                if (cudaFuncSetAttribute(csr_fused_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF_MAX_SMEM) != cudaSuccess)
+                    return EGSPR_E_LAUNCH;
+                configured = true;
+            }
+            csr_fused_kernel<Src><<<clouds, CF_THREADS, smem, st>>>(src, n, epc, clouds, csr_ptr, csr_row, csr_col, csr_eid, err_flag);
+            EGSPR_CHECK_LAUNCH();
+            return EGSPR_OK;
+        }
+    }
     int32_t *deg = (int32_t *)ws;
     int32_t *tmp = deg + ((G + 31) / 32) * 32;
     if (cudaMemsetAsync(deg, 0, sizeof(int32_t) * G, st) != cudaSuccess) return EGSPR_E_LAUNCH;

@@ -100,7 +100,8 @@ class RegistrationEngine:
                        "egspr_knn_build"); n_launch += 2
         _lib.check(lib.egspr_csr_from_nbr(p(self.nbr), C, N, k, p(self.csr_ptr), p(self.csr_row), p(self.csr_col),
                                           p(self.csr_eid), p(self.ws), self.ws_bytes, p(self.err), st), "egspr_csr_from_nbr")
-        n_launch += 4
+        # csr: one fused launch for small clouds (csr.cu: shared-memory build), else count/scan/fill/emit
+        n_launch += 1 if (4 * (2 * N + 1 + N * k) <= 200 * 1024 and C >= 16) else 4
         _lib.check(lib.egspr_node_embed(p(self.feat), p(self.x), G, p(pin), p(layers[0]), p(self.h[0]), p(self.x4[0]),
                                         p(self.P[0]), p(self.Q[0]), st), "egspr_node_embed"); n_launch += 1
         cur = 0
