@@ -144,6 +144,13 @@ int egspr_head_train(const float *h_out_src, const float *h_out_tgt, const float
                      int n, float *w_out, float *sim_out, float *R, float *t, float *Hout,
                      float *loss_parts, void *stream);
 
+/* ---- a17: calculate_pose_error / registration_recall tools/evaluation_metrics.py:14-43 and the F1 of
+ * evl:1277, batched on the device (the reference pulls every pose to the host: evl:1249-1270).  fp64 like the
+ * reference's numpy code.  src_pts, tgt_pts [pairs][n][3]; gt_pose [pairs][16]; out [pairs][5] doubles =
+ * (rotation error deg, translation error cm, recall = sqrt(TP/n), precision = TP/n, F1). tau: 0.09 m. */
+int egspr_pose_metrics(const float *R, const float *t, const float *gt_pose, const float *src_pts,
+                       const float *tgt_pts, int pairs, int n, double tau, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

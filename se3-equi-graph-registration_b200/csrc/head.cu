@@ -428,6 +428,58 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) kabsch_kernel(const float *__r
                  Hout ? Hout + b * 9 : nullptr, sc);
 }
 
+// ---- a17: tools/evaluation_metrics.py:14-43 (+ the F1 of src/eval_egnn_metrics.py:1277) on the device ----
+// One CTA per pair, fp64 like the reference's numpy code (float32 inputs promoted by the float64 pose):
+//   TE = 100 |t_gt - t|  (cm),  RE = deg(acos(clip((tr(R_gt^T R) - 1) / 2, -1, 1))),
+//   TP = #{ |R p_i + t - q_i| < tau },  recall = sqrt(TP / n),  precision = TP / n,
+//   F1 = 2 P R / (P + R + 1e-6).      out[pair] = (RE, TE, recall, precision, F1)
+__global__ void __launch_bounds__(256) pose_metrics_kernel(const float *__restrict__ R, const float *__restrict__ t,
+                                                           const float *__restrict__ gt_pose, const float *__restrict__ src,
+                                                           const float *__restrict__ tgt, int n, double tau,
+                                                           double *__restrict__ out) {
+    __shared__ int warp_cnt[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double Rm[9], tv[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rm[i] = (double)__ldg(R + b * 9 + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tv[i] = (double)__ldg(t + b * 3 + i);
+    const float *p = src + (size_t)b * n * 3, *q = tgt + (size_t)b * n * 3;
+    int cnt = 0;
+    for (int i = tid; i < n; i += 256) {
+        const double x = (double)__ldg(p + 3 * i), y = (double)__ldg(p + 3 * i + 1), z = (double)__ldg(p + 3 * i + 2);
+        const double dx = (Rm[0] * x + Rm[1] * y + Rm[2] * z) + tv[0] - (double)__ldg(q + 3 * i);
+        const double dy = (Rm[3] * x + Rm[4] * y + Rm[5] * z) + tv[1] - (double)__ldg(q + 3 * i + 1);
+        const double dz = (Rm[6] * x + Rm[7] * y + Rm[8] * z) + tv[2] - (double)__ldg(q + 3 * i + 2);
+        cnt += (sqrt(dx * dx + dy * dy + dz * dz) < tau) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) warp_cnt[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int tp = 0;
+        for (int w = 0; w < 8; ++w) tp += warp_cnt[w];
+        const float *g = gt_pose + b * 16;
+        double te = 0.0, tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const double d = (double)g[4 * i + 3] - tv[i]; te += d * d; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tr += (double)g[4 * k + i] * Rm[3 * k + i];        // trace(R_gt^T R)
+        double c = (tr - 1.0) / 2.0;
+        c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+        const double prec = n > 0 ? (double)tp / (double)n : 0.0;
+        const double rec = n > 0 ? sqrt((double)tp / (double)n) : 0.0;
+        out[b * 5 + 0] = acos(c) * (180.0 / 3.14159265358979323846);
+        out[b * 5 + 1] = sqrt(te) * 100.0;
+        out[b * 5 + 2] = rec;
+        out[b * 5 + 3] = prec;
+        out[b * 5 + 4] = 2.0 * (prec * rec) / (prec + rec + 1e-6);
+    }
+}
+
 static int head_threads(int n) {
     static const int forced = getenv("EGSPR_HEAD_THREADS") ? atoi(getenv("EGSPR_HEAD_THREADS")) : 0;   // developer switch
     if (forced == 256 || forced == 512 || forced == 1024) return forced;
@@ -505,4 +557,13 @@ extern "C" const char *egspr_error_string(int code) {
         case EGSPR_E_LAUNCH: return "CUDA launch failed";
         default: return "unknown egspr error";
     }
+}
+
+extern "C" int egspr_pose_metrics(const float *R, const float *t, const float *gt_pose, const float *src_pts,
+                                  const float *tgt_pts, int pairs, int n, double tau, double *out, void *stream) {
+    using namespace egspr;
+    if (!R || !t || !gt_pose || !src_pts || !tgt_pts || !out || pairs <= 0 || n < 0) return EGSPR_E_INVALID;
+    pose_metrics_kernel<<<pairs, 256, 0, (cudaStream_t)stream>>>(R, t, gt_pose, src_pts, tgt_pts, n, tau, out);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
 }

@@ -191,6 +191,12 @@ class RegistrationEngine:
         done.synchronize()
         return self._host_out[s]
 
+    def metrics(self, tau=0.09):
+        """Per-pair (rotation error deg, translation error cm, recall, precision, F1) of the last batch against
+        its gt_pose, on the device: float64 [B,5] (tools/evaluation_metrics.py:14-43, evl:1277)."""
+        B = self.B
+        return ops.pose_metrics(self.R, self.t, self.gt_pose, self.x[:B], self.x[B:], tau)
+
     def outputs(self):
         B = self.B
         return {"R": self.R, "t": self.t, "w": self.w, "H": self.Hm,

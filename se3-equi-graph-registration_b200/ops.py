@@ -228,3 +228,18 @@ def head_train(h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose):
                                                _ptr(w), _ptr(sim), _ptr(R), _ptr(t), _ptr(Hm), _ptr(lp), _stream()),
                    "egspr_head_train")
     return R, t, w, sim, Hm, lp
+
+
+def pose_metrics(R, t, gt_pose, src_pts, tgt_pts, tau=0.09):
+    """tools/evaluation_metrics.py:14-43 + the F1 of evl:1277 for a batch, on the device (fp64).
+    R [B,3,3], t [B,3], gt_pose [B,4,4], src_pts / tgt_pts [B,n,3]  ->  float64 [B,5] =
+    (rotation error deg, translation error cm, recall, precision, F1)."""
+    R = _req(R, "R", torch.float32, 3); t = _req(t, "t", torch.float32, 2)
+    gt_pose = _req(gt_pose.to(torch.float32), "gt_pose", torch.float32, 3)
+    src_pts = _req(src_pts, "src_pts", torch.float32, 3); tgt_pts = _req(tgt_pts, "tgt_pts", torch.float32, 3)
+    B, n, _ = src_pts.shape
+    out = torch.empty((B, 5), dtype=torch.float64, device=R.device)
+    with torch.cuda.device(R.device):
+        _lib.check(_lib.lib().egspr_pose_metrics(_ptr(R), _ptr(t), _ptr(gt_pose), _ptr(src_pts), _ptr(tgt_pts), B, n,
+                                                 float(tau), _ptr(out), _stream()), "egspr_pose_metrics")
+    return out

@@ -446,3 +446,21 @@ def test_engine_submit_collect_pipeline_matches_register(model):
     got.append((R.clone(), t.clone()))
     for (Rw, tw), (Rg, tg) in zip(want, got):
         assert torch.equal(Rw, Rg) and torch.equal(tw, tg)
+
+
+def test_device_pose_metrics_match_reference_metrics(golden_dir, model):
+    """egspr_pose_metrics (fp64 on the device) == tools/evaluation_metrics.py + evl:1277 (numpy port pinned by the
+    known-answer fixture in test_oracle.py): RE/TE to 1e-9 relative, inlier counts exact."""
+    B, N = 6, 2048
+    data = P.synthetic.make_batch(77, B, n=N)
+    keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "labels", "gt_pose")
+    eng = P.RegistrationEngine(model, batch=B, n=N, k=16, use_graph=False)
+    R, t = eng.register(*[data[k] for k in keys])
+    got = eng.metrics().cpu().numpy()
+    ref = P.metrics.evaluate_batch(R.cpu().numpy(), t.cpu().numpy(), data["gt_pose"].numpy(), data["src_pts"].numpy(), data["tgt_pts"].numpy())
+    for j, key in enumerate(("rot_err", "trans_err", "recall", "precision", "f1")):
+        assert np.allclose(got[:, j], np.asarray(ref[key], dtype=np.float64), rtol=1e-9, atol=1e-9), key
+    # a pose that is exactly the ground truth: zero errors, recall = sqrt(fraction of inliers within tau)
+    gt = data["gt_pose"].to(DEV)
+    m = ops.pose_metrics(gt[:, :3, :3].contiguous(), gt[:, :3, 3].contiguous(), gt, data["src_pts"].to(DEV), data["tgt_pts"].to(DEV)).cpu().numpy()
+    assert np.all(m[:, 0] < 0.05) and np.all(m[:, 1] < 1e-6) and np.all(m[:, 3] > 0.5)     # acos near 1: sqrt(fp32 eps) ~ 0.01 deg
