@@ -122,19 +122,31 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
     const int bar_id = 1 + grp;
 
     const int64_t tiles = (a.G + 127) / 128;
-    for (int64_t tile = (int64_t)blockIdx.x * NT_GROUPS + grp; tile < tiles; tile += (int64_t)gridDim.x * NT_GROUPS) {
+    const int64_t tstep = (int64_t)gridDim.x * NT_GROUPS;
+    // the next tile's input rows are loaded one tile ahead (registers), under the stage-3 MMA / stores
+    float hn[32], an[32];
+    {
+        const int64_t t0 = (int64_t)blockIdx.x * NT_GROUPS + grp;
+        if (t0 < tiles) {
+            const int64_t gl0 = min(t0 * 128 + ht, a.G - 1);
+            load_row32(hn, a.h_in + gl0 * H);
+            if (do_s1) load_row32(an, a.agg + gl0 * H);
+        }
+    }
+    for (int64_t tile = (int64_t)blockIdx.x * NT_GROUPS + grp; tile < tiles; tile += tstep) {
         const int64_t g = tile * 128 + ht;
         const bool live = g < a.G;
-        const int64_t gl = live ? g : a.G - 1;
         float h[32], v[32];
-        load_row32(h, a.h_in + gl * H);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h[i] = hn[i];
         if (a.x3 && live) {
             *reinterpret_cast<float4 *>(a.x4_out + g * 4) =
                 make_float4(__ldg(a.x3 + g * 3), __ldg(a.x3 + g * 3 + 1), __ldg(a.x3 + g * 3 + 2), 0.f);
         }
         if (do_s1) {
             // stage 1: A = [h | agg]: A_hi columns 32..95, A_lo columns 96..159, D columns 0..31
-            load_row32(v, a.agg + gl * H);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = an[i];
             nt_store_hilo(tw + 32, tw + 96, h);
             nt_store_hilo(tw + 64, tw + 128, v);
             tmem_wait_st();
@@ -178,6 +190,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
             }
         }
         if (live && !a.out_to_h) store_row32(a.h_out + g * H, v);
+        if (tile + tstep < tiles) {              // next tile's rows: in flight during stage 3
+            const int64_t gln = min((tile + tstep) * 128 + ht, a.G - 1);
+            load_row32(hn, a.h_in + gln * H);
+            if (do_s1) load_row32(an, a.agg + gln * H);
+        }
         if (n3) {
             // stage 3: A_hi columns 64..95, A_lo columns 96..127, D columns 0..n3-1
             nt_store_hilo(tw + 64, tw + 96, v);
