@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_warp_select_kernel(
 //           1e-4 relative slack) or the block covers the whole grid.
 // ================================================================================================
 constexpr int GRID_MAXC = 32768;      // upper bound of cells per cloud (shared-memory counters of the build CTA)
-// cell capacity reserved per cloud: the grid aims at ~4 points per cell (n/4 cells; the per-axis rounding can
+// cell capacity reserved per cloud: the grid aims at ~2 points per cell (n/2 cells; the per-axis rounding can
 // overshoot, the build shrinks the grid until it fits)
 static inline int grid_capacity(int n) { return n < 1024 ? 1024 : (n > GRID_MAXC ? GRID_MAXC : n); }
 constexpr int GRID_BUILD_THREADS = 512;
@@ -97,7 +97,7 @@ struct GridParams {        // per cloud, 16 floats
 
 __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
     const float *__restrict__ x, int n, float4 *__restrict__ sorted, int *__restrict__ cell_start,
-    GridParams *__restrict__ params, int maxc) {
+    GridParams *__restrict__ params, int maxc, float pts_per_cell) {
     extern __shared__ int cnt[];          // [maxc + 1]
     __shared__ float red[6][GRID_BUILD_THREADS / 32];
     __shared__ GridParams gp;
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
             mn[a] = l; ext[a] = h - l;
         }
         const float emax = fmaxf(fmaxf(ext[0], ext[1]), fmaxf(ext[2], 1e-30f));
-        // cells wanted: ~4 points per cell; degenerate (flat) axes get a single cell
-        float target = fmaxf(1.0f, (float)n * 0.25f);
+        // cells wanted: n / pts_per_cell; degenerate (flat) axes get a single cell
+        float target = fmaxf(1.0f, (float)n / pts_per_cell);
         if (target > (float)maxc) target = (float)maxc;
         float e[3]; int live = 0; float vol = 1.0f;
         for (int a = 0; a < 3; ++a) { e[a] = ext[a]; if (e[a] > 1e-4f * emax) { ++live; vol *= e[a]; } }
@@ -649,7 +649,8 @@ extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t
     if (build_smem > 48 * 1024 &&
         cudaFuncSetAttribute(knn_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem) != cudaSuccess)
         return EGSPR_E_LAUNCH;
-    knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, build_smem, st>>>(x, n, sorted, cell_start, params, maxc);
+    static const float ppc = getenv("EGSPR_KNN_PPC") ? (float)atof(getenv("EGSPR_KNN_PPC")) : 2.0f;   // target points per cell (measured optimum at 2048-point clouds, k = 16)
+    knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, build_smem, st>>>(x, n, sorted, cell_start, params, maxc, ppc);
     dim3 grid((n + GQ_WARPS - 1) / GQ_WARPS, clouds);
     static const bool nested = getenv("EGSPR_KNN_NESTED") != nullptr;    // developer switch: the nested-loop query kernel
     static const bool flat32 = getenv("EGSPR_KNN_FLAT32") != nullptr;    // developer switch: one query per warp even for k <= 16
