@@ -181,12 +181,16 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     __syncthreads();
     fence_after_sync();
     pdl_wait();                     // everything above touched only static weights / on-chip state
-    const uint32_t tmem_g = *tmem_holder + 96u * grp;                   // this group's 96 columns (D | A_hi | A_lo)
+    // warp-uniform copies (shuffle from lane 0) so the MMA issue code runs on the uniform datapath
+    const int hw_u = __shfl_sync(0xffffffffu, hw, 0), grp_u = __shfl_sync(0xffffffffu, grp, 0);
+    const uint32_t tmem_g = __shfl_sync(0xffffffffu, *tmem_holder, 0) + 96u * grp_u;   // this group's 96 columns (D | A_hi | A_lo)
     const uint32_t tmem_w = tmem_g + ((uint32_t)(hw * 32) << 16);       // ... at this warp's 32 lanes
     const uint32_t tD = tmem_g, tAhi = tmem_g + 32, tAlo = tmem_g + 64;
-    const uint64_t dX1 = make_desc_sw128(smem_u32(base + VS_W));
-    const uint64_t dW2hi = make_desc_sw128(smem_u32(base + VS_W + 4096)), dW2lo = make_desc_sw128(smem_u32(base + VS_W + 8192));
-    const uint64_t dW3hi = make_desc_sw128(smem_u32(base + VS_W + 12288)), dW3lo = make_desc_sw128(smem_u32(base + VS_W + 16384));
+    const uint32_t w_s = __shfl_sync(0xffffffffu, smem_u32(base + VS_W), 0);
+    const uint64_t dX1 = make_desc_sw128(w_s);
+    const uint64_t dW2hi = make_desc_sw128(w_s + 4096), dW2lo = make_desc_sw128(w_s + 8192);
+    const uint64_t dW3hi = make_desc_sw128(w_s + 12288), dW3lo = make_desc_sw128(w_s + 16384);
+    const uint32_t mbar_u = __shfl_sync(0xffffffffu, mbar, 0);
     uint32_t phase = 0;
 
     // ---- this group's contiguous range of aggregation rows ----
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(1);
         bar_sync(bar_id, 128);
         TS_MARK(2);
-        if (ht == 0) {
+        if (hw_u == 0 && elect_one()) {     // stage 1 is issued by warp 0, stage 2 by warp 1, stage 3 by warp 2
             fence_after_sync();
             umma_tf32_ts(tD, tAhi + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
             umma_tf32_ts(tD, tAhi + 8, dX1 + 2, IDESC_TF32_M128_N32, 1);
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
                 umma_tf32_ts(tD, tAhi + 0, dX1 + 4, IDESC_TF32_M128_N32, 1);      // hi x Wlo
                 umma_tf32_ts(tD, tAhi + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
             }
-            umma_commit(mbar);
+            umma_commit(mbar_u);
         }
         // stage csr_ptr[nstart ...] of this tile's rows for the segment sums (visible after barriers 2, 3)
         const int rlast = s_rlast[0];
@@ -354,11 +358,11 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(5);
         bar_sync(bar_id, 128);
         TS_MARK(6);
-        if (ht == 0) {
+        if (hw_u == 1 && elect_one()) {
             fence_after_sync();
             if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW2hi);
             else issue_3xtf32_ts(tD, tAhi, tAlo, dW2hi, dW2lo);
-            umma_commit(mbar);
+            umma_commit(mbar_u);
         }
         {   // the next tile's endpoint coordinates travel while stages 2 and 3 run
             const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
@@ -404,11 +408,11 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(8);
         bar_sync(bar_id, 128);
         TS_MARK(9);
-        if (ht == 0) {
+        if (hw_u == 2 && elect_one()) {
             fence_after_sync();
             if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW3hi);
             else issue_3xtf32_ts(tD, tAhi, tAlo, dW3hi, dW3lo);
-            umma_commit(mbar);
+            umma_commit(mbar_u);
         }
         // ---- feature segment sums while the tensor core works: 8 threads per aggregation row (4 features
         // each), up to 16 rows of the tile in parallel; every thread adds its row's edges in ascending order ----
