@@ -112,12 +112,16 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
     __syncthreads();
     fence_after_sync();
     pdl_wait();                     // everything above touched only static weights / on-chip state
-    const uint32_t tg = *tmem_holder + NT_COLS * grp;
+    // warp-uniform copies (shuffle from lane 0) so the MMA issue code runs on the uniform datapath
+    const int hw_u = __shfl_sync(0xffffffffu, hw, 0), grp_u = __shfl_sync(0xffffffffu, grp, 0);
+    const uint32_t tg = __shfl_sync(0xffffffffu, *tmem_holder, 0) + NT_COLS * grp_u;
+    const uint32_t w_s = __shfl_sync(0xffffffffu, smem_u32(base), 0);
+    const uint32_t mbar_u = __shfl_sync(0xffffffffu, mbar, 0);
     const uint32_t tw = tg + ((uint32_t)(hw * 32) << 16);
-    const uint64_t dW1Ahi = make_desc_sw128(smem_u32(base + NS_W1A)), dW1Alo = make_desc_sw128(smem_u32(base + NS_W1A + 4096));
-    const uint64_t dW1Bhi = make_desc_sw128(smem_u32(base + NS_W1B)), dW1Blo = make_desc_sw128(smem_u32(base + NS_W1B + 4096));
-    const uint64_t dW2hi = make_desc_sw128(smem_u32(base + NS_W2)), dW2lo = make_desc_sw128(smem_u32(base + NS_W2 + 4096));
-    const uint64_t dW3hi = make_desc_sw128(smem_u32(base + NS_W3)), dW3lo = make_desc_sw128(smem_u32(base + NS_W3 + 8192));
+    const uint64_t dW1Ahi = make_desc_sw128(w_s + NS_W1A), dW1Alo = make_desc_sw128(w_s + NS_W1A + 4096);
+    const uint64_t dW1Bhi = make_desc_sw128(w_s + NS_W1B), dW1Blo = make_desc_sw128(w_s + NS_W1B + 4096);
+    const uint64_t dW2hi = make_desc_sw128(w_s + NS_W2), dW2lo = make_desc_sw128(w_s + NS_W2 + 4096);
+    const uint64_t dW3hi = make_desc_sw128(w_s + NS_W3), dW3lo = make_desc_sw128(w_s + NS_W3 + 8192);
     uint32_t phase = 0;
     const int bar_id = 1 + grp;
 
@@ -152,11 +156,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
             tmem_wait_st();
             fence_before_sync();
             bar_sync(bar_id, 128);
-            if (ht == 0) {
+            if (hw_u == 0 && elect_one()) {
                 fence_after_sync();
                 nt_issue_k32(tg, tg + 32, tg + 96, dW1Ahi, dW1Alo, IDESC_TF32_M128_N32, true);
                 nt_issue_k32(tg, tg + 64, tg + 128, dW1Bhi, dW1Blo, IDESC_TF32_M128_N32, false);
-                umma_commit(mbar);
+                umma_commit(mbar_u);
             }
             mbar_wait(mbar, phase); phase ^= 1;
             fence_after_sync();
@@ -173,10 +177,10 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
             tmem_wait_st();
             fence_before_sync();
             bar_sync(bar_id, 128);
-            if (ht == 0) {
+            if (hw_u == 1 && elect_one()) {
                 fence_after_sync();
                 nt_issue_k32(tg, tg + 32, tg + 96, dW2hi, dW2lo, IDESC_TF32_M128_N32, true);
-                umma_commit(mbar);
+                umma_commit(mbar_u);
             }
             mbar_wait(mbar, phase); phase ^= 1;
             fence_after_sync();
@@ -201,10 +205,10 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
             tmem_wait_st();
             fence_before_sync();
             bar_sync(bar_id, 128);
-            if (ht == 0) {
+            if (hw_u == 2 && elect_one()) {
                 fence_after_sync();
                 nt_issue_k32(tg, tg + 64, tg + 96, dW3hi, dW3lo, n3 == 64 ? IDESC_TF32_M128_N64 : IDESC_TF32_M128_N32, true);
-                umma_commit(mbar);
+                umma_commit(mbar_u);
             }
             mbar_wait(mbar, phase); phase ^= 1;
             fence_after_sync();
