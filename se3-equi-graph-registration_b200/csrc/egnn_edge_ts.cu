@@ -205,30 +205,36 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         const int i = n - nbase;
         return (i < V_SPTR) ? sp[i] : __ldg(a.csr_ptr + n);
     };
-    // coordinate segment sums of one finished tile: thread (slot = ht/4, component = ht%4) per row
-    auto coord_pass = [&](int tpar, int tp0, int tend_, int nfirst, int nlast, float x_pre) {
-        const int comp = ht & 3;
+    // coordinate segment sums of one finished tile: threads 112..127 of the group (warp 3, which has the least
+    // feature-row work), ONE aggregation row per thread, all three components as a float4 -- runs beside the
+    // feature sums of the following tile, off the other warps' critical path
+    auto coord_pass = [&](int tpar, int tp0, int tend_, int nfirst, int nlast, float4 x_pre) {
+        if (ht < 112) return;
         bool first = true;
-        const float *dx_t = reinterpret_cast<const float *>(dxs2 + tpar * 128);
+        const float4 *dx_t = dxs2 + tpar * 128;
         const int *sp = sptr2 + tpar * V_SPTR;
-        for (int n = nfirst + (ht >> 2); n <= nlast; n += 32) {
-            const float x_old = first ? x_pre : ((comp < 3) ? __ldg(a.x4 + (int64_t)n * 4 + comp) : 0.f);
+        for (int n = nfirst + (ht - 112); n <= nlast; n += 16) {
+            const float4 x_old = first ? x_pre : ldg4(a.x4 + (int64_t)n * 4);
             first = false;
             const int b0 = ptr_at(sp, nfirst, n), b1 = ptr_at(sp, nfirst, n + 1);
             const int lo = max(b0, tp0) - tp0, hi = min(b1, tend_) - tp0;
-            float s1 = (b0 < tp0) ? carry[tpar * 36 + 32 + comp] : 0.f;
+            float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 < tp0) s1 = *reinterpret_cast<const float4 *>(carry + tpar * 36 + 32);
             int q = lo;
-            for (; q + 4 <= hi; q += 4) {
-                const float d0 = dx_t[4 * q + comp], d1 = dx_t[4 * q + 4 + comp], d2 = dx_t[4 * q + 8 + comp], d3 = dx_t[4 * q + 12 + comp];
-                s1 += d0; s1 += d1; s1 += d2; s1 += d3;
+            for (; q + 4 <= hi; q += 4) {                             // strictly sequential edge order
+                const float4 d0 = dx_t[q], d1 = dx_t[q + 1], d2 = dx_t[q + 2], d3 = dx_t[q + 3];
+                s1.x += d0.x; s1.y += d0.y; s1.z += d0.z;
+                s1.x += d1.x; s1.y += d1.y; s1.z += d1.z;
+                s1.x += d2.x; s1.y += d2.y; s1.z += d2.z;
+                s1.x += d3.x; s1.y += d3.y; s1.z += d3.z;
             }
-            for (; q < hi; ++q) s1 += dx_t[4 * q + comp];
+            for (; q < hi; ++q) { const float4 d0 = dx_t[q]; s1.x += d0.x; s1.y += d0.y; s1.z += d0.z; }
             if (b1 <= tend_) {
-                const float xv = (comp < 3) ? x_old + s1 : 0.f;                                   // coord + agg  :267
-                a.x4_out[(int64_t)n * 4 + comp] = xv;
-                if (a.x3_out && comp < 3) a.x3_out[(int64_t)n * 3 + comp] = xv;
+                const float4 xv = make_float4(x_old.x + s1.x, x_old.y + s1.y, x_old.z + s1.z, 0.f);   // coord + agg  :267
+                *reinterpret_cast<float4 *>(a.x4_out + (int64_t)n * 4) = xv;
+                if (a.x3_out) { a.x3_out[(int64_t)n * 3] = xv.x; a.x3_out[(int64_t)n * 3 + 1] = xv.y; a.x3_out[(int64_t)n * 3 + 2] = xv.z; }
             } else {
-                carry[(tpar ^ 1) * 36 + 32 + comp] = s1;
+                *reinterpret_cast<float4 *>(carry + (tpar ^ 1) * 36 + 32) = s1;
             }
         }
     };
@@ -261,10 +267,10 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             rn = __ldg(a.csr_row + pn); cn = __ldg(a.csr_col + pn);
         }
         // old coordinate of the row this thread finishes in the pending coordinate pass (previous tile)
-        float x_pre = 0.f;
+        float4 x_pre = make_float4(0.f, 0.f, 0.f, 0.f);
         {
-            const int n = prev_nstart + (ht >> 2);
-            if (n <= prev_rlast && (ht & 3) < 3) x_pre = __ldg(a.x4 + (int64_t)n * 4 + (ht & 3));
+            const int n = prev_nstart + (ht - 112);
+            if (ht >= 112 && n <= prev_rlast) x_pre = ldg4(a.x4 + (int64_t)n * 4);
         }
         // csr_ptr window of this tile's rows (staged into shared memory after the first barrier)
         const int pt0 = __ldg(a.csr_ptr + min((int64_t)nstart + ht, G)), pt1 = __ldg(a.csr_ptr + min((int64_t)nstart + 128 + ht, G));
@@ -442,6 +448,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
                 else *reinterpret_cast<float4 *>(carry + (par ^ 1) * 36 + fq) = s0;
             }
         }
+        // the previous tile's coordinate sums (its dxs were completed before this tile's barriers)
+        if (prev_rlast >= 0) coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast, x_pre);
         // ---- accumulator -> registers, SiLU + wc2 epilogue (:219-229, :264) ----
         TS_MARK(10);
         mbar_wait(mbar, phase); phase ^= 1;
@@ -457,8 +465,6 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             ffma2(s4[0], s4[1], v[o], v[o + 1], wc.x, wc.y); ffma2(s4[2], s4[3], v[o + 2], v[o + 3], wc.z, wc.w);
         }
         const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        // the previous tile's coordinate pass (its dxs were completed before this tile's barriers)
-        if (prev_rlast >= 0) coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast, x_pre);
         dxs2[par * 128 + ht] = make_float4(dx * s, dy * s, dz * s, 0.f);                  // trans = coord_diff * s
         prev_p0 = p0; prev_tend = tend; prev_nstart = nstart; prev_rlast = rlast;
         nstart = (ptr_at(sp, nstart, rlast + 1) <= tend) ? rlast + 1 : rlast;
@@ -466,9 +472,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     if (prev_rlast >= 0) {
         fence_before_sync();
         bar_sync(bar_id, 128);      // the last tile's dxs are complete
-        const int n = prev_nstart + (ht >> 2);
+        const int n = prev_nstart + (ht - 112);
         coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast,
-                   (n <= prev_rlast && (ht & 3) < 3) ? __ldg(a.x4 + (int64_t)n * 4 + (ht & 3)) : 0.f);
+                   (ht >= 112 && n <= prev_rlast) ? ldg4(a.x4 + (int64_t)n * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
     // rows after the last edge of the range have no edges at all: zero aggregate, unchanged coordinates
     for (int n = nstart + hw; n < nB; n += 4) {
