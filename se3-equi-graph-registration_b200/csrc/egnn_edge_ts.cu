@@ -47,7 +47,8 @@ constexpr int V_SPTR = 256;           // csr_ptr entries of a tile's rows staged
 constexpr int VG_DXS = VG_MT + 128 * V_MROW * 4;      // float4[2][128]  coord_diff * s of the tile (by tile parity)
 constexpr int VG_CARRY = VG_DXS + 2 * 128 * 16;       // float[2][36]    running sums of a row that spans tiles
 constexpr int VG_SPTR = VG_CARRY + 2 * 36 * 4;        // int[2][V_SPTR]  csr_ptr[nstart ...] of the tile (by tile parity)
-constexpr int VG_RLAST = VG_SPTR + 2 * V_SPTR * 4;    // int             aggregation row of the tile's last edge
+constexpr int VG_QT = VG_SPTR + 2 * V_SPTR * 4;       // float[128][36]  Q[col] row of every edge of the tile (coalesced cp.async gather)
+constexpr int VG_RLAST = VG_QT + 128 * V_MROW * 4;    // int             aggregation row of the tile's last edge
 constexpr int VG_MBAR = VG_RLAST + 8;
 constexpr int VG_SIZE = ((VG_MBAR + 8 + 127) / 128) * 128;
 constexpr int VS_TMEM = VS_GRP + V_GROUPS * VG_SIZE;
@@ -63,6 +64,12 @@ __device__ long long g_ts_dbg[4 * 64 * 12];
 #else
 #define TS_MARK(slot)
 #endif
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // this thread's 32 values -> hi / lo halves of the A operand in TMEM (columns [0,32) of each)
 __device__ __forceinline__ void store_hilo_tmem(uint32_t t_hi, uint32_t t_lo, const float (&v)[32]) {
@@ -137,6 +144,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     float *carry = reinterpret_cast<float *>(gb + VG_CARRY);
     int *sptr2 = reinterpret_cast<int *>(gb + VG_SPTR);
     int *s_rlast = reinterpret_cast<int *>(gb + VG_RLAST);
+    const float *qrow = reinterpret_cast<const float *>(gb + VG_QT) + ht * V_MROW;          // this thread's edge's Q row
+    // gather target of lane l in round i: chunk l%8 of the row of this warp's edge 4*i + l/8
+    const uint32_t qt_dst = smem_u32(gb + VG_QT) + (uint32_t)((hw * 32 + (lane >> 3)) * (V_MROW * 4) + (lane & 7) * 16);
     const uint32_t mbar = smem_u32(gb + VG_MBAR);
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(base + VS_TMEM);
     const int bar_id = 1 + grp;
@@ -240,6 +250,18 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     };
     int prev_p0 = 0, prev_tend = 0, prev_nstart = 0, prev_rlast = -1;     // the tile whose coordinate pass is pending
 
+    // Q[col] rows of a tile, gathered COALESCED: 8 lanes fetch the 8 16-byte chunks of one row, so a warp-wide
+    // cp.async touches 4 full 128-byte lines (4 L1 wavefronts) instead of 32 quarter-sectors of 32 different lines
+    // (32 wavefronts) -- the per-thread LDG.128 form made the L1 data pipe the busiest unit of the kernel (62 %).
+    // The rows land in shared memory in thread order; only lanes of the same warp write / read a warp's 32 rows.
+    auto gather_q = [&](int c_own) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c_src = __shfl_sync(0xffffffffu, c_own, 4 * i + (lane >> 3));
+            cp_async16_cg(qt_dst + (uint32_t)(4 * i * V_MROW * 4), a.Q + (int64_t)c_src * H + 4 * (lane & 7));
+        }
+        cp_async_commit();
+    };
     int rn = 0, cn = 0;              // endpoints of this thread's edge in the NEXT tile (loaded one tile ahead)
     float xrn0 = 0.f, xrn1 = 0.f, xrn2 = 0.f, xcn0 = 0.f, xcn1 = 0.f, xcn2 = 0.f;   // ... and their coordinates
     if (pbeg < pend) {
@@ -248,6 +270,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
         xrn0 = t0.x; xrn1 = t0.y; xrn2 = t0.z; xcn0 = t1.x; xcn1 = t1.y; xcn2 = t1.z;
     }
+    gather_q(cn);                    // first tile's Q rows (all lanes take part in the shuffles)
 #ifdef EGSPR_TS_TIMING
     int tile_no = -1;
 #endif
@@ -260,7 +283,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         const int tend = min(p0 + 128, pend);
         int p = p0 + ht;
         if (p >= pend) p = pend - 1;               // idle slot: recompute the last edge, never reduced
-        const int r = rn, c = cn;
+        const int r = rn;
         const float3 xr = make_float3(xrn0, xrn1, xrn2), xc = make_float3(xcn0, xcn1, xcn2);
         {
             const int pn = min(p + 128, pend - 1);
@@ -275,11 +298,11 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         // csr_ptr window of this tile's rows (staged into shared memory after the first barrier)
         const int pt0 = __ldg(a.csr_ptr + min((int64_t)nstart + ht, G)), pt1 = __ldg(a.csr_ptr + min((int64_t)nstart + 128 + ht, G));
         // first edge Linear, node halves (bias in Q): issued now, consumed after the stage-1 MMA
-        float4 pv[8], qv[8];
+        float4 pv[8];
         {
-            const float *Pr = a.P + (int64_t)r * H, *Qc = a.Q + (int64_t)c * H;
+            const float *Pr = a.P + (int64_t)r * H;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { pv[i] = ldg4(Pr + 4 * i); qv[i] = ldg4(Qc + 4 * i); }
+            for (int i = 0; i < 8; ++i) pv[i] = ldg4(Pr + 4 * i);
         }
         if (ht == tend - 1 - p0) s_rlast[0] = r;
         float dx, dy, dz;
@@ -350,12 +373,17 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(4);
         fence_after_sync();
         tmem_ld32(tmem_w, v);
+        cp_async_wait_all();            // this tile's Q rows (gathered during the previous tile) are in shared memory
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {   // + P[row] + Q[col], SiLU  (:203-206)
-            fadd2(pv[i].x, pv[i].y, qv[i].x, qv[i].y); fadd2(pv[i].z, pv[i].w, qv[i].z, qv[i].w);
+            const float4 qv = *reinterpret_cast<const float4 *>(qrow + 4 * i);
+            fadd2(pv[i].x, pv[i].y, qv.x, qv.y); fadd2(pv[i].z, pv[i].w, qv.z, qv.w);
             fadd2(v[4 * i], v[4 * i + 1], pv[i].x, pv[i].y); fadd2(v[4 * i + 2], v[4 * i + 3], pv[i].z, pv[i].w);
             silu_pair<FAST>(v[4 * i], v[4 * i + 1]); silu_pair<FAST>(v[4 * i + 2], v[4 * i + 3]);
         }
+        __syncwarp();                   // every lane of the warp has read its Q row: refill the warp's rows for the next tile
+        gather_q(cn);
         // ---------------- stage 2: per-head second Linear (block-diagonal) ----------------
         if constexpr (FAST) store_tf32_tmem(tmem_w + 32, v);
         else store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
@@ -469,6 +497,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         prev_p0 = p0; prev_tend = tend; prev_nstart = nstart; prev_rlast = rlast;
         nstart = (ptr_at(sp, nstart, rlast + 1) <= tend) ? rlast + 1 : rlast;
     }
+    cp_async_wait_all();             // the look-ahead gather of the (non-existent) tile after the last one
     if (prev_rlast >= 0) {
         fence_before_sync();
         bar_sync(bar_id, 128);      // the last tile's dxs are complete
