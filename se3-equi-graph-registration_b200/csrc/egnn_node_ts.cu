@@ -41,7 +41,10 @@ constexpr int NS_W3 = 24576;         // [Wp ; Wq] 64 rows hi (8 KB), lo (8 KB)
 constexpr int NS_PAR = 40960;        // b1[32], b2[32], b3[64]
 constexpr int NS_MBAR = NS_PAR + 512;
 constexpr int NS_TMEM = NS_MBAR + 8 * NT_GROUPS;
-constexpr int NS_END = NS_TMEM + 16;
+constexpr int NT_SROW = 36;           // floats per staged row (144 B: conflict-free 16-byte accesses)
+constexpr int NS_STAGE = ((NS_TMEM + 16 + 127) / 128) * 128;     // per warp: 3 x [32][36] floats (h rows, agg rows, store staging)
+constexpr int NT_WSTAGE = 3 * 32 * NT_SROW * 4;
+constexpr int NS_END = NS_STAGE + (NT_THREADS / 32) * NT_WSTAGE;
 constexpr size_t NT_SMEM_BYTES = NS_END + 1024;
 
 constexpr uint32_t IDESC_TF32_M128_N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
@@ -66,6 +69,43 @@ __device__ __forceinline__ void nt_issue_k32(uint32_t d, uint32_t ahi, uint32_t 
     for (int k = 0; k < 4; ++k) umma_tf32_ts(d, ahi + 8 * k, wlo + 2 * k, idesc, 1);
 }
 
+__device__ __forceinline__ void nt_cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// The 32 rows of a warp are CONTIGUOUS in global memory (4 KB).  Moving them one row per thread (8 x LDG.128,
+// every instruction touching 32 different lines) costs 32 L1 wavefronts per instruction; moved as 8 lanes per
+// row through a shared-memory staging tile it costs 4.
+__device__ __forceinline__ void nt_rows_async(uint32_t stage_s, const float *src, int64_t g0, int64_t G, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + (lane >> 3);
+        const int64_t g = min(g0 + row, G - 1);
+        nt_cp_async16(stage_s + (uint32_t)(row * (NT_SROW * 4) + (lane & 7) * 16), src + g * H + 4 * (lane & 7));
+    }
+}
+__device__ __forceinline__ void nt_row_from_stage(float (&v)[32], const float *stage, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = *reinterpret_cast<const float4 *>(stage + lane * NT_SROW + 4 * i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+// registers (one row per thread) -> staging -> coalesced global store of the warp's rows [g0, g0 + 32) below G
+__device__ __forceinline__ void nt_rows_store(const float (&v)[32], float *stage, float *dst, int64_t g0, int64_t G, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4 *>(stage + lane * NT_SROW + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + (lane >> 3);
+        if (g0 + row < G)
+            *reinterpret_cast<float4 *>(dst + (g0 + row) * H + 4 * (lane & 7)) =
+                *reinterpret_cast<const float4 *>(stage + row * NT_SROW + 4 * (lane & 7));
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ void nt_fill_tile(uint8_t *hi_t, uint8_t *lo_t, const float *wt_in_major, int rows, int tid) {
     // B operand: row = output o, K = input k; source is [in][out] with 32 outputs per input row
     for (int i = tid; i < rows * 32; i += NT_THREADS) {
@@ -84,6 +124,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
     float *par = reinterpret_cast<float *>(base + NS_PAR);
     const uint32_t mbar = smem_u32(base + NS_MBAR + 8 * grp);
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(base + NS_TMEM);
+    const int lane = tid & 31;
+    float *stA = reinterpret_cast<float *>(base + NS_STAGE + (tid >> 5) * NT_WSTAGE), *stB = stA + 32 * NT_SROW, *stC = stB + 32 * NT_SROW;
+    const uint32_t stA_s = smem_u32(stA), stB_s = smem_u32(stB);
     const bool do_s1 = a.agg != nullptr, do_s2 = a.w2t != nullptr;
     const int n3 = a.w3pt ? (a.w3qt ? 64 : 32) : 0;
     pdl_trigger();                  // the next kernel's prologue may overlap this kernel's tail
@@ -127,30 +170,36 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
 
     const int64_t tiles = (a.G + 127) / 128;
     const int64_t tstep = (int64_t)gridDim.x * NT_GROUPS;
-    // the next tile's input rows are loaded one tile ahead (registers), under the stage-3 MMA / stores
-    float hn[32], an[32];
+    // the next tile's input rows travel one tile ahead (cp.async into the warp's staging tiles)
     {
         const int64_t t0 = (int64_t)blockIdx.x * NT_GROUPS + grp;
         if (t0 < tiles) {
-            const int64_t gl0 = min(t0 * 128 + ht, a.G - 1);
-            load_row32(hn, a.h_in + gl0 * H);
-            if (do_s1) load_row32(an, a.agg + gl0 * H);
+            nt_rows_async(stA_s, a.h_in, t0 * 128 + hw * 32, a.G, lane);
+            if (do_s1) nt_rows_async(stB_s, a.agg, t0 * 128 + hw * 32, a.G, lane);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int64_t tile = (int64_t)blockIdx.x * NT_GROUPS + grp; tile < tiles; tile += tstep) {
         const int64_t g = tile * 128 + ht;
+        const int64_t gw0 = tile * 128 + hw * 32;          // first row of this warp
         const bool live = g < a.G;
         float h[32], v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = hn[i];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        nt_row_from_stage(h, stA, lane);
+        if (do_s1) nt_row_from_stage(v, stB, lane);
+        __syncwarp();
+        if (tile + tstep < tiles) {              // next tile's rows: in flight during this tile's three stages
+            nt_rows_async(stA_s, a.h_in, (tile + tstep) * 128 + hw * 32, a.G, lane);
+            if (do_s1) nt_rows_async(stB_s, a.agg, (tile + tstep) * 128 + hw * 32, a.G, lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (a.x3 && live) {
             *reinterpret_cast<float4 *>(a.x4_out + g * 4) =
                 make_float4(__ldg(a.x3 + g * 3), __ldg(a.x3 + g * 3 + 1), __ldg(a.x3 + g * 3 + 2), 0.f);
         }
         if (do_s1) {
             // stage 1: A = [h | agg]: A_hi columns 32..95, A_lo columns 96..159, D columns 0..31
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = an[i];
             nt_store_hilo(tw + 32, tw + 96, h);
             nt_store_hilo(tw + 64, tw + 128, v);
             tmem_wait_st();
@@ -193,12 +242,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
                 for (int i = 0; i < 32; ++i) v[i] += par[32 + i];
             }
         }
-        if (live && !a.out_to_h) store_row32(a.h_out + g * H, v);
-        if (tile + tstep < tiles) {              // next tile's rows: in flight during stage 3
-            const int64_t gln = min((tile + tstep) * 128 + ht, a.G - 1);
-            load_row32(hn, a.h_in + gln * H);
-            if (do_s1) load_row32(an, a.agg + gln * H);
-        }
+        if (!a.out_to_h) nt_rows_store(v, stC, a.h_out, gw0, a.G, lane);
         if (n3) {
             // stage 3: A_hi columns 64..95, A_lo columns 96..127, D columns 0..n3-1
             nt_store_hilo(tw + 64, tw + 96, v);
@@ -217,12 +261,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += par[64 + i];
             }
-            if (live) store_row32((a.out_to_h ? a.h_out : a.P_out) + g * H, v);
+            nt_rows_store(v, stC, a.out_to_h ? a.h_out : a.P_out, gw0, a.G, lane);
             if (n3 == 64) {
                 tmem_ld32(tw + 32, v);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += par[96 + i];
-                if (live) store_row32(a.Q_out + g * H, v);
+                nt_rows_store(v, stC, a.Q_out, gw0, a.G, lane);
             }
         }
         fence_before_sync();     // this tile's tcgen05.ld are ordered before the next tile's MMAs (after its barrier)
