@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     pdl_wait();                     // everything above touched only static weights / on-chip state
     // warp-uniform copies (shuffle from lane 0) so the MMA issue code runs on the uniform datapath
     const int hw_u = __shfl_sync(0xffffffffu, hw, 0), grp_u = __shfl_sync(0xffffffffu, grp, 0);
-    const uint32_t tmem_g = __shfl_sync(0xffffffffu, *tmem_holder, 0) + 96u * grp_u;   // this group's 96 columns (D | A_hi | A_lo)
+    const uint32_t tmem_g = __shfl_sync(0xffffffffu, *tmem_holder, 0) + 128u * grp_u;  // this group's 128 columns (D | A_hi | A_lo | stage-1 operand)
     const uint32_t tmem_w = tmem_g + ((uint32_t)(hw * 32) << 16);       // ... at this warp's 32 lanes
-    const uint32_t tD = tmem_g, tAhi = tmem_g + 32, tAlo = tmem_g + 64;
+    const uint32_t tD = tmem_g, tAhi = tmem_g + 32, tAlo = tmem_g + 64, tA1 = tmem_g + 96;
     const uint32_t w_s = __shfl_sync(0xffffffffu, smem_u32(base + VS_W), 0);
     const uint64_t dX1 = make_desc_sw128(w_s);
     const uint64_t dW2hi = make_desc_sw128(w_s + 4096), dW2lo = make_desc_sw128(w_s + 8192);
@@ -262,6 +262,49 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         }
         cp_async_commit();
     };
+    // stage-1 operand of one edge: geometry (:271-278, :128-181) -> [hi(16) | lo(16)] in this group's TMEM columns
+    // 96..127.  It is produced ONE TILE AHEAD (under the stage-2 MMA of the previous tile), so a tile starts
+    // with its first MMA instead of ~250 instructions of geometry.
+    auto geometry_to_tmem = [&](float xr0, float xr1, float xr2, float xc0, float xc1, float xc2, float ea,
+                                float &dx, float &dy, float &dz) {
+        float geo[16];
+        dx = xr0 - xc0; dy = xr1 - xc1; dz = xr2 - xc2;                              // :273
+        const float radial = dx * dx + dy * dy + dz * dz;                            // :274
+        const float dist = fast_sqrt(radial);                                        // :179
+        const float ia = fast_rcp(dist + 1e-8f);                                     // :140
+        float ax = dx * ia, ay = dy * ia, az = dz * ia;
+        const float cx = xr1 * xc2 - xr2 * xc1, cy = xr2 * xc0 - xr0 * xc2,          // :143
+                    cz = xr0 * xc1 - xr1 * xc0;
+        const float ib = fast_rcp(fast_sqrt(cx * cx + cy * cy + cz * cz) + 1e-8f);   // :144
+        float bx = cx * ib, by = cy * ib, bz = cz * ib;
+        float ex = ay * bz - az * by, ey = az * bx - ax * bz, ez = ax * by - ay * bx;  // :149
+        const float na2 = ax * ax + ay * ay + az * az, nb2 = bx * bx + by * by + bz * bz,
+                    nc2 = ex * ex + ey * ey + ez * ez;
+        if (na2 < 1e-12f || nb2 < 1e-12f || nc2 < 1e-12f) {                          // norms < 1e-6  :152-163
+            ax = 1.f; ay = 0.f; az = 0.f; bx = 0.f; by = 1.f; bz = 0.f; ex = 0.f; ey = 0.f; ez = 1.f;
+        }
+        geo[0] = radial; geo[1] = dist; geo[2] = xr0 * xc0 + xr1 * xc1 + xr2 * xc2;  // :180
+        geo[3] = ax; geo[4] = bx; geo[5] = ex;      // so3 row-major, columns (a,b,c)  :159,:165
+        geo[6] = ay; geo[7] = by; geo[8] = ey;
+        geo[9] = az; geo[10] = bz; geo[11] = ez;
+        geo[12] = ea; geo[13] = 0.f; geo[14] = 0.f; geo[15] = 0.f;
+        float hi[16], lo[16];
+        if constexpr (FAST) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hi[i] = tf32_rna(geo[i]);
+            tmem_st16(tmem_w + 96, hi);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { hi[i] = tf32_hi(geo[i]); lo[i] = geo[i] - hi[i]; }
+            tmem_st16(tmem_w + 96, hi);          // columns 0..15  = hi(geo)
+            tmem_st16(tmem_w + 112, lo);         // columns 16..31 = lo(geo)
+        }
+    };
+    auto edge_attr_of = [&](int r_, int p_) -> float {
+        if (!a.edge_attr) return a.edge_attr_const;
+        const int64_t cloud = r_ / a.n_per_cloud;
+        return __ldg(a.edge_attr + cloud * a.edges_per_cloud + __ldg(a.csr_eid + p_));
+    };
     int rn = 0, cn = 0;              // endpoints of this thread's edge in the NEXT tile (loaded one tile ahead)
     float xrn0 = 0.f, xrn1 = 0.f, xrn2 = 0.f, xcn0 = 0.f, xcn1 = 0.f, xcn2 = 0.f;   // ... and their coordinates
     if (pbeg < pend) {
@@ -271,6 +314,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         xrn0 = t0.x; xrn1 = t0.y; xrn2 = t0.z; xcn0 = t1.x; xcn1 = t1.y; xcn2 = t1.z;
     }
     gather_q(cn);                    // first tile's Q rows (all lanes take part in the shuffles)
+    float dxn = 0.f, dyn = 0.f, dzn = 0.f;      // coord_diff of this thread's edge in the next tile
+    if (pbeg < pend)
+        geometry_to_tmem(xrn0, xrn1, xrn2, xcn0, xcn1, xcn2, edge_attr_of(rn, min(pbeg + ht, pend - 1)), dxn, dyn, dzn);
 #ifdef EGSPR_TS_TIMING
     int tile_no = -1;
 #endif
@@ -284,7 +330,6 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         int p = p0 + ht;
         if (p >= pend) p = pend - 1;               // idle slot: recompute the last edge, never reduced
         const int r = rn;
-        const float3 xr = make_float3(xrn0, xrn1, xrn2), xc = make_float3(xcn0, xcn1, xcn2);
         {
             const int pn = min(p + 128, pend - 1);
             rn = __ldg(a.csr_row + pn); cn = __ldg(a.csr_col + pn);
@@ -305,47 +350,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             for (int i = 0; i < 8; ++i) pv[i] = ldg4(Pr + 4 * i);
         }
         if (ht == tend - 1 - p0) s_rlast[0] = r;
-        float dx, dy, dz;
-        // ---------------- stage 1 operand: geometry (:271-278, :128-181) ----------------
-        {
-            float geo[16];
-            float ea = a.edge_attr_const;
-            if (a.edge_attr) {
-                const int64_t cloud = r / a.n_per_cloud;
-                ea = __ldg(a.edge_attr + cloud * a.edges_per_cloud + __ldg(a.csr_eid + p));
-            }
-            dx = xr.x - xc.x; dy = xr.y - xc.y; dz = xr.z - xc.z;                        // :273
-            const float radial = dx * dx + dy * dy + dz * dz;                            // :274
-            const float dist = fast_sqrt(radial);                                        // :179
-            const float ia = fast_rcp(dist + 1e-8f);                                     // :140
-            float ax = dx * ia, ay = dy * ia, az = dz * ia;
-            const float cx = xr.y * xc.z - xr.z * xc.y, cy = xr.z * xc.x - xr.x * xc.z,  // :143
-                        cz = xr.x * xc.y - xr.y * xc.x;
-            const float ib = fast_rcp(fast_sqrt(cx * cx + cy * cy + cz * cz) + 1e-8f);   // :144
-            float bx = cx * ib, by = cy * ib, bz = cz * ib;
-            float ex = ay * bz - az * by, ey = az * bx - ax * bz, ez = ax * by - ay * bx;  // :149
-            const float na2 = ax * ax + ay * ay + az * az, nb2 = bx * bx + by * by + bz * bz,
-                        nc2 = ex * ex + ey * ey + ez * ez;
-            if (na2 < 1e-12f || nb2 < 1e-12f || nc2 < 1e-12f) {                          // norms < 1e-6  :152-163
-                ax = 1.f; ay = 0.f; az = 0.f; bx = 0.f; by = 1.f; bz = 0.f; ex = 0.f; ey = 0.f; ez = 1.f;
-            }
-            geo[0] = radial; geo[1] = dist; geo[2] = xr.x * xc.x + xr.y * xc.y + xr.z * xc.z;   // :180
-            geo[3] = ax; geo[4] = bx; geo[5] = ex;      // so3 row-major, columns (a,b,c)  :159,:165
-            geo[6] = ay; geo[7] = by; geo[8] = ey;
-            geo[9] = az; geo[10] = bz; geo[11] = ez;
-            geo[12] = ea; geo[13] = 0.f; geo[14] = 0.f; geo[15] = 0.f;
-            float hi[16], lo[16];
-            if constexpr (FAST) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) hi[i] = tf32_rna(geo[i]);
-                tmem_st16(tmem_w + 32, hi);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { hi[i] = tf32_hi(geo[i]); lo[i] = geo[i] - hi[i]; }
-                tmem_st16(tmem_w + 32, hi);          // A_hi columns 0..15  = hi(geo)
-                tmem_st16(tmem_w + 48, lo);          // A_hi columns 16..31 = lo(geo)
-            }
-        }
+        const float dx = dxn, dy = dyn, dz = dzn;       // stage-1 operand of this tile was written one tile ahead
         tmem_wait_st();
         fence_before_sync();
         TS_MARK(1);
@@ -353,13 +358,13 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(2);
         if (hw_u == 0 && elect_one()) {     // stage 1 is issued by warp 0, stage 2 by warp 1, stage 3 by warp 2
             fence_after_sync();
-            umma_tf32_ts(tD, tAhi + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
-            umma_tf32_ts(tD, tAhi + 8, dX1 + 2, IDESC_TF32_M128_N32, 1);
+            umma_tf32_ts(tD, tA1 + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
+            umma_tf32_ts(tD, tA1 + 8, dX1 + 2, IDESC_TF32_M128_N32, 1);
             if constexpr (!FAST) {
-                umma_tf32_ts(tD, tAhi + 16, dX1 + 0, IDESC_TF32_M128_N32, 1);     // lo x Whi
-                umma_tf32_ts(tD, tAhi + 24, dX1 + 2, IDESC_TF32_M128_N32, 1);
-                umma_tf32_ts(tD, tAhi + 0, dX1 + 4, IDESC_TF32_M128_N32, 1);      // hi x Wlo
-                umma_tf32_ts(tD, tAhi + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
+                umma_tf32_ts(tD, tA1 + 16, dX1 + 0, IDESC_TF32_M128_N32, 1);     // lo x Whi
+                umma_tf32_ts(tD, tA1 + 24, dX1 + 2, IDESC_TF32_M128_N32, 1);
+                umma_tf32_ts(tD, tA1 + 0, dX1 + 4, IDESC_TF32_M128_N32, 1);      // hi x Wlo
+                umma_tf32_ts(tD, tA1 + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
             }
             umma_commit(mbar_u);
         }
@@ -373,6 +378,10 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(4);
         fence_after_sync();
         tmem_ld32(tmem_w, v);
+        {   // the next tile's endpoint coordinates (rn, cn were loaded at the top of this tile)
+            const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
+            xrn0 = t0.x; xrn1 = t0.y; xrn2 = t0.z; xcn0 = t1.x; xcn1 = t1.y; xcn2 = t1.z;
+        }
         cp_async_wait_all();            // this tile's Q rows (gathered during the previous tile) are in shared memory
         __syncwarp();
 #pragma unroll
@@ -398,10 +407,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             else issue_3xtf32_ts(tD, tAhi, tAlo, dW2hi, dW2lo);
             umma_commit(mbar_u);
         }
-        {   // the next tile's endpoint coordinates travel while stages 2 and 3 run
-            const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
-            xrn0 = t0.x; xrn1 = t0.y; xrn2 = t0.z; xcn0 = t1.x; xcn1 = t1.y; xcn2 = t1.z;
-        }
+        // the NEXT tile's stage-1 operand, under this tile's stage-2 MMA (the stage-1 MMA of this tile is complete)
+        geometry_to_tmem(xrn0, xrn1, xrn2, xcn0, xcn1, xcn2, edge_attr_of(rn, min(p + 128, pend - 1)), dxn, dyn, dzn);
         mbar_wait(mbar, phase); phase ^= 1;
         TS_MARK(7);
         fence_after_sync();
