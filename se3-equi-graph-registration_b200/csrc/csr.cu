@@ -15,7 +15,7 @@ namespace egspr {
 struct NbrSource {   // edges implied by nbr[cloud][i][s]: row = nbr, col = i, e = i*k+s
     const int32_t *nbr; int n, k;
     __device__ __forceinline__ void get(int cloud, int64_t e, int64_t epc, int &r, int &c) const {
-        r = nbr[cloud * epc + e]; c = (int)(e / k);
+        r = nbr[cloud * epc + e]; c = (int)((unsigned)e / (unsigned)k);      // e < n*k < 2^31: 32-bit division
     }
 };
 struct EdgeSource {  // edges[cloud][2][E] int64 (torch_cluster / reference layout)
