@@ -78,16 +78,21 @@ __device__ __forceinline__ void fmul2(float &d0, float &d1, float b0, float b1) 
     asm("{\n.reg .b64 ra, rb;\nmov.b64 ra, {%0, %1};\nmov.b64 rb, {%2, %3};\nmul.rn.f32x2 ra, ra, rb;\nmov.b64 {%0, %1}, ra;\n}"
         : "+f"(d0), "+f"(d1) : "f"(b0), "f"(b1));
 }
-// SiLU on a pair: the multiplies / add run packed (FMUL2, FADD2), the two MUFU pairs stay scalar
+// SiLU on a pair: the multiplies / adds run packed (FMUL2, FADD2); 3 MUFU per pair (two ex2, ONE shared rcp)
 __device__ __forceinline__ void silu2(float &x0, float &x1) {
     float t0 = x0, t1 = x1;
     fmul2(t0, t1, -1.4426950408889634f, -1.4426950408889634f);
     asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(t0));
     asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(t1));
+    // one reciprocal for the pair: 1/a = b / (a b), 1/b = a / (a b); e is clamped so a*b cannot overflow
+    // (x < -41: silu(x) = x / (1 + 1e18) instead of x e^x, both below 1e-16 in magnitude)
+    t0 = fminf(t0, 1e18f); t1 = fminf(t1, 1e18f);
     fadd2(t0, t1, 1.0f, 1.0f);
-    asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(t0));
-    asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(t1));
-    fmul2(x0, x1, t0, t1);
+    float r = t0 * t1;
+    asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(r));
+    float r0 = t1, r1 = t0;
+    fmul2(r0, r1, r, r);
+    fmul2(x0, x1, r0, r1);
 }
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
