@@ -464,3 +464,33 @@ def test_device_pose_metrics_match_reference_metrics(golden_dir, model):
     gt = data["gt_pose"].to(DEV)
     m = ops.pose_metrics(gt[:, :3, :3].contiguous(), gt[:, :3, 3].contiguous(), gt, data["src_pts"].to(DEV), data["tgt_pts"].to(DEV)).cpu().numpy()
     assert np.all(m[:, 0] < 0.05) and np.all(m[:, 1] < 1e-6) and np.all(m[:, 3] > 0.5)     # acos near 1: sqrt(fp32 eps) ~ 0.01 deg
+
+
+@pytest.mark.parametrize("impl", [1, 3, 4])
+def test_irregular_graph_hub_rows_and_isolated_nodes(model, impl):
+    """User-supplied edge lists (the module API accepts any [row, col]): an aggregation row with hundreds of
+    incoming edges (spans several 128-edge tiles of the streaming reduction -> the carry path), rows with
+    no incoming edge at all (zero aggregate, unchanged coordinates), multi-edges, several clouds."""
+    g = torch.Generator().manual_seed(5)
+    C, N = 3, 300
+    rows, cols = [], []
+    for c in range(C):
+        r = [torch.full((700,), 7 + c, dtype=torch.int64), torch.randint(0, N // 2, (900,), generator=g),   # hub row; rows N/2.. get nothing
+             torch.full((130,), N // 2 - 1, dtype=torch.int64)]                                            # a second long row at the end of the used range
+        r = torch.cat(r)
+        cc = torch.randint(0, N, (r.numel(),), generator=g)
+        perm = torch.randperm(r.numel(), generator=g)
+        rows.append(r[perm]); cols.append(cc[perm])
+    edges = torch.stack([torch.stack([rows[c], cols[c]]) for c in range(C)])          # [C,2,E]
+    E = edges.shape[-1]
+    feat = torch.randn(C, N, 32, generator=g); x = torch.rand(C, N, 3, generator=g) * 2
+    ea = torch.rand(C, E, generator=g)
+    gr = ops.csr_from_edges(edges.to(DEV), N)
+    layers, pin, pout = model.egnn.packs()
+    h, xo = ops.egnn_forward(feat.to(DEV), x.to(DEV), gr, layers, pin, pout, edge_attr=ea.to(DEV), impl=impl)
+    sd = {k: v.cpu() for k, v in model.egnn.state_dict().items()}
+    loose = 30.0 if impl == 4 else 1.0
+    for c in range(C):
+        href, xref = O.egnn_forward(sd, feat[c], x[c], rows[c], cols[c], ea[c][:, None])
+        assert float((h[c].cpu() - href).abs().max()) <= loose * H_TOL * float(href.abs().max()), c
+        assert float((xo[c].cpu() - xref).abs().max()) <= loose * X_TOL * max(1.0, float(xref.abs().max())), c
