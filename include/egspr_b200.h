@@ -151,6 +151,16 @@ int egspr_head_train(const float *h_out_src, const float *h_out_tgt, const float
 int egspr_pose_metrics(const float *R, const float *t, const float *gt_pose, const float *src_pts,
                        const float *tgt_pts, int pairs, int n, double tau, double *out, void *stream);
 
+/* ---- 8(f).3: feature-space correspondence search, data_preprocess/3DMatch_Feature.py:158-166 -------------
+ * For every descriptor a[i] (32 floats, unit norm) the nearest b[j] under
+ *     distance = sqrt(2 - 2 * <a[i], b[j]> + 1e-6)        (float32, operation by operation like the numpy code)
+ * idx[i] = np.argmin(distance[i, :]) (first index on ties), dist[i] = np.min(distance[i, :]).  The [na, nb]
+ * similarity matrix is a tcgen05 GEMM (3xTF32) that is never written to memory.  The reference's target_idx
+ * (argmin over axis 0, mutual check) is the same call with a and b swapped.
+ * workspace: na * 8 bytes. */
+int egspr_feature_nn(const float *a, int na, const float *b, int nb, void *workspace, size_t workspace_bytes,
+                     int32_t *idx, float *dist, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

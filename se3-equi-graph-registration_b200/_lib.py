@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("EGSPR_LIB_PATH") or os.path.join(_HERE, "libegspr_b200.so")   # override: developer A/B builds
-SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_edge_ts.cu", "egnn_node_ts.cu", "head.cu"]
+SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_edge_ts.cu", "egnn_node_ts.cu", "head.cu", "feature_match.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -38,6 +38,7 @@ SIGNATURES = {
     "egspr_head_eval": (_i, [_p] * 11 + [_i, _i, _i] + [_p] * 6),
     "egspr_head_train": (_i, [_p] * 6 + [_i, _i] + [_p] * 7),
     "egspr_pose_metrics": (_i, [_p] * 5 + [_i, _i, ctypes.c_double, _p, _p]),
+    "egspr_feature_nn": (_i, [_p, _i, _p, _i, _p, _z, _p, _p, _p]),
 }
 
 

@@ -243,3 +243,35 @@ def pose_metrics(R, t, gt_pose, src_pts, tgt_pts, tau=0.09):
         _lib.check(_lib.lib().egspr_pose_metrics(_ptr(R), _ptr(t), _ptr(gt_pose), _ptr(src_pts), _ptr(tgt_pts), B, n,
                                                  float(tau), _ptr(out), _stream()), "egspr_pose_metrics")
     return out
+
+
+def feature_nn(a, b):
+    """Nearest descriptor of b for every descriptor of a under the reference's feature distance
+    sqrt(2 - 2 <a,b> + 1e-6) (data_preprocess/3DMatch_Feature.py:158-160).
+    a [Na,32], b [Nb,32] f32 (unit norm) -> idx [Na] i32 (np.argmin, first index on ties), dist [Na] f32."""
+    a = _req(a, "a", torch.float32, 2); b = _req(b, "b", torch.float32, 2)
+    if a.shape[1] != H or b.shape[1] != H:
+        raise NotImplementedError(f"descriptor width must be {H}")
+    na, nb = a.shape[0], b.shape[0]
+    idx = torch.empty(na, dtype=torch.int32, device=a.device)
+    dist = torch.empty(na, dtype=torch.float32, device=a.device)
+    ws = torch.empty(na, dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().egspr_feature_nn(_ptr(a), na, _ptr(b), nb, _ptr(ws), ws.numel() * 8, _ptr(idx), _ptr(dist), _stream()),
+                   "egspr_feature_nn")
+    return idx, dist
+
+
+def feature_correspondences(src_desc, tgt_desc, use_mutual=False):
+    """Correspondence set of data_preprocess/3DMatch_Feature.py:158-166: nearest target descriptor of every
+    source descriptor; with use_mutual only the pairs that are each other's nearest neighbour.
+    Returns corr [M,2] i64 (source index, target index) and the per-source distances [Ns]."""
+    source_idx, source_dis = feature_nn(src_desc, tgt_desc)
+    ar = torch.arange(source_idx.numel(), device=source_idx.device)
+    if use_mutual:
+        target_idx, _ = feature_nn(tgt_desc, src_desc)
+        keep = target_idx.long()[source_idx.long()] == ar
+        corr = torch.stack([ar[keep], source_idx.long()[keep]], dim=-1)
+    else:
+        corr = torch.stack([ar, source_idx.long()], dim=-1)
+    return corr, source_dis
