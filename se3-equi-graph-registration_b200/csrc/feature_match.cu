@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(FM_THREADS) feature_nn_kernel(const float *__r
                                                                unsigned long long *__restrict__ best_packed) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t mbar = smem_u32(base + FS_MBAR);
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(base + FS_TMEM);
     if (warp == 0) tmem_alloc(smem_u32(tmem_holder), 256);
