@@ -136,3 +136,21 @@ def test_oracle_against_live_reference():
                          data["labels"], data["gt_pose"])
     for i in (0, 1, 4, 5, 6, 7):
         assert torch.allclose(out[i], ref[i], rtol=0, atol=1e-6 * float(ref[i].abs().max()))
+
+
+def test_feature_match_oracle_known_answers():
+    """oracle/feature_match_oracle.py restates data_preprocess/3DMatch_Feature.py:158-166 (three numpy lines inside a
+    file-processing loop that cannot be imported); pin it on hand-computable cases."""
+    from oracle import feature_match_oracle as FO
+    e = np.eye(4, 32, dtype=np.float32)                          # 4 orthonormal descriptors
+    src = e[[0, 1, 2, 3]]
+    tgt = np.stack([e[2], e[0], e[0], (e[1] + e[3]) / np.sqrt(2)]).astype(np.float32)
+    corr, sidx, sdis, D = FO.correspondences(src, tgt, use_mutual=False)
+    assert sidx.tolist() == [1, 3, 0, 3]                         # duplicate target e0 at 1 and 2: the first wins (np.argmin)
+    assert np.allclose(sdis[[0, 2]], np.sqrt(1e-6), rtol=1e-3)   # exact matches: sqrt(2 - 2 + 1e-6)
+    assert np.allclose(sdis[[1, 3]], np.sqrt(2 - np.sqrt(2) + 1e-6), rtol=1e-5)
+    assert corr.tolist() == [[0, 1], [1, 3], [2, 0], [3, 3]]
+    corr_m, *_ = FO.correspondences(src, tgt, use_mutual=True)
+    # target 3 is equally close to sources 1 and 3 -> argmin over axis 0 picks source 1: (3,3) is not mutual
+    assert corr_m.tolist() == [[0, 1], [1, 3], [2, 0]]
+    assert D.dtype == np.float32
