@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_flat_kernel(
 template <int W, int E>
 __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
-    int n, int k, int32_t *__restrict__ nbr, int merge_min, int maxc) {
+    int n, int k, int32_t *__restrict__ nbr, int merge_min, int maxc, int l0) {
     constexpr unsigned FULL = 0xffffffffu;
     // E = list entries per lane: the list holds W * E >= k entries
     constexpr int QPW = 32 / W;                    // queries per warp
@@ -454,18 +454,19 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     float thr_d = 1e10f;
     int thr_i = -1;
     const int kl = (k - 1) / E, kj = (k - 1) % E;          // lane / slot of the k-th entry
-    const int Lmax = max(max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz)), 1);
+    const int Lmax = max(max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz)), l0);
     bool done = !valid;
-    for (int L = 1; !__all_sync(FULL, done); ++L) {
+    const int w0 = 2 * l0 + 1;         // the first step scans the whole (2 l0 + 1)^3 block (shells 0 .. l0 together)
+    for (int L = l0; !__all_sync(FULL, done); ++L) {
         const int w = 2 * L - 1;
-        const int nseg = done ? 0 : ((L == 1) ? 9 : 8 * L + 2 * w * w);
+        const int nseg = done ? 0 : ((L == l0) ? w0 * w0 : 8 * L + 2 * w * w);
         for (int s0 = 0; __any_sync(FULL, s0 < nseg); s0 += W) {
             const int s = s0 + sl;
             int start = 0, len = 0;
             if (s < nseg) {
                 int dz, dy, x0, x1;
-                if (L == 1) {
-                    dz = s / 3 - 1; dy = s % 3 - 1; x0 = cx - 1; x1 = cx + 1;
+                if (L == l0) {
+                    dz = s / w0 - l0; dy = s % w0 - l0; x0 = cx - l0; x1 = cx + l0;
                 } else if (s < 8 * L) {
                     x0 = cx - L; x1 = cx + L;
                     if (s < 2 * L + 1) { dz = -L; dy = s - L; }
@@ -605,7 +606,8 @@ static void launch_knn_sub(const float4 *sorted, const int *cell_start, const Gr
     constexpr int QPB = GQ_WARPS * (32 / W);
     dim3 grid((n + QPB - 1) / QPB, clouds);
     static const int merge_min = getenv("EGSPR_KNN_MERGE_MIN") ? atoi(getenv("EGSPR_KNN_MERGE_MIN")) : 5;
-    knn_grid_query_sub_kernel<W, E><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min, maxc);
+    static const int l0 = getenv("EGSPR_KNN_L0") ? atoi(getenv("EGSPR_KNN_L0")) : 1;       // radius of the first block
+    knn_grid_query_sub_kernel<W, E><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min, maxc, l0 < 1 ? 1 : l0);
 }
 
 __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int k,
