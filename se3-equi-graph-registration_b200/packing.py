@@ -96,3 +96,45 @@ class PackCache:
                 self._val = self._build_fn()
             self._key = key
         return self._val
+
+
+# ---- gradients: the backward kernels write d loss / d pack in the SAME layouts; these undo the re-layout -----------
+def _g(buf, off, *shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return buf[off:off + n].reshape(*shape)
+
+
+def unpack_layer_grad(gpack, gcl):
+    """gpack [LAYER_PACK] (written by egspr_egcl_backward) -> list of gradients, one per `gcl.parameters()`
+    entry, in that order and with the parameters' shapes (inverse of pack_layer, which is a permutation)."""
+    heads = list(gcl.edge_mlps)
+    F_in = heads[0][0].weight.shape[1]
+    w1 = torch.cat([_g(gpack, OFF["WPT"], 32, 32).t(), _g(gpack, OFF["WQT"], 32, 32).t(),
+                    _g(gpack, OFF["WG"], 12, 32).t()] +
+                   ([_g(gpack, OFF["WEA"], 32, 1)] if F_in == 77 else []), dim=1)          # [32, F_in]
+    b1 = _g(gpack, OFF["BQ"], 32)
+    w2 = _g(gpack, OFF["W2P"], 4, 8, 8)
+    b2 = _g(gpack, OFF["B2"], 32)
+    by_param = {}
+    for g, m in enumerate(heads):
+        by_param[m[0].weight] = w1[8 * g:8 * g + 8]
+        by_param[m[0].bias] = b1[8 * g:8 * g + 8]
+        by_param[m[2].weight] = w2[g].t()
+        by_param[m[2].bias] = b2[8 * g:8 * g + 8]
+    by_param[gcl.layer_norm.weight] = _g(gpack, OFF["LNG"], 32)
+    by_param[gcl.layer_norm.bias] = _g(gpack, OFF["LNB"], 32)
+    by_param[gcl.coord_mlp[0].weight] = _g(gpack, OFF["WC1"], 32, 32)
+    by_param[gcl.coord_mlp[0].bias] = _g(gpack, OFF["BC1"], 32)
+    by_param[gcl.coord_mlp[2].weight] = _g(gpack, OFF["WC2"], 1, 32)
+    by_param[gcl.node_mlp[0].weight] = _g(gpack, OFF["WN1T"], 64, 32).t()
+    by_param[gcl.node_mlp[0].bias] = _g(gpack, OFF["BN1"], 32)
+    by_param[gcl.node_mlp[2].weight] = _g(gpack, OFF["WN2T"], 32, 32).t()
+    by_param[gcl.node_mlp[2].bias] = _g(gpack, OFF["BN2"], 32)
+    return [by_param[p].contiguous() for p in gcl.parameters()]
+
+
+def unpack_linear32_grad(gpack, lin):
+    """gpack [EMBED_PACK] -> [d weight (32,32), d bias (32)] of an embedding Linear."""
+    return [_g(gpack, 0, 32, 32).t().contiguous(), _g(gpack, 1024, 32).contiguous()]
