@@ -161,6 +161,48 @@ int egspr_pose_metrics(const float *R, const float *t, const float *gt_pose, con
 int egspr_feature_nn(const float *a, int na, const float *b, int nb, void *workspace, size_t workspace_bytes,
                      int32_t *idx, float *dist, void *stream);
 
+/* =====================================================================================================================
+ * Training step (BASELINE config 4): the backward pass `loss.backward()` runs through the same path at 3dm:1125.
+ * All gradient buffers are fp32; weight gradients are ACCUMULATED (+=) into grad packs that use the SAME layouts as
+ * the weight packs (the host mirror zero-fills them and maps them back onto the nn.Parameters' .grad).
+ * ===================================================================================================================== */
+
+/* ---- E_GCL.forward (3dm:280-289) backward for every cloud of the batch.
+ * Inputs saved by the forward pass: the layer INPUT state h, x4, P, Q and the per-node message sums agg (what
+ * egspr_egcl_forward left in agg_ws).  Nothing per-edge is saved: the edge kernel recomputes each edge's forward.
+ * csr_*: the row-major CSR of the forward pass; csc_ptr [G+1] / csc_eid [E]: the same edges grouped by col =
+ * edge_index[1] (egspr_csr_from_edges on the edge tensor with its two rows swapped gives exactly these as its
+ * csr_ptr / csr_eid outputs).
+ * dh_out [G][32], dx_out [G][3]: gradient w.r.t. the layer outputs (h', coord').  Writes dh_in [G][32], dx_in [G][3]
+ * (gradient w.r.t. the layer inputs; must not alias the *_out buffers) and adds to grad_pack [EGSPR_LAYER_PACK_FLOATS].
+ * workspace: egspr_egcl_backward_workspace_bytes(G, E).  Data path is deterministic (segment sums in CSR order);
+ * weight gradients are reduced per CTA and combined with one atomicAdd per entry and CTA. */
+size_t egspr_egcl_backward_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int egspr_egcl_backward(const float *h, const float *x4, const float *P, const float *Q, const float *agg,
+                        const int32_t *csr_ptr, const int32_t *csr_row, const int32_t *csr_col,
+                        const int32_t *csr_eid, const int32_t *csc_ptr, const int32_t *csc_eid,
+                        const float *edge_attr, float edge_attr_const, int64_t num_nodes,
+                        int64_t edges_per_cloud, int n_per_cloud, const float *layer_pack,
+                        const float *dh_out, const float *dx_out, float *dh_in, float *dx_in,
+                        float *grad_pack, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- embedding_in / embedding_out (nn.Linear(32,32), 3dm:320-321, 332, 337) as stand-alone ops for the training
+ * path (the inference path fuses them into the node kernels).  embed_pack: WT [in][out] + bias.
+ * backward: dx (optional) = dy W, grad_pack [EGSPR_EMBED_PACK_FLOATS] += (x^T dy, sum dy). */
+int egspr_linear32_forward(const float *x, int64_t rows, const float *embed_pack, float *y, void *stream);
+int egspr_linear32_backward(const float *x, const float *dy, int64_t rows, const float *embed_pack, float *dx,
+                            float *grad_pack, void *stream);
+
+/* ---- backward of egspr_head_train (3dm:696-758): given dR [pairs][9], dt [pairs][3] and (optionally) dsim
+ * [pairs][n] = gradient w.r.t. the similarity scores sim_out, writes the gradients of the four EGNN outputs:
+ * dh_src, dh_tgt [pairs][n][32], dx_src, dx_tgt [pairs][n][3].  The SVD is differentiated in closed form
+ * (R = V D U^T; for sigma pairs of equal sign only 1/(s_i + s_j) appears), fp64 per pair, fp32 per point.
+ * 2*n floats of dynamic shared memory: n <= 24576. */
+int egspr_head_train_backward(const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                              const float *x_out_tgt, const float *labels, const float *dR, const float *dt,
+                              const float *dsim, int pairs, int n, float *dh_src, float *dh_tgt,
+                              float *dx_src, float *dx_tgt, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ from .modules import (E_GCL, EGNN, CrossAttentionPoseRegression, knn_graph, knn_
                       get_edges_batch, unsorted_segment_sum, egnn_equi_loss, pose_loss,
                       save_checkpoint, load_checkpoint)
 from .engine import RegistrationEngine  # noqa: F401
+from . import train  # noqa: F401
 
 
 def build_model(checkpoint=None, device="cuda:0", n_layers=3, variant=None):

@@ -10,7 +10,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("EGSPR_LIB_PATH") or os.path.join(_HERE, "libegspr_b200.so")   # override: developer A/B builds
-SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_edge_ts.cu", "egnn_node_ts.cu", "head.cu", "feature_match.cu"]
+SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_edge_ts.cu", "egnn_node_ts.cu", "head.cu", "feature_match.cu",
+           "egnn_backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -39,6 +40,11 @@ SIGNATURES = {
     "egspr_head_train": (_i, [_p] * 6 + [_i, _i] + [_p] * 7),
     "egspr_pose_metrics": (_i, [_p] * 5 + [_i, _i, ctypes.c_double, _p, _p]),
     "egspr_feature_nn": (_i, [_p, _i, _p, _i, _p, _z, _p, _p, _p]),
+    "egspr_egcl_backward_workspace_bytes": (_z, [_l, _l]),
+    "egspr_egcl_backward": (_i, [_p] * 11 + [_p, _f, _l, _l, _i] + [_p] * 7 + [_z, _p]),
+    "egspr_linear32_forward": (_i, [_p, _l, _p, _p, _p]),
+    "egspr_linear32_backward": (_i, [_p, _p, _l, _p, _p, _p, _p]),
+    "egspr_head_train_backward": (_i, [_p] * 8 + [_i, _i] + [_p] * 5),
 }
 
 
@@ -50,7 +56,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(_CSRC, "egspr_common.cuh"), os.path.join(_CSRC, "egnn_layer.cuh"), os.path.join(_CSRC, "tcgen05.cuh"),
+    deps = sources() + [os.path.join(_CSRC, "egspr_common.cuh"), os.path.join(_CSRC, "egnn_layer.cuh"), os.path.join(_CSRC, "tcgen05.cuh"), os.path.join(_CSRC, "egnn_backward_math.cuh"),
                         os.path.join(_HERE, "..", "include", "egspr_b200.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 

@@ -1,0 +1,77 @@
+"""torch.autograd glue for the training step (3dm:1092-1126): two Functions whose backward passes are the
+hand-written kernels (ops.egnn_backward, ops.head_train_backward).  PyTorch only routes the gradients between them
+and onto the nn.Parameters' .grad -- the parameters stay the single source of truth, the weight packs and gradient
+packs are derived re-layouts (packing.py)."""
+import torch
+
+from . import ops, packing
+
+
+def egnn_param_list(egnn_or_layers, embedding_in=None, embedding_out=None):
+    """Flat parameter list in the order EGNNFunction returns gradients:
+    [embedding_in.weight, .bias]? + [embedding_out.weight, .bias]? + every layer's parameters()."""
+    params = []
+    if embedding_in is not None:
+        params += [embedding_in.weight, embedding_in.bias]
+    if embedding_out is not None:
+        params += [embedding_out.weight, embedding_out.bias]
+    for gcl in egnn_or_layers:
+        params += list(gcl.parameters())
+    return params
+
+
+class EGNNFunction(torch.autograd.Function):
+    """(feat [C,N,32], x [C,N,3], *params) -> (h_out, x_out); `spec` carries the non-tensor context."""
+
+    @staticmethod
+    def forward(ctx, spec, feat, x, *params):
+        layers, emb_in, emb_out, graph, edge_attr, edge_attr_const = spec
+        layer_packs = [g.layer_pack() for g in layers]
+        pin = packing.pack_linear32(emb_in) if emb_in is not None else None
+        pout = packing.pack_linear32(emb_out) if emb_out is not None else None
+        h_out, x_out, saved = ops.egnn_forward_saved(feat, x, graph, layer_packs, pin, pout, edge_attr=edge_attr,
+                                                     edge_attr_const=edge_attr_const)
+        ctx.spec = spec
+        ctx.saved = saved
+        ctx.packs = (layer_packs, pin, pout)
+        return h_out, x_out
+
+    @staticmethod
+    def backward(ctx, dh_out, dx_out):
+        layers, emb_in, emb_out, graph, _, _ = ctx.spec
+        layer_packs, pin, pout = ctx.packs
+        need_dfeat = ctx.needs_input_grad[1]
+        dfeat, dx, gpacks, g_in, g_out = ops.egnn_backward(ctx.saved, graph, layer_packs, pin, pout, dh_out, dx_out,
+                                                           need_dfeat=need_dfeat or emb_in is None)
+        grads = []
+        if emb_in is not None:
+            grads += packing.unpack_linear32_grad(g_in, emb_in)
+        if emb_out is not None:
+            grads += packing.unpack_linear32_grad(g_out, emb_out)
+        for gcl, gp in zip(layers, gpacks):
+            grads += packing.unpack_layer_grad(gp, gcl)
+        ctx.saved = None
+        return (None, dfeat if need_dfeat else None, dx, *grads)
+
+
+class HeadTrainFunction(torch.autograd.Function):
+    """(h_src_out, h_tgt_out, x_src_out, x_tgt_out, labels, gt_pose) -> (R, t, sim, w, H, loss_parts); gradients flow
+    through R, t and sim (3dm:681, 696-758)."""
+
+    @staticmethod
+    def forward(ctx, hs, ht, xs, xt, labels_f, gt_pose):
+        R, t, w, sim, Hm, lp = ops.head_train(hs, ht, xs, xt, labels_f, gt_pose)
+        ctx.save_for_backward(hs, ht, xs, xt, labels_f)
+        ctx.mark_non_differentiable(w, Hm, lp)
+        return R, t, sim, w, Hm, lp
+
+    @staticmethod
+    def backward(ctx, dR, dt, dsim, *_):
+        hs, ht, xs, xt, labels_f = ctx.saved_tensors
+        B = hs.shape[0]
+        if dR is None:
+            dR = torch.zeros((B, 3, 3), dtype=torch.float32, device=hs.device)
+        if dt is None:
+            dt = torch.zeros((B, 3), dtype=torch.float32, device=hs.device)
+        dhs, dht, dxs, dxt = ops.head_train_backward(hs, ht, xs, xt, labels_f, dR, dt, dsim)
+        return dhs, dht, dxs, dxt, None, None

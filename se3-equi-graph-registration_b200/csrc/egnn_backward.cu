@@ -1,0 +1,500 @@
+// Backward pass of the E_GCL / EGNN stack (the gradient `loss.backward()` produces in the reference's training
+// step, src/3dmatch_train_egnn_with_batch.py:1125, through E_GCL.forward 3dm:280-289 and EGNN.forward 3dm:328-340).
+//
+// Three kernels per layer, all fp32 on CUDA cores, deterministic data path (no atomics on activations):
+//   node_mlp_backward_kernel   thread = node: node_model (3dm:252-260) backward -> dh (direct part), dagg
+//   edge_backward_kernel       thread = edge (row-CSR order): recomputes the edge's forward from the layer input
+//                              (nothing per-edge is kept from the forward pass) and pushes (dagg[row], dx_out[row])
+//                              back to dpre (= dP[row] = dQ[col]) and the two endpoints' coordinate gradients,
+//                              written per ORIGINAL edge id
+//   node_gather_backward_kernel thread = node: sums dpre / dx over the node's row list (row-CSR) and col list
+//                              (col-CSR), then the P/Q halves of the first edge Linear back to dh
+// Weight gradients: every kernel stages the rows of its outer products in shared memory per 128-row tile, each
+// thread owns 8 (or 2 / 4) entries of a weight matrix in registers across all tiles of its CTA, column sums
+// (biases, LayerNorm, wc2) are transposed-reduced with warp shuffles; one atomicAdd per entry and CTA at the end.
+// The arithmetic itself lives in egnn_backward_math.cuh, which the CPU test-suite compiles with g++.
+#include "egnn_backward_math.cuh"
+#include "egspr_common.cuh"
+
+namespace egspr {
+using namespace bwd;
+
+constexpr int BT = 128;    // threads per CTA = rows (edges / nodes) per tile
+constexpr int RS = 33;     // stash row stride in floats: odd -> own-row writes and column reads are conflict-free
+constexpr unsigned FULLM = 0xffffffffu;
+
+// sum over the 32 lanes of v[lane'] for every column: returns, in lane L, sum over lanes of v[L]
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+    float a[16], b[8], c[4], d[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float keep = up ? v[j + 16] : v[j], send = up ? v[j] : v[j + 16];
+            a[j] = keep + __shfl_xor_sync(FULLM, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float keep = up ? a[j + 8] : a[j], send = up ? a[j] : a[j + 8];
+            b[j] = keep + __shfl_xor_sync(FULLM, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float keep = up ? b[j + 4] : b[j], send = up ? b[j] : b[j + 4];
+            c[j] = keep + __shfl_xor_sync(FULLM, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float keep = up ? c[j + 2] : c[j], send = up ? c[j] : c[j + 2];
+            d[j] = keep + __shfl_xor_sync(FULLM, send, 2);
+        }
+    }
+    const bool up = lane & 1;
+    const float keep = up ? d[1] : d[0], send = up ? d[0] : d[1];
+    return keep + __shfl_xor_sync(FULLM, send, 1);
+}
+
+// acc[q] += sum over the tile's rows of In[e][i] * Out[e][8 ob + q],  i = tid & 31, ob = tid >> 5
+__device__ __forceinline__ void outer8(float (&acc)[8], const float *__restrict__ sIn, const float *__restrict__ sOut) {
+    const int i = threadIdx.x & 31, ob = (threadIdx.x >> 5) * 8;
+#pragma unroll 4
+    for (int e = 0; e < BT; ++e) {
+        const float a = sIn[e * RS + i];
+        const float *o = sOut + e * RS + ob;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(a, o[q], acc[q]);
+    }
+}
+// in_major: gradient matrix stored [in][out] (transposed packs) else [out][in]
+__device__ __forceinline__ void flush8(const float (&acc)[8], float *__restrict__ gp, bool in_major) {
+    const int i = threadIdx.x & 31, ob = (threadIdx.x >> 5) * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(gp + (in_major ? 32 * i + ob + q : 32 * (ob + q) + i), acc[q]);
+}
+
+__device__ __forceinline__ void stash_row(float *__restrict__ dst, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+}
+__device__ __forceinline__ void load_row32g(float (&v)[32], const float *__restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = ldg4(p + 4 * i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_row32g(float *__restrict__ p, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4 *>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void add_row32g(float (&v)[32], const float *__restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = ldg4(p + 4 * i);
+        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// node MLP backward
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NB_W_LO = B_WN1T, NB_W_N = B_BN2 + 32 - B_WN1T;       // pack slice this kernel reads
+constexpr size_t NB_SMEM = sizeof(float) * (NB_W_N + 5 * BT * RS);
+
+__global__ void __launch_bounds__(BT) node_mlp_backward_kernel(const float *__restrict__ h, const float *__restrict__ agg,
+                                                               const float *__restrict__ dh_out, int64_t G,
+                                                               const float *__restrict__ pack, float *__restrict__ dh_in,
+                                                               float *__restrict__ dagg, float *__restrict__ gpack) {
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;                                   // pack[NB_W_LO, +NB_W_N)
+    float *sA = smem + NB_W_N, *sDout = sA + BT * RS, *sH = sDout + BT * RS, *sAgg = sH + BT * RS, *sDz = sAgg + BT * RS;
+    for (int i = threadIdx.x; i < NB_W_N; i += BT) sw[i] = __ldg(pack + NB_W_LO + i);
+    __syncthreads();
+    const float *w = sw - NB_W_LO;
+    float accW2[8] = {0}, accW1h[8] = {0}, accW1a[8] = {0};
+    float colDout = 0.f, colDz = 0.f;
+    const int64_t tiles = (G + BT - 1) / BT;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t n = tile * BT + threadIdx.x;
+        float *rA = sA + threadIdx.x * RS, *rD = sDout + threadIdx.x * RS, *rH = sH + threadIdx.x * RS,
+              *rG = sAgg + threadIdx.x * RS, *rZ = sDz + threadIdx.x * RS;
+        float dout[32], dz1[32];
+        if (n < G) {
+            {
+                float t[32];
+                load_row32g(t, h + n * H);
+                stash_row(rH, t);
+                load_row32g(t, agg + n * H);
+                stash_row(rG, t);
+            }
+            load_row32g(dout, dh_out + n * H);
+            stash_row(rD, dout);
+            node_backward(w, rH, rG, dout, rD, rA, rZ, dh_in + n * H, dagg + n * H);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dz1[j] = rZ[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { dout[j] = 0.f; dz1[j] = 0.f; rA[j] = 0.f; rH[j] = 0.f; rG[j] = 0.f; rZ[j] = 0.f; rD[j] = 0.f; }
+        }
+        colDout += warp_colsum32(dout);
+        colDz += warp_colsum32(dz1);
+        __syncthreads();
+        outer8(accW2, sA, sDout);        // dWn2T[i][o] += a[i] dout[o]
+        outer8(accW1h, sH, sDz);         // dWn1T[i][o] += h[i] dz1[o]
+        outer8(accW1a, sAgg, sDz);       // dWn1T[32+i][o] += agg[i] dz1[o]
+        __syncthreads();
+    }
+    flush8(accW2, gpack + B_WN2T, true);
+    flush8(accW1h, gpack + B_WN1T, true);
+    flush8(accW1a, gpack + B_WN1T + 1024, true);
+    const int lane = threadIdx.x & 31;
+    atomicAdd(gpack + B_BN2 + lane, colDout);
+    atomicAdd(gpack + B_BN1 + lane, colDz);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// edge backward
+// ---------------------------------------------------------------------------------------------------------------
+struct EdgeBwdArgs {
+    const float *x4, *P, *Q;
+    const int32_t *csr_ptr, *csr_row, *csr_col, *csr_eid;
+    const float *edge_attr;
+    float edge_attr_const;
+    int64_t num_nodes, edges_per_cloud;
+    int n_per_cloud;
+    const float *pack;
+    const float *dagg, *dx_out;     // [G][32], [G][3]
+    float *dpre, *dxe;              // [E][32], [E][8] indexed by cloud * edges_per_cloud + original edge id
+    float *gpack;
+};
+
+constexpr int EB_W_N = EDGE_PART + 32;     // edge part of the pack + the edge_attr column
+constexpr size_t EB_SMEM = sizeof(float) * (EB_W_N + V_COUNT * BT * RS + BT * 13);
+
+struct DevSink {
+    float colacc[C_COUNT];
+    template <int ID>
+    __host__ __device__ __forceinline__ void col(const float (&v)[32]) {
+#ifdef __CUDA_ARCH__
+        colacc[ID] += warp_colsum32(v);
+#endif
+    }
+};
+
+__global__ void __launch_bounds__(BT) edge_backward_kernel(const EdgeBwdArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;                          // [0,1824) edge part, [1824,1856) edge_attr column
+    float *sV = smem + EB_W_N;                 // V_COUNT stashes of [BT][RS]
+    float *sGeo = sV + V_COUNT * BT * RS;      // [BT][13]
+    for (int i = threadIdx.x; i < EDGE_PART; i += BT) sw[i] = __ldg(a.pack + i);
+    if (threadIdx.x < 32) sw[EDGE_PART + threadIdx.x] = __ldg(a.pack + B_WEA + threadIdx.x);
+    __syncthreads();
+    const int tid = threadIdx.x;
+    DevSink sink;
+    float *rM = sV + V_M * BT * RS + tid * RS, *rDC1 = sV + V_DC1 * BT * RS + tid * RS, *rA1 = sV + V_A1 * BT * RS + tid * RS,
+          *rDU = sV + V_DU * BT * RS + tid * RS, *rDPRE = sV + V_DPRE * BT * RS + tid * RS, *rGeo = sGeo + tid * 13;
+#pragma unroll
+    for (int c = 0; c < C_COUNT; ++c) sink.colacc[c] = 0.f;
+    float accWc1[8] = {0}, accW2[2] = {0, 0}, accWg[4] = {0, 0, 0, 0};
+    const int64_t E = __ldg(a.csr_ptr + a.num_nodes);
+    const int64_t tiles = (E + BT - 1) / BT;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t p0 = tile * BT + tid;
+        const bool valid = p0 < E;
+        const int64_t p = valid ? p0 : E - 1;          // idle threads redo the last edge with zero upstream gradient
+        const int r = __ldg(a.csr_row + p), c = __ldg(a.csr_col + p);
+        const int64_t cloud = r / a.n_per_cloud;
+        const int64_t ge = cloud * a.edges_per_cloud + __ldg(a.csr_eid + p);
+        const float ea = a.edge_attr ? __ldg(a.edge_attr + ge) : a.edge_attr_const;
+        const float4 xr4 = ldg4(a.x4 + (int64_t)r * 4), xc4 = ldg4(a.x4 + (int64_t)c * 4);
+        const float xr[3] = {xr4.x, xr4.y, xr4.z}, xc[3] = {xc4.x, xc4.y, xc4.z};
+        {
+            float pq[32];
+            load_row32g(pq, a.P + (int64_t)r * H);
+            add_row32g(pq, a.Q + (int64_t)c * H);
+            stash_row(rDPRE, pq);
+        }
+        float dagg[32], dxo[3];
+        if (valid) {
+            load_row32g(dagg, a.dagg + (int64_t)r * H);
+            dxo[0] = __ldg(a.dx_out + (int64_t)r * 3); dxo[1] = __ldg(a.dx_out + (int64_t)r * 3 + 1); dxo[2] = __ldg(a.dx_out + (int64_t)r * 3 + 2);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dagg[j] = 0.f;
+            dxo[0] = dxo[1] = dxo[2] = 0.f;
+        }
+        float dxr[3], dxc[3];
+        edge_backward(sw, sw + EDGE_PART, xr, xc, ea, dagg, dxo, rM, rDC1, rA1, rDU, rDPRE, rGeo, sink, dxr, dxc);
+        if (valid) {
+            float dpre[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dpre[j] = rDPRE[j];
+            store_row32g(a.dpre + ge * H, dpre);
+            *reinterpret_cast<float4 *>(a.dxe + ge * 8) = make_float4(dxr[0], dxr[1], dxr[2], 0.f);
+            *reinterpret_cast<float4 *>(a.dxe + ge * 8 + 4) = make_float4(dxc[0], dxc[1], dxc[2], 0.f);
+        }
+        __syncthreads();
+        // weight gradients of this tile
+        outer8(accWc1, sV + V_M * BT * RS, sV + V_DC1 * BT * RS);          // dWc1[o][i] += dc1[o] m[i]
+        {
+            const int idx = 2 * tid, hb = (idx >> 6) * 8, ii = (idx >> 3) & 7, oo = idx & 7;   // dW2P[hd][i][o] += a1 du
+            const float *sA1 = sV + V_A1 * BT * RS + hb + ii, *sDu = sV + V_DU * BT * RS + hb + oo;
+#pragma unroll 4
+            for (int e = 0; e < BT; ++e) {
+                const float av = sA1[e * RS];
+                accW2[0] = fmaf(av, sDu[e * RS], accW2[0]);
+                accW2[1] = fmaf(av, sDu[e * RS + 1], accW2[1]);
+            }
+        }
+        {
+            const int o = tid & 31, gb = tid >> 5;                             // dWg[k][o] += geo[k] dpre[o], k = gb + 4 j
+            const float *sDp = sV + V_DPRE * BT * RS + o;
+#pragma unroll 4
+            for (int e = 0; e < BT; ++e) {
+                const float dv = sDp[e * RS];
+                const float *gr = sGeo + e * 13 + gb;
+                accWg[0] = fmaf(gr[0], dv, accWg[0]);
+                accWg[1] = fmaf(gr[4], dv, accWg[1]);
+                accWg[2] = fmaf(gr[8], dv, accWg[2]);
+                if (gb == 0) accWg[3] = fmaf(gr[12], dv, accWg[3]);
+            }
+        }
+        __syncthreads();
+    }
+    flush8(accWc1, a.gpack + B_WC1, false);
+    atomicAdd(a.gpack + B_W2P + 2 * tid, accW2[0]);
+    atomicAdd(a.gpack + B_W2P + 2 * tid + 1, accW2[1]);
+    {
+        const int o = tid & 31, gb = tid >> 5;
+        atomicAdd(a.gpack + B_WG + 32 * gb + o, accWg[0]);
+        atomicAdd(a.gpack + B_WG + 32 * (gb + 4) + o, accWg[1]);
+        atomicAdd(a.gpack + B_WG + 32 * (gb + 8) + o, accWg[2]);
+        if (gb == 0) atomicAdd(a.gpack + B_WEA + o, accWg[3]);
+    }
+    const int lane = tid & 31;
+    atomicAdd(a.gpack + B_WC2 + lane, sink.colacc[C_DWC2]);
+    atomicAdd(a.gpack + B_BC1 + lane, sink.colacc[C_DBC1]);
+    atomicAdd(a.gpack + B_LNB + lane, sink.colacc[C_DLNB]);
+    atomicAdd(a.gpack + B_LNG + lane, sink.colacc[C_DLNG]);
+    atomicAdd(a.gpack + B_B2 + lane, sink.colacc[C_DB2]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// node gather + P/Q backward
+// ---------------------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    const float *h;
+    const int32_t *csr_ptr, *csr_eid, *csc_ptr, *csc_eid;
+    int64_t num_nodes, edges_per_cloud;
+    int n_per_cloud;
+    const float *pack;
+    const float *dpre, *dxe, *dx_out;
+    float *dh_in, *dx_in;      // dh_in holds the node-MLP part on entry
+    float *gpack;
+};
+constexpr int GB_W_LO = B_WPT, GB_W_N = 2048;
+constexpr size_t GB_SMEM = sizeof(float) * (GB_W_N + 3 * BT * RS);
+
+__global__ void __launch_bounds__(BT) node_gather_backward_kernel(const GatherArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;
+    float *sH = smem + GB_W_N, *sDp = sH + BT * RS, *sDq = sDp + BT * RS;
+    for (int i = threadIdx.x; i < GB_W_N; i += BT) sw[i] = __ldg(a.pack + GB_W_LO + i);
+    __syncthreads();
+    float accP[8] = {0}, accQ[8] = {0};
+    float colQ = 0.f;
+    const int64_t G = a.num_nodes;
+    const int64_t tiles = (G + BT - 1) / BT;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t n = tile * BT + threadIdx.x;
+        float *rH = sH + threadIdx.x * RS, *rP = sDp + threadIdx.x * RS, *rQ = sDq + threadIdx.x * RS;
+        float dq[32];
+        if (n < G) {
+            const int64_t ebase = (n / a.n_per_cloud) * a.edges_per_cloud;
+            float dp[32];
+            float dx[3] = {__ldg(a.dx_out + n * 3), __ldg(a.dx_out + n * 3 + 1), __ldg(a.dx_out + n * 3 + 2)};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { dp[j] = 0.f; dq[j] = 0.f; }
+            for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; ++p) {   // edges with row == n
+                const int64_t ge = ebase + __ldg(a.csr_eid + p);
+                add_row32g(dp, a.dpre + ge * H);
+                const float4 t = ldg4(a.dxe + ge * 8);
+                dx[0] += t.x; dx[1] += t.y; dx[2] += t.z;
+            }
+            for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; ++p) {   // edges with col == n
+                const int64_t ge = ebase + __ldg(a.csc_eid + p);
+                add_row32g(dq, a.dpre + ge * H);
+                const float4 t = ldg4(a.dxe + ge * 8 + 4);
+                dx[0] += t.x; dx[1] += t.y; dx[2] += t.z;
+            }
+            a.dx_in[n * 3] = dx[0]; a.dx_in[n * 3 + 1] = dx[1]; a.dx_in[n * 3 + 2] = dx[2];
+            linear32_backward_input(sw, dp, a.dh_in + n * H, true);
+            linear32_backward_input(sw + 1024, dq, a.dh_in + n * H, true);
+            float hv[32];
+            load_row32g(hv, a.h + n * H);
+            stash_row(rH, hv); stash_row(rP, dp);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { dq[j] = 0.f; rH[j] = 0.f; rP[j] = 0.f; }
+        }
+        stash_row(rQ, dq);
+        colQ += warp_colsum32(dq);
+        __syncthreads();
+        outer8(accP, sH, sDp);      // dWPT[i][o] += h[i] dP[o]
+        outer8(accQ, sH, sDq);
+        __syncthreads();
+    }
+    flush8(accP, a.gpack + B_WPT, true);
+    flush8(accQ, a.gpack + B_WQT, true);
+    atomicAdd(a.gpack + B_BQ + (threadIdx.x & 31), colQ);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Linear(32,32) forward / backward (embedding_in 3dm:332, embedding_out 3dm:337) -- embed pack: WT [in][out], b
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT) linear32_forward_kernel(const float *__restrict__ x, int64_t rows,
+                                                              const float *__restrict__ pack, float *__restrict__ y) {
+    __shared__ __align__(16) float sw[1056];
+    for (int i = threadIdx.x; i < 1056; i += BT) sw[i] = __ldg(pack + i);
+    __syncthreads();
+    for (int64_t n = (int64_t)blockIdx.x * BT + threadIdx.x; n < rows; n += (int64_t)gridDim.x * BT) {
+        float xv[32], yv[32];
+        load_row32g(xv, x + n * H);
+#pragma unroll
+        for (int o = 0; o < 32; ++o) yv[o] = sw[1024 + o];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+#pragma unroll
+            for (int o = 0; o < 32; ++o) yv[o] = fmaf(sw[32 * i + o], xv[i], yv[o]);
+        store_row32g(y + n * H, yv);
+    }
+}
+
+constexpr size_t LB_SMEM = sizeof(float) * (1024 + 2 * BT * RS);
+
+__global__ void __launch_bounds__(BT) linear32_backward_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                               int64_t rows, const float *__restrict__ pack,
+                                                               float *__restrict__ dx, float *__restrict__ gpack) {
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem, *sX = smem + 1024, *sDy = sX + BT * RS;
+    for (int i = threadIdx.x; i < 1024; i += BT) sw[i] = __ldg(pack + i);
+    __syncthreads();
+    float acc[8] = {0};
+    float colDy = 0.f;
+    const int64_t tiles = (rows + BT - 1) / BT;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t n = tile * BT + threadIdx.x;
+        float *rX = sX + threadIdx.x * RS, *rD = sDy + threadIdx.x * RS;
+        float dyv[32];
+        if (n < rows) {
+            float xv[32];
+            load_row32g(xv, x + n * H);
+            load_row32g(dyv, dy + n * H);
+            stash_row(rX, xv);
+            if (dx) linear32_backward_input(sw, dyv, dx + n * H, false);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { dyv[j] = 0.f; rX[j] = 0.f; }
+        }
+        stash_row(rD, dyv);
+        colDy += warp_colsum32(dyv);
+        __syncthreads();
+        outer8(acc, sX, sDy);       // dWT[i][o] += x[i] dy[o]
+        __syncthreads();
+    }
+    flush8(acc, gpack, true);
+    atomicAdd(gpack + 1024 + (threadIdx.x & 31), colDy);
+}
+
+template <class K>
+static int prep_kernel(K kernel, size_t smem, int &ctas_per_sm) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EGSPR_E_LAUNCH;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, BT, smem) != cudaSuccess || ctas_per_sm < 1)
+        ctas_per_sm = 1;
+    return EGSPR_OK;
+}
+static unsigned grid_for(int64_t tiles, int ctas_per_sm) {
+    int64_t g = (int64_t)sm_count() * ctas_per_sm;
+    if (g > tiles) g = tiles;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace egspr
+
+extern "C" size_t egspr_egcl_backward_workspace_bytes(int64_t num_nodes, int64_t num_edges) {
+    if (num_nodes <= 0 || num_edges < 0) return 0;
+    return sizeof(float) * ((size_t)num_nodes * 32 + (size_t)num_edges * 40) + 256;
+}
+
+extern "C" int egspr_egcl_backward(const float *h, const float *x4, const float *P, const float *Q, const float *agg,
+                                   const int32_t *csr_ptr, const int32_t *csr_row, const int32_t *csr_col,
+                                   const int32_t *csr_eid, const int32_t *csc_ptr, const int32_t *csc_eid,
+                                   const float *edge_attr, float edge_attr_const, int64_t num_nodes,
+                                   int64_t edges_per_cloud, int n_per_cloud, const float *layer_pack,
+                                   const float *dh_out, const float *dx_out, float *dh_in, float *dx_in,
+                                   float *grad_pack, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace egspr;
+    if (!h || !x4 || !P || !Q || !agg || !csr_ptr || !csr_row || !csr_col || !csr_eid || !csc_ptr || !csc_eid ||
+        !layer_pack || !dh_out || !dx_out || !dh_in || !dx_in || !grad_pack || !workspace || num_nodes <= 0 ||
+        n_per_cloud <= 0 || edges_per_cloud <= 0 || num_nodes % n_per_cloud != 0)
+        return EGSPR_E_INVALID;
+    if (dh_in == dh_out || dx_in == dx_out) return EGSPR_E_INVALID;
+    const int64_t E = (num_nodes / n_per_cloud) * edges_per_cloud;
+    if (workspace_bytes < egspr_egcl_backward_workspace_bytes(num_nodes, E)) return EGSPR_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *dagg = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    float *dpre = dagg + (size_t)num_nodes * 32;
+    float *dxe = dpre + (size_t)E * 32;
+    static int occ_node = 0, occ_edge = 0, occ_gather = 0;
+    if (!occ_node) {
+        if (int e = prep_kernel(node_mlp_backward_kernel, NB_SMEM, occ_node)) return e;
+        if (int e = prep_kernel(edge_backward_kernel, EB_SMEM, occ_edge)) return e;
+        if (int e = prep_kernel(node_gather_backward_kernel, GB_SMEM, occ_gather)) return e;
+    }
+    const int64_t ntiles = (num_nodes + BT - 1) / BT, etiles = (E + BT - 1) / BT;
+    node_mlp_backward_kernel<<<grid_for(ntiles, occ_node), BT, NB_SMEM, st>>>(h, agg, dh_out, num_nodes, layer_pack, dh_in, dagg, grad_pack);
+    EGSPR_CHECK_LAUNCH();
+    EdgeBwdArgs ea{x4, P, Q, csr_ptr, csr_row, csr_col, csr_eid, edge_attr, edge_attr_const, num_nodes, edges_per_cloud,
+                   n_per_cloud, layer_pack, dagg, dx_out, dpre, dxe, grad_pack};
+    edge_backward_kernel<<<grid_for(etiles, occ_edge), BT, EB_SMEM, st>>>(ea);
+    EGSPR_CHECK_LAUNCH();
+    GatherArgs ga{h, csr_ptr, csr_eid, csc_ptr, csc_eid, num_nodes, edges_per_cloud, n_per_cloud, layer_pack, dpre, dxe,
+                  dx_out, dh_in, dx_in, grad_pack};
+    node_gather_backward_kernel<<<grid_for(ntiles, occ_gather), BT, GB_SMEM, st>>>(ga);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_linear32_forward(const float *x, int64_t rows, const float *embed_pack, float *y, void *stream) {
+    using namespace egspr;
+    if (!x || !embed_pack || !y || rows <= 0) return EGSPR_E_INVALID;
+    const int64_t tiles = (rows + BT - 1) / BT;
+    linear32_forward_kernel<<<grid_for(tiles, 8), BT, 0, (cudaStream_t)stream>>>(x, rows, embed_pack, y);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_linear32_backward(const float *x, const float *dy, int64_t rows, const float *embed_pack, float *dx,
+                                       float *grad_pack, void *stream) {
+    using namespace egspr;
+    if (!x || !dy || !embed_pack || !grad_pack || rows <= 0) return EGSPR_E_INVALID;
+    static int occ = 0;
+    if (!occ) {
+        if (int e = prep_kernel(linear32_backward_kernel, LB_SMEM, occ)) return e;
+    }
+    const int64_t tiles = (rows + BT - 1) / BT;
+    linear32_backward_kernel<<<grid_for(tiles, occ), BT, LB_SMEM, (cudaStream_t)stream>>>(x, dy, rows, embed_pack, dx, grad_pack);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}

@@ -6,10 +6,12 @@
 // with g++ to check every formula against torch autograd of the oracle on the CPU (no GPU needed).
 //
 // The forward state of an edge is recomputed here from the layer input (h -> P,Q; x), nothing per-edge is kept
-// from the forward pass.  Vectors a weight gradient needs are handed to a `Sink`:
-//     sink.vec<ID>(v[32])     rows of the outer products   dW += sum_e out_e (x) in_e
-//     sink.col<ID>(v[32])     rows whose column sums are bias / LayerNorm / wc2 gradients
-//     sink.geo(g[13])         the 13 geometric inputs [radial, dist, dot, so3(9), edge_attr]
+// from the forward pass.  The 32-vectors the weight gradients need (rows of the outer products
+// dW += sum_e out_e (x) in_e) are written to caller-provided ROWS -- on the device the thread's private rows of the
+// shared-memory tile the CTA reduces afterwards, on the host plain arrays.  The rows double as the working storage
+// of the loops: every large loop is rolled over an index that addresses a row (or the weights) and unrolled over
+// an index that addresses registers, so the code stays small and no register array is indexed dynamically.
+// Vectors whose column sums are bias / LayerNorm / wc2 gradients go to `sink.col<ID>(v[32])`.
 #pragma once
 #include <math.h>
 
@@ -29,6 +31,9 @@ constexpr int B_WG = 0, B_W2P = 384, B_B2 = 640, B_LNG = 672, B_LNB = 704, B_WC1
 
 enum VecId { V_M = 0, V_DC1 = 1, V_A1 = 2, V_DU = 3, V_DPRE = 4, V_COUNT = 5 };
 enum ColId { C_DWC2 = 0, C_DBC1 = 1, C_DLNB = 2, C_DLNG = 3, C_DB2 = 4, C_COUNT = 5 };
+
+struct alignas(16) F4 { float x, y, z, w; };
+EGSPR_HD F4 ld4(const float *p) { return *reinterpret_cast<const F4 *>(p); }     // p 16-byte aligned (weights)
 
 EGSPR_HD float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
@@ -108,42 +113,61 @@ EGSPR_HD void edge_geometry_backward(const float *xr, const float *xc, const Edg
 }
 
 // One edge: recompute the forward (edge_model 3dm:231-250, coord_model 3dm:262-268) and push the gradient back.
-//   w        layer pack (shared memory on the device)
-//   xr, xc   coordinates of row / col endpoint;  Pr = P[row], Qc = Q[col] (32 floats each);  ea = edge_attr value
-//   dagg     d loss / d agg[row]  (32)           dxo = d loss / d coord_out[row]  (3)
-// Outputs: dpre[32] (= gradient of P[row] and of Q[col]), dxr[3], dxc[3]; weight-gradient rows go to `sink`.
+//   w        layer pack, 16-byte aligned (shared memory on the device; only the edge part [0, 1824) is read);
+//            wea = the edge_attr column (pack + B_WEA)
+//   xr, xc   coordinates of row / col endpoint;  ea = edge_attr value
+//   dagg     d loss / d agg[row]  (32 floats)    dxo = d loss / d coord_out[row]  (3)
+//   rows     rDPRE holds P[row] + Q[col] on entry.  On return: rM = message m, rDC1 = d loss / d (coord_mlp.0 output),
+//            rA1 = SiLU output of the first edge Linear, rDU = d loss / d (LayerNorm input), rDPRE = d loss / d (first
+//            Linear output) = the gradient of P[row] and of Q[col];  geo[13] = [radial, dist, dot, so3(9), edge_attr]
+// Outputs: dxr[3], dxc[3] (coordinate gradients of the two endpoints).
 template <class Sink>
-EGSPR_HD void edge_backward(const float *w, const float *xr, const float *xc, const float *Pr, const float *Qc,
-                            float ea, const float *dagg, const float *dxo, Sink &sink, float *dpre, float *dxr,
-                            float *dxc) {
+EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, const float *xc, float ea,
+                            const float *dagg, const float *dxo, float *rM, float *rDC1, float *rA1, float *rDU,
+                            float *rDPRE, float *geo, Sink &sink, float *dxr, float *dxc) {
     EdgeGeo g;
-    float geo[13];
     edge_geometry(xr, xc, g, geo);
     geo[12] = ea;
-    sink.geo(geo);
-    // first edge Linear, P/Q factorised (bias folded in Q), + SiLU
-    float a1[32], ds1[32];
+    float gk[12];
 #pragma unroll
-    for (int o = 0; o < 32; ++o) {
-        float pre = Pr[o] + Qc[o];
+    for (int k = 0; k < 12; ++k) gk[k] = geo[k];
+    // first edge Linear, P/Q factorised (bias folded in Q), + SiLU.  rDPRE: pq -> d silu / d pre
+#pragma unroll 1
+    for (int o4 = 0; o4 < 32; o4 += 4) {
+        const F4 we = ld4(wea + o4);
+        float p0 = fmaf(we.x, ea, rDPRE[o4]), p1 = fmaf(we.y, ea, rDPRE[o4 + 1]), p2 = fmaf(we.z, ea, rDPRE[o4 + 2]),
+              p3 = fmaf(we.w, ea, rDPRE[o4 + 3]);
 #pragma unroll
-        for (int k = 0; k < 12; ++k) pre = fmaf(w[B_WG + 32 * k + o], geo[k], pre);
-        pre = fmaf(w[B_WEA + o], ea, pre);
-        const float sg = sigmoidf_(pre);
-        a1[o] = pre * sg;
-        ds1[o] = sg * (1.0f + pre * (1.0f - sg));           // d silu / d pre
+        for (int k = 0; k < 12; ++k) {
+            const F4 wv = ld4(w + B_WG + 32 * k + o4);
+            p0 = fmaf(wv.x, gk[k], p0); p1 = fmaf(wv.y, gk[k], p1); p2 = fmaf(wv.z, gk[k], p2); p3 = fmaf(wv.w, gk[k], p3);
+        }
+        const float pr[4] = {p0, p1, p2, p3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float sg = sigmoidf_(pr[q]);
+            rA1[o4 + q] = pr[q] * sg;
+            rDPRE[o4 + q] = sg * (1.0f + pr[q] * (1.0f - sg));
+        }
     }
-    sink.template vec<V_A1>(a1);
     // per-head second Linear (block diagonal) + LayerNorm(32), eps 1e-5, biased variance  (:245-249)
     float uh[32];
 #pragma unroll
-    for (int o = 0; o < 32; ++o) uh[o] = w[B_B2 + o];
+    for (int o4 = 0; o4 < 32; o4 += 4) {
+        const F4 b = ld4(w + B_B2 + o4);
+        uh[o4] = b.x; uh[o4 + 1] = b.y; uh[o4 + 2] = b.z; uh[o4 + 3] = b.w;
+    }
 #pragma unroll
-    for (int hd = 0; hd < 4; ++hd)
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int o = 0; o < 8; ++o) uh[8 * hd + o] = fmaf(w[B_W2P + 64 * hd + 8 * i + o], a1[8 * hd + i], uh[8 * hd + o]);
+    for (int hd = 0; hd < 4; ++hd) {
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+            const float av = rA1[8 * hd + i];
+            const F4 w0 = ld4(w + B_W2P + 64 * hd + 8 * i), w1 = ld4(w + B_W2P + 64 * hd + 8 * i + 4);
+            float *u = uh + 8 * hd;
+            u[0] = fmaf(w0.x, av, u[0]); u[1] = fmaf(w0.y, av, u[1]); u[2] = fmaf(w0.z, av, u[2]); u[3] = fmaf(w0.w, av, u[3]);
+            u[4] = fmaf(w1.x, av, u[4]); u[5] = fmaf(w1.y, av, u[5]); u[6] = fmaf(w1.z, av, u[6]); u[7] = fmaf(w1.w, av, u[7]);
+        }
+    }
     float mean = 0.f;
 #pragma unroll
     for (int o = 0; o < 32; ++o) mean += uh[o];
@@ -152,135 +176,177 @@ EGSPR_HD void edge_backward(const float *w, const float *xr, const float *xc, co
 #pragma unroll
     for (int o = 0; o < 32; ++o) { const float t = uh[o] - mean; var = fmaf(t, t, var); }
     const float rstd = 1.0f / sqrtf(var * (1.0f / 32.0f) + 1e-5f);
-    float m[32];
-#pragma unroll
-    for (int o = 0; o < 32; ++o) { uh[o] = (uh[o] - mean) * rstd; m[o] = fmaf(uh[o], w[B_LNG + o], w[B_LNB + o]); }
-    sink.template vec<V_M>(m);
     // coord MLP: s = wc2 . SiLU(Wc1 m + bc1)  (:219-229);  trans = coord_diff * s  (:264)
     const float dsc = g.d[0] * dxo[0] + g.d[1] * dxo[1] + g.d[2] * dxo[2];   // d loss / d s
     float s = 0.f;
-    float dc1[32];
     {
-        float a2ds[32];
+        float m[32];
 #pragma unroll
         for (int o = 0; o < 32; ++o) {
-            float c1 = w[B_BC1 + o];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) c1 = fmaf(w[B_WC1 + 32 * o + i], m[i], c1);
-            const float sg = sigmoidf_(c1);
-            const float a2 = c1 * sg;
-            s = fmaf(w[B_WC2 + o], a2, s);
-            a2ds[o] = a2 * dsc;
-            dc1[o] = w[B_WC2 + o] * dsc * (sg * (1.0f + c1 * (1.0f - sg)));
+            uh[o] = (uh[o] - mean) * rstd;
+            m[o] = fmaf(uh[o], w[B_LNG + o], w[B_LNB + o]);
+            rM[o] = m[o];
         }
-        sink.template col<C_DWC2>(a2ds);
+#pragma unroll 1
+        for (int o = 0; o < 32; ++o) {
+            float c0 = w[B_BC1 + o], c1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                const F4 w0 = ld4(w + B_WC1 + 32 * o + i), w1 = ld4(w + B_WC1 + 32 * o + i + 4);
+                c0 = fmaf(w0.x, m[i], c0); c1 = fmaf(w0.y, m[i + 1], c1); c0 = fmaf(w0.z, m[i + 2], c0); c1 = fmaf(w0.w, m[i + 3], c1);
+                c0 = fmaf(w1.x, m[i + 4], c0); c1 = fmaf(w1.y, m[i + 5], c1); c0 = fmaf(w1.z, m[i + 6], c0); c1 = fmaf(w1.w, m[i + 7], c1);
+            }
+            const float c = c0 + c1;
+            const float sg = sigmoidf_(c);
+            const float a2 = c * sg;
+            const float wc = w[B_WC2 + o];
+            s = fmaf(wc, a2, s);
+            rDU[o] = a2 * dsc;                                              // scratch: rows of the wc2 gradient
+            rDC1[o] = wc * dsc * (sg * (1.0f + c * (1.0f - sg)));
+        }
     }
-    sink.template vec<V_DC1>(dc1);
-    sink.template col<C_DBC1>(dc1);
+    {
+        float v[32];
+#pragma unroll
+        for (int o = 0; o < 32; ++o) v[o] = rDU[o];
+        sink.template col<C_DWC2>(v);
+#pragma unroll
+        for (int o = 0; o < 32; ++o) v[o] = rDC1[o];
+        sink.template col<C_DBC1>(v);
+    }
     // message gradient: from the node aggregate and from the coord MLP
     float dm[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) dm[i] = dagg[i];
+#pragma unroll 1
+    for (int o = 0; o < 32; ++o) {
+        const float dc = rDC1[o];
 #pragma unroll
-    for (int o = 0; o < 32; ++o)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) dm[i] = fmaf(w[B_WC1 + 32 * o + i], dc1[o], dm[i]);
+        for (int i = 0; i < 32; i += 4) {
+            const F4 wv = ld4(w + B_WC1 + 32 * o + i);
+            dm[i] = fmaf(wv.x, dc, dm[i]); dm[i + 1] = fmaf(wv.y, dc, dm[i + 1]);
+            dm[i + 2] = fmaf(wv.z, dc, dm[i + 2]); dm[i + 3] = fmaf(wv.w, dc, dm[i + 3]);
+        }
+    }
     sink.template col<C_DLNB>(dm);
     // LayerNorm backward
-    float du[32];
     {
         float dg[32];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             dg[i] = dm[i] * uh[i];
-            const float duh = dm[i] * w[B_LNG + i];
-            du[i] = duh;
-            s1 += duh;
-            s2 = fmaf(duh, uh[i], s2);
+            dm[i] *= w[B_LNG + i];
+            s1 += dm[i];
+            s2 = fmaf(dm[i], uh[i], s2);
         }
         sink.template col<C_DLNG>(dg);
         s1 *= (1.0f / 32.0f);
         s2 *= (1.0f / 32.0f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) du[i] = rstd * (du[i] - s1 - uh[i] * s2);
+        for (int i = 0; i < 32; ++i) { dm[i] = rstd * (dm[i] - s1 - uh[i] * s2); rDU[i] = dm[i]; }   // dm is now du
     }
-    sink.template vec<V_DU>(du);
-    sink.template col<C_DB2>(du);
-    // second Linear backward + SiLU backward
+    sink.template col<C_DB2>(dm);
+    // second Linear backward + SiLU backward.  rDPRE: d silu / d pre -> dpre
 #pragma unroll
-    for (int hd = 0; hd < 4; ++hd)
-#pragma unroll
+    for (int hd = 0; hd < 4; ++hd) {
+#pragma unroll 1
         for (int i = 0; i < 8; ++i) {
-            float t = 0.f;
-#pragma unroll
-            for (int o = 0; o < 8; ++o) t = fmaf(w[B_W2P + 64 * hd + 8 * i + o], du[8 * hd + o], t);
-            dpre[8 * hd + i] = t * ds1[8 * hd + i];
+            const F4 w0 = ld4(w + B_W2P + 64 * hd + 8 * i), w1 = ld4(w + B_W2P + 64 * hd + 8 * i + 4);
+            const float *du = dm + 8 * hd;
+            float t = w0.x * du[0];
+            t = fmaf(w0.y, du[1], t); t = fmaf(w0.z, du[2], t); t = fmaf(w0.w, du[3], t);
+            t = fmaf(w1.x, du[4], t); t = fmaf(w1.y, du[5], t); t = fmaf(w1.z, du[6], t); t = fmaf(w1.w, du[7], t);
+            rDPRE[8 * hd + i] *= t;
         }
-    {
-        float dp[32];
-#pragma unroll
-        for (int o = 0; o < 32; ++o) dp[o] = dpre[o];
-        sink.template vec<V_DPRE>(dp);
     }
     // geometry backward (+ the coordinate update's own use of coord_diff)
     float gg[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        float t = 0.f;
+    for (int k = 0; k < 12; ++k) gg[k] = 0.f;
+#pragma unroll 1
+    for (int o4 = 0; o4 < 32; o4 += 4) {
+        const float d0 = rDPRE[o4], d1 = rDPRE[o4 + 1], d2 = rDPRE[o4 + 2], d3 = rDPRE[o4 + 3];
 #pragma unroll
-        for (int o = 0; o < 32; ++o) t = fmaf(w[B_WG + 32 * k + o], dpre[o], t);
-        gg[k] = t;
+        for (int k = 0; k < 12; ++k) {
+            const F4 wv = ld4(w + B_WG + 32 * k + o4);
+            gg[k] = fmaf(wv.x, d0, gg[k]); gg[k] = fmaf(wv.y, d1, gg[k]); gg[k] = fmaf(wv.z, d2, gg[k]); gg[k] = fmaf(wv.w, d3, gg[k]);
+        }
     }
     const float gde[3] = {s * dxo[0], s * dxo[1], s * dxo[2]};
     edge_geometry_backward(xr, xc, g, gg, gde, dxr, dxc);
 }
 
 // node_model backward (3dm:252-260): out = h + Wn2 SiLU(Wn1 [h|agg] + bn1) + bn2.
-//   dout = d loss / d h_out[n].  Outputs: dh (the part that does not go through P/Q), dagg, and the rows the
-//   weight gradients need: a (SiLU output), dz1.
-EGSPR_HD void node_backward(const float *w, const float *h, const float *agg, const float *dout, float *dh, float *dagg,
-                            float *a, float *dz1) {
-    float ds[32];
+//   w        layer pack (16-byte aligned); rH, rAgg: rows holding h[n], agg[n]; dout[32] = d loss / d h_out[n]
+//            (registers) with a copy in the row rDout
+//   rows     rA <- SiLU output, rZ <- dz1 (gradient at the first Linear's output)
+//   dh[32] <- the part of d loss / d h[n] that does not go through P/Q, dagg[32] <- d loss / d agg[n]
+//            (written one element at a time: pointers to global memory on the device)
+EGSPR_HD void node_backward(const float *w, const float *rH, const float *rAgg, const float *dout, const float *rDout,
+                            float *rA, float *rZ, float *dh, float *dagg) {
+    float z[32];
+#pragma unroll
+    for (int o4 = 0; o4 < 32; o4 += 4) {
+        const F4 b = ld4(w + B_BN1 + o4);
+        z[o4] = b.x; z[o4 + 1] = b.y; z[o4 + 2] = b.z; z[o4 + 3] = b.w;
+    }
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+        const float v = i < 32 ? rH[i] : rAgg[i - 32];
+#pragma unroll
+        for (int o4 = 0; o4 < 32; o4 += 4) {
+            const F4 wv = ld4(w + B_WN1T + 32 * i + o4);
+            z[o4] = fmaf(wv.x, v, z[o4]); z[o4 + 1] = fmaf(wv.y, v, z[o4 + 1]);
+            z[o4 + 2] = fmaf(wv.z, v, z[o4 + 2]); z[o4 + 3] = fmaf(wv.w, v, z[o4 + 3]);
+        }
+    }
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
-        float z = w[B_BN1 + o];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) z = fmaf(w[B_WN1T + 32 * i + o], h[i], z);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) z = fmaf(w[B_WN1T + 32 * (32 + i) + o], agg[i], z);
-        const float sg = sigmoidf_(z);
-        a[o] = z * sg;
-        ds[o] = sg * (1.0f + z * (1.0f - sg));
+        const float sg = sigmoidf_(z[o]);
+        rA[o] = z[o] * sg;
+        rZ[o] = sg * (1.0f + z[o] * (1.0f - sg));           // d silu / d z, replaced by dz1 below
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 32; ++i) {
-        float t = 0.f;
+        float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-        for (int o = 0; o < 32; ++o) t = fmaf(w[B_WN2T + 32 * i + o], dout[o], t);
-        dz1[i] = t * ds[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        float t = dout[i], u = 0.f;
-#pragma unroll
-        for (int o = 0; o < 32; ++o) {
-            t = fmaf(w[B_WN1T + 32 * i + o], dz1[o], t);
-            u = fmaf(w[B_WN1T + 32 * (32 + i) + o], dz1[o], u);
+        for (int o4 = 0; o4 < 32; o4 += 4) {
+            const F4 wv = ld4(w + B_WN2T + 32 * i + o4);
+            t0 = fmaf(wv.x, dout[o4], t0); t1 = fmaf(wv.y, dout[o4 + 1], t1);
+            t0 = fmaf(wv.z, dout[o4 + 2], t0); t1 = fmaf(wv.w, dout[o4 + 3], t1);
         }
-        dh[i] = t;
-        dagg[i] = u;
+        rZ[i] *= (t0 + t1);
+    }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) z[o] = rZ[o];               // dz1 in registers
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int o4 = 0; o4 < 32; o4 += 4) {
+            const F4 wv = ld4(w + B_WN1T + 32 * i + o4);
+            t0 = fmaf(wv.x, z[o4], t0); t1 = fmaf(wv.y, z[o4 + 1], t1);
+            t0 = fmaf(wv.z, z[o4 + 2], t0); t1 = fmaf(wv.w, z[o4 + 3], t1);
+        }
+        if (i < 32) dh[i] = rDout[i] + (t0 + t1);
+        else dagg[i - 32] = t0 + t1;
     }
 }
 
-// y = W x (+ b) with W stored transposed ([in][out]):  dx[i] (+)= sum_o wt[32 i + o] dy[o]
+// y = W x (+ b) with W stored transposed ([in][out], 16-byte aligned):  dx[i] (+)= sum_o wt[32 i + o] dy[o];
+// dy in registers, dx written one element at a time
 EGSPR_HD void linear32_backward_input(const float *wt, const float *dy, float *dx, bool accumulate) {
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 32; ++i) {
-        float t = accumulate ? dx[i] : 0.f;
+        float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-        for (int o = 0; o < 32; ++o) t = fmaf(wt[32 * i + o], dy[o], t);
-        dx[i] = t;
+        for (int o4 = 0; o4 < 32; o4 += 4) {
+            const F4 wv = ld4(wt + 32 * i + o4);
+            t0 = fmaf(wv.x, dy[o4], t0); t1 = fmaf(wv.y, dy[o4 + 1], t1);
+            t0 = fmaf(wv.z, dy[o4 + 2], t0); t1 = fmaf(wv.w, dy[o4 + 3], t1);
+        }
+        dx[i] = (accumulate ? dx[i] : 0.f) + (t0 + t1);
     }
 }
 

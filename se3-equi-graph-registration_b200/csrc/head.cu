@@ -61,7 +61,9 @@ __device__ __forceinline__ float block_max(float v, BlockScratch &sc) {
 }
 
 // ---- 3x3 SVD by one-sided Jacobi in fp64, R = V diag(1,1,det) U^T  (3dm:741-751) ---------------
-__device__ void kabsch_solve(const double (&Hm)[3][3], double (&R)[3][3]) {
+// Hm = U diag(sg) W^T with sg descending; d = -1 if det(W U^T) < 0 (the reference then flips the smallest-sigma
+// row of Vt).  Returns false for Hm == 0 (any basis; R = I).
+__device__ bool kabsch_svd(const double (&Hm)[3][3], double (&U)[3][3], double (&W)[3][3], double (&sg)[3], double &d) {
     double A[3][3], V[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -100,22 +102,17 @@ __device__ void kabsch_solve(const double (&Hm)[3][3], double (&R)[3][3]) {
     if (sig[o1] < sig[o2]) { int t = o1; o1 = o2; o2 = t; }
     if (sig[o0] < sig[o1]) { int t = o0; o0 = o1; o1 = t; }
     const int ord[3] = {o0, o1, o2};
-    double U[3][3], W[3][3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const int s = ord[j];
         const double inv = sig[s] > 1e-300 ? 1.0 / sig[s] : 0.0;
+        sg[j] = sig[s];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { U[i][j] = A[i][s] * inv; W[i][j] = V[i][s]; }
     }
     const double smax = sig[o0];
-    if (!(smax > 0.0)) {   // H == 0: any basis; LAPACK returns identity factors
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) R[i][j] = (i == j) ? 1.0 : 0.0;
-        return;
-    }
+    d = 1.0;
+    if (!(smax > 0.0)) return false;   // H == 0: any basis; LAPACK returns identity factors
     if (sig[o1] <= 1e-14 * smax) {   // rank 1: complete U with any unit vector orthogonal to U0
         const double ax = fabs(U[0][0]), ay = fabs(U[1][0]), az = fabs(U[2][0]);
         double e[3] = {0, 0, 0};
@@ -134,7 +131,19 @@ __device__ void kabsch_solve(const double (&Hm)[3][3], double (&R)[3][3]) {
         return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
                M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
     };
-    const double d = det3(W) * det3(U) < 0.0 ? -1.0 : 1.0;   // det(V U^T) < 0 -> Vt[-1,:] *= -1
+    d = det3(W) * det3(U) < 0.0 ? -1.0 : 1.0;   // det(V U^T) < 0 -> Vt[-1,:] *= -1
+    return true;
+}
+
+__device__ void kabsch_solve(const double (&Hm)[3][3], double (&R)[3][3]) {
+    double U[3][3], W[3][3], sg[3], d;
+    if (!kabsch_svd(Hm, U, W, sg, d)) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) R[i][j] = (i == j) ? 1.0 : 0.0;
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -480,6 +489,174 @@ __global__ void __launch_bounds__(256) pose_metrics_kernel(const float *__restri
     }
 }
 
+// ---- backward of the train-variant head (3dm:696-758): (dR, dt, dsim) -> gradients of the EGNN outputs ----------
+// R = V D U^T of H = U S V^T is differentiated in closed form (no 1/(s_i^2 - s_j^2) terms for equal-sign pairs):
+//   A = V^T (dR - dt cs^T) U,   Mbar_ij = alpha_ij A_ij + beta_ji A_ji (i != j),   dH = U Mbar V^T
+//   same-sign pair: alpha_ij = -d/(s_i+s_j), beta_ij = d/(s_i+s_j);  mixed pair: alpha_ij = beta_ij = d_i/(s_i-s_j)
+// then through H, the centroids, w = softmax(sim)/(sum+1e-6) to sim, x_src_out, x_tgt_out, and sim = <h_s,h_t> to h.
+struct HeadTrainBwdArgs {
+    const float *h_out_src, *h_out_tgt, *x_out_src, *x_out_tgt, *labels, *dR, *dt, *dsim;
+    int n;
+    float *dh_src, *dh_tgt, *dx_src, *dx_tgt;
+};
+
+__global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(const HeadTrainBwdArgs a) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ BlockScratch sc;
+    __shared__ float gsh[24];      // G_H [9], dcs' [3], dct' [3], cs [3], ct [3], ok
+    const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
+    const size_t nb = (size_t)b * n;
+    float *sw = dyn, *sdw = dyn + n;
+    const float *p = a.x_out_src + nb * 3, *q = a.x_out_tgt + nb * 3;
+    // forward recompute: weights
+    float mx = -3.4e38f;
+    float cnt[1] = {0.f};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float s = dot32(a.h_out_src + (nb + i) * H, a.h_out_tgt + (nb + i) * H);
+        const bool valid = __ldg(a.labels + nb + i) != 0.f;
+        sw[i] = valid ? s : -3.4e38f;
+        if (valid) { mx = fmaxf(mx, s); cnt[0] += 1.f; }
+    }
+    mx = block_max(mx, sc);
+    block_sum<1>(cnt, sc);
+    float z[1] = {0.f};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float v = sw[i];
+        const float e = v > -3.0e38f ? expf(v - mx) : 0.f;
+        sw[i] = e; z[0] += e;
+    }
+    block_sum<1>(z, sc);
+    const float inv_z = z[0] > 0.f ? 1.0f / z[0] : 0.f;
+    float swt[1] = {0.f};
+    for (int i = tid; i < n; i += blockDim.x) { const float w = sw[i] * inv_z; sw[i] = w; swt[0] += w; }
+    block_sum<1>(swt, sc);
+    const float inv_w = 1.0f / (swt[0] + 1e-6f);
+    for (int i = tid; i < n; i += blockDim.x) sw[i] *= inv_w;
+    __syncthreads();
+    // centroids, H, sums of w*pc, w*qc
+    float c[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float wi = sw[i];
+        if (wi != 0.f) {
+            c[0] = fmaf(wi, p[i * 3], c[0]); c[1] = fmaf(wi, p[i * 3 + 1], c[1]); c[2] = fmaf(wi, p[i * 3 + 2], c[2]);
+            c[3] = fmaf(wi, q[i * 3], c[3]); c[4] = fmaf(wi, q[i * 3 + 1], c[4]); c[5] = fmaf(wi, q[i * 3 + 2], c[5]);
+            c[6] += wi;
+        }
+    }
+    block_sum<7>(c, sc);
+    float hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float wi = sw[i];
+        if (wi != 0.f) {
+            const float a0 = wi * (p[i * 3] - c[0]), a1 = wi * (p[i * 3 + 1] - c[1]), a2 = wi * (p[i * 3 + 2] - c[2]);
+            const float b0 = q[i * 3] - c[3], b1 = q[i * 3 + 1] - c[4], b2 = q[i * 3 + 2] - c[5];
+            hm[0] = fmaf(a0, b0, hm[0]); hm[1] = fmaf(a0, b1, hm[1]); hm[2] = fmaf(a0, b2, hm[2]);
+            hm[3] = fmaf(a1, b0, hm[3]); hm[4] = fmaf(a1, b1, hm[4]); hm[5] = fmaf(a1, b2, hm[5]);
+            hm[6] = fmaf(a2, b0, hm[6]); hm[7] = fmaf(a2, b1, hm[7]); hm[8] = fmaf(a2, b2, hm[8]);
+        }
+    }
+    block_sum<9>(hm, sc);
+    if (tid == 0) {
+        bool ok = cnt[0] > 0.5f;
+        double GH[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, dcs[3] = {0, 0, 0}, dct[3] = {0, 0, 0};
+        if (ok) {
+            hm[0] += 1e-6f; hm[4] += 1e-6f; hm[8] += 1e-6f;
+            double Hd[3][3], U[3][3], W[3][3], sg[3], d3;
+            for (int i = 0; i < 9; ++i) Hd[i / 3][i % 3] = (double)hm[i];
+            ok = kabsch_svd(Hd, U, W, sg, d3);
+            if (ok) {
+                const double dd[3] = {1.0, 1.0, d3};
+                double R[3][3], GR[3][3], A[3][3], Mb[3][3];
+                double dtv[3] = {(double)a.dt[b * 3], (double)a.dt[b * 3 + 1], (double)a.dt[b * 3 + 2]};
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) {
+                        R[i][j] = W[i][0] * U[j][0] + W[i][1] * U[j][1] + d3 * W[i][2] * U[j][2];
+                        GR[i][j] = (double)a.dR[b * 9 + i * 3 + j] - dtv[i] * (double)c[j];     // t = ct - R cs
+                    }
+                for (int i = 0; i < 3; ++i) {
+                    dcs[i] = -(R[0][i] * dtv[0] + R[1][i] * dtv[1] + R[2][i] * dtv[2]);
+                    dct[i] = dtv[i];
+                }
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) {
+                        double t = 0;
+                        for (int k = 0; k < 3; ++k)
+                            for (int l = 0; l < 3; ++l) t += W[k][i] * GR[k][l] * U[l][j];
+                        A[i][j] = t;
+                    }
+                auto coef = [&](int i, int j, bool beta) {   // alpha_ij / beta_ij
+                    if (dd[i] == dd[j]) {
+                        const double den = fmax(sg[i] + sg[j], 1e-300);
+                        return (beta ? dd[i] : -dd[i]) / den;
+                    }
+                    double den = sg[i] - sg[j];
+                    if (fabs(den) < 1e-300) den = den < 0 ? -1e-300 : 1e-300;
+                    return dd[i] / den;
+                };
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) Mb[i][j] = (i == j) ? 0.0 : coef(i, j, false) * A[i][j] + coef(j, i, true) * A[j][i];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) {
+                        double t = 0;
+                        for (int k = 0; k < 3; ++k)
+                            for (int l = 0; l < 3; ++l) t += U[i][k] * Mb[k][l] * W[j][l];
+                        GH[i][j] = t;
+                    }
+                // centroids enter pc, qc as well:  dcs' = dcs - G_H sum_j w_j qc_j,  dct' = dct - G_H^T sum_j w_j pc_j
+                const double om = 1.0 - (double)c[6];       // sum_j w_j qc_j = ct (1 - sum w), likewise for pc
+                for (int i = 0; i < 3; ++i) {
+                    double u = 0, v = 0;
+                    for (int j = 0; j < 3; ++j) { u += GH[i][j] * (double)c[3 + j] * om; v += GH[j][i] * (double)c[j] * om; }
+                    dcs[i] -= u; dct[i] -= v;
+                }
+            }
+        }
+        for (int i = 0; i < 9; ++i) gsh[i] = (float)GH[i / 3][i % 3];
+        for (int i = 0; i < 3; ++i) { gsh[9 + i] = (float)dcs[i]; gsh[12 + i] = (float)dct[i]; gsh[15 + i] = c[i]; gsh[18 + i] = c[3 + i]; }
+        gsh[21] = ok ? 1.f : 0.f;
+    }
+    __syncthreads();
+    const bool ok = gsh[21] != 0.f;
+    float g[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g[i] = gsh[i];
+    const float dcs0 = gsh[9], dcs1 = gsh[10], dcs2 = gsh[11], dct0 = gsh[12], dct1 = gsh[13], dct2 = gsh[14];
+    const float cs0 = gsh[15], cs1 = gsh[16], cs2 = gsh[17], ct0 = gsh[18], ct1 = gsh[19], ct2 = gsh[20];
+    // pass A: dw_i, coordinate gradients, D1 = sum_i w_i dw_i
+    float d1[1] = {0.f};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float wi = sw[i];
+        float dw = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f, dq0 = 0.f, dq1 = 0.f, dq2 = 0.f;
+        if (ok && wi != 0.f) {
+            const float p0 = p[i * 3], p1 = p[i * 3 + 1], p2 = p[i * 3 + 2], q0 = q[i * 3], q1 = q[i * 3 + 1], q2 = q[i * 3 + 2];
+            const float pc0 = p0 - cs0, pc1 = p1 - cs1, pc2 = p2 - cs2, qc0 = q0 - ct0, qc1 = q1 - ct1, qc2 = q2 - ct2;
+            const float gq0 = g[0] * qc0 + g[1] * qc1 + g[2] * qc2, gq1 = g[3] * qc0 + g[4] * qc1 + g[5] * qc2,
+                        gq2 = g[6] * qc0 + g[7] * qc1 + g[8] * qc2;                       // G_H qc
+            const float gp0 = g[0] * pc0 + g[3] * pc1 + g[6] * pc2, gp1 = g[1] * pc0 + g[4] * pc1 + g[7] * pc2,
+                        gp2 = g[2] * pc0 + g[5] * pc1 + g[8] * pc2;                       // G_H^T pc
+            dw = pc0 * gq0 + pc1 * gq1 + pc2 * gq2 + p0 * dcs0 + p1 * dcs1 + p2 * dcs2 + q0 * dct0 + q1 * dct1 + q2 * dct2;
+            dp0 = wi * (gq0 + dcs0); dp1 = wi * (gq1 + dcs1); dp2 = wi * (gq2 + dcs2);
+            dq0 = wi * (gp0 + dct0); dq1 = wi * (gp1 + dct1); dq2 = wi * (gp2 + dct2);
+            d1[0] = fmaf(wi, dw, d1[0]);
+        }
+        sdw[i] = dw;
+        float *o = a.dx_src + (nb + i) * 3, *o2 = a.dx_tgt + (nb + i) * 3;
+        o[0] = dp0; o[1] = dp1; o[2] = dp2; o2[0] = dq0; o2[1] = dq1; o2[2] = dq2;
+    }
+    block_sum<1>(d1, sc);
+    const float D1 = d1[0] * (1.0f + 1e-6f);
+    // pass B: d sim_i = w_i (dw_i - D1 (1 + eps)) + external dsim_i;  sim = <h_s, h_t>
+    const int lane8 = tid & 7;
+    for (int i0 = (tid >> 3); i0 < n; i0 += (blockDim.x >> 3)) {      // 8 lanes per 128-byte row
+        const int i = i0;
+        float ds = sw[i] * (sdw[i] - D1);
+        if (a.dsim) ds += __ldg(a.dsim + nb + i);
+        const float4 hs = ldg4(a.h_out_src + (nb + i) * H + 4 * lane8), ht = ldg4(a.h_out_tgt + (nb + i) * H + 4 * lane8);
+        *reinterpret_cast<float4 *>(a.dh_src + (nb + i) * H + 4 * lane8) = make_float4(ds * ht.x, ds * ht.y, ds * ht.z, ds * ht.w);
+        *reinterpret_cast<float4 *>(a.dh_tgt + (nb + i) * H + 4 * lane8) = make_float4(ds * hs.x, ds * hs.y, ds * hs.z, ds * hs.w);
+    }
+}
+
 static int head_threads(int n) {
     static const int forced = getenv("EGSPR_HEAD_THREADS") ? atoi(getenv("EGSPR_HEAD_THREADS")) : 0;   // developer switch
     if (forced == 256 || forced == 512 || forced == 1024) return forced;
@@ -546,7 +723,24 @@ extern "C" int egspr_head_train(const float *h_out_src, const float *h_out_tgt, 
     return EGSPR_OK;
 }
 
-extern "C" int egspr_version(void) { return 100; }
+extern "C" int egspr_head_train_backward(const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                                         const float *x_out_tgt, const float *labels, const float *dR, const float *dt,
+                                         const float *dsim, int pairs, int n, float *dh_src, float *dh_tgt,
+                                         float *dx_src, float *dx_tgt, void *stream) {
+    using namespace egspr;
+    if (!h_out_src || !h_out_tgt || !x_out_src || !x_out_tgt || !labels || !dR || !dt || !dh_src || !dh_tgt || !dx_src ||
+        !dx_tgt || pairs <= 0 || n <= 0)
+        return EGSPR_E_INVALID;
+    if (2 * n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
+    const size_t smem = sizeof(float) * 2 * (size_t)n;
+    if (int e = ensure_smem(head_train_backward_kernel, smem)) return e;
+    HeadTrainBwdArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, dR, dt, dsim, n, dh_src, dh_tgt, dx_src, dx_tgt};
+    head_train_backward_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_version(void) { return 101; }
 
 extern "C" const char *egspr_error_string(int code) {
     switch (code) {

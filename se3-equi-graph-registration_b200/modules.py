@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import autograd as _ag
 from . import ops, packing
 
 
@@ -75,6 +76,12 @@ def unsorted_segment_sum(data, segment_ids, num_segments):
         _lib.check(_lib.lib().egspr_segment_sum(ops._ptr(data), C, ops._ptr(g.ptr), ops._ptr(g.eid), num_segments,
                                                 ops._ptr(out), ops._stream()), "egspr_segment_sum")
     return out
+
+
+def _needs_grad(module, *tensors):
+    """True when autograd is recording and a parameter or an input wants a gradient: the training path."""
+    return torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters()) or
+                                        any(torch.is_tensor(t) and t.requires_grad for t in tensors))
 
 
 def _edges_to_tensor(edges):
@@ -136,6 +143,12 @@ class E_GCL(nn.Module):
         """(h [N,32], [row,col], coord [N,3], edge_attr [E,1]|None) -> (h', coord', edge_attr)  3dm:280-289"""
         graph = ops.csr_from_edges(_edges_to_tensor(edge_index), h.shape[0])
         ea = None if edge_attr is None else edge_attr.to(torch.float32)
+        if _needs_grad(self, h, coord):
+            self._check_supported()
+            spec = ([self], None, None, ops.with_csc(graph), ea, 0.0)
+            h2, x2 = _ag.EGNNFunction.apply(spec, h.unsqueeze(0).to(torch.float32), coord.unsqueeze(0).to(torch.float32),
+                                            *_ag.egnn_param_list([self]))
+            return h2[0], x2[0], edge_attr
         h2, x2 = ops.egnn_forward(h.unsqueeze(0), coord.unsqueeze(0), graph, [self.layer_pack()], None, None,
                                   edge_attr=ea, edge_attr_const=0.0)
         return h2[0], x2[0], edge_attr
@@ -174,6 +187,13 @@ class EGNN(nn.Module):
 
     def forward_batch(self, h, x, graph, edge_attr=None, edge_attr_const=1.0):
         """Batched form used by the head and the engine: h [C,N,32], x [C,N,3], graph = ops.BatchGraph."""
+        if _needs_grad(self, h, x):
+            # training path (3dm:1092-1126): forward keeps the per-layer state, backward = the gradient kernels
+            gcls = [self._modules["gcl_%d" % i] for i in range(self.n_layers)]
+            for g in gcls:
+                g._check_supported()
+            spec = (gcls, self.embedding_in, self.embedding_out, ops.with_csc(graph), edge_attr, float(edge_attr_const))
+            return _ag.EGNNFunction.apply(spec, h, x, *_ag.egnn_param_list(gcls, self.embedding_in, self.embedding_out))
         layers, pin, pout = self.packs()
         return ops.egnn_forward(h, x, graph, layers, pin, pout, edge_attr=edge_attr,
                                 edge_attr_const=edge_attr_const, impl=self.impl)
@@ -265,10 +285,6 @@ class CrossAttentionPoseRegression(nn.Module):
         """Same 11 inputs / 9 outputs as the reference (3dm:634, 796; evl:643, 827):
         (R [B,3,3], t [B,3], corr_loss+sim_loss | None, egnn_equi_loss, h_src, x_src, h_tgt, x_tgt, labels).
         edges_* : [B,2,E] int64 (or a prebuilt ops.BatchGraph); edge_attr_* : [B,E,1] or None (= ones)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "egspr_b200 round 1 ships the forward (inference / validation) kernels; run under torch.no_grad(). "
-                "Backward kernels are listed under 'next' in DESIGN.md")
         B, N, _ = h_src.shape
         labels_f = labels.to(torch.float32).reshape(B, N)
         hs, xs, ht, xt = self._egnn_both(h_src, x_src, edges_src, edge_attr_src, h_tgt, x_tgt, edges_tgt, edge_attr_tgt)
@@ -279,8 +295,14 @@ class CrossAttentionPoseRegression(nn.Module):
             total_loss = lp.sum(0).sum() / (B * N)                                           # evl:687
             self.last_aux = {"w": w, "H": Hm}
             return R, t, None, total_loss, hs, xs, ht, xt, labels
-        R, t, w, sim, Hm, lp = ops.head_train(hs, ht, xs, xt, labels_f, gt_pose)
-        total_loss = lp.sum(0).sum() / (B * N)                                               # 3dm:677
+        grad = _needs_grad(self, h_src, h_tgt, x_src, x_tgt)
+        if grad:
+            R, t, sim, w, Hm, lp = _ag.HeadTrainFunction.apply(hs, ht, xs, xt, labels_f, gt_pose.to(torch.float32))
+            total_loss = egnn_equi_loss(hs, xs, ht, xt, gt_pose[:, :3, :3].to(torch.float32),
+                                        gt_pose[:, :3, -1].to(torch.float32), labels_f)      # 3dm:677, differentiable
+        else:
+            R, t, w, sim, Hm, lp = ops.head_train(hs, ht, xs, xt, labels_f, gt_pose)
+            total_loss = lp.sum(0).sum() / (B * N)                                           # 3dm:677
         self.last_aux = {"w": w, "H": Hm}
         # correspondence BCE on the top-128 + similarity-consistency loss (3dm:681-694, 760-781)
         k = min(self.top_k, N)

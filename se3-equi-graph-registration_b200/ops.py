@@ -70,6 +70,9 @@ class BatchGraph:
     n: int
     edges_per_cloud: int
     err: torch.Tensor     # [1] i32, 1 if an index was out of range
+    cptr: torch.Tensor = None   # [G+1] i32  the same edges grouped by col (backward pass only, see with_csc)
+    ceid: torch.Tensor = None   # [E] i32
+    edges: torch.Tensor = None  # the [C,2,E] i64 edge tensor the graph was built from (kept for with_csc)
 
     def check(self):
         if int(self.err.item()) != 0:
@@ -111,7 +114,21 @@ def csr_from_edges(edges, n):
     with torch.cuda.device(edges.device):
         _lib.check(_lib.lib().egspr_csr_from_edges(_ptr(edges), C, n, E, _ptr(g.ptr), _ptr(g.row), _ptr(g.col), _ptr(g.eid),
                                                    _ptr(ws), ws_bytes, _ptr(g.err), _stream()), "egspr_csr_from_edges")
+    g.edges = edges
     return g
+
+
+def with_csc(graph, nbr=None):
+    """Adds the col-grouped edge lists the backward pass needs (graph.cptr / graph.ceid): the CSR of the same edge
+    tensor with its two rows swapped.  Graphs built from k-NN ids pass `nbr` (the edge tensor is rebuilt from it)."""
+    if graph.cptr is not None:
+        return graph
+    edges = graph.edges if graph.edges is not None else (nbr_to_edges(nbr) if nbr is not None else None)
+    if edges is None:
+        raise ValueError("with_csc needs the edge tensor (or the k-NN ids) the graph was built from")
+    t = csr_from_edges(edges.flip(1).contiguous(), graph.n)
+    graph.cptr, graph.ceid = t.ptr, t.eid
+    return graph
 
 
 def egnn_forward(feat, x, graph, layer_packs, embed_in_pack, embed_out_pack, edge_attr=None,
@@ -275,3 +292,125 @@ def feature_correspondences(src_desc, tgt_desc, use_mutual=False):
     else:
         corr = torch.stack([ar, source_idx.long()], dim=-1)
     return corr, source_dis
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training path: forward that keeps the per-layer state, and the backward kernels
+# ---------------------------------------------------------------------------------------------------------------
+def linear32_forward(x, pack):
+    x = _req(x, "x", torch.float32)
+    y = torch.empty_like(x)
+    rows = x.numel() // H
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().egspr_linear32_forward(_ptr(x), rows, _ptr(pack), _ptr(y), _stream()), "egspr_linear32_forward")
+    return y
+
+
+def linear32_backward(x, dy, pack, need_dx=True):
+    """-> (dx | None, grad_pack [EMBED_PACK])"""
+    x = _req(x, "x", torch.float32); dy = _req(dy, "dy", torch.float32)
+    rows = x.numel() // H
+    dx = torch.empty_like(x) if need_dx else None
+    gp = torch.zeros(pack.numel(), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().egspr_linear32_backward(_ptr(x), _ptr(dy), rows, _ptr(pack), _ptr(dx), _ptr(gp), _stream()),
+                   "egspr_linear32_backward")
+    return dx, gp
+
+
+def egnn_forward_saved(feat, x, graph, layer_packs, embed_in_pack, embed_out_pack, edge_attr=None, edge_attr_const=1.0):
+    """EGNN.forward (3dm:328-340) keeping what the backward pass needs: per layer the input state (h, x4, P, Q) and
+    the message sums agg.  Tensor-core forward kernels (impl 3); embedding_out runs as its own Linear so that the
+    last layer's output survives.  Returns h_out [C,N,32], x_out [C,N,3], saved (dict)."""
+    feat = _req(feat, "h", torch.float32, 3)
+    x = _req(x, "x", torch.float32, 3)
+    C, N, F = feat.shape
+    if F != H:
+        raise NotImplementedError(f"feature width must be {H}, got {F}")
+    if (C, N) != (graph.clouds, graph.n) or tuple(x.shape) != (C, N, 3):
+        raise ValueError("feature / coordinate / graph shapes disagree")
+    if edge_attr is not None:
+        edge_attr = _req(edge_attr, "edge_attr", torch.float32).reshape(-1)
+        if edge_attr.numel() != C * graph.edges_per_cloud:
+            raise ValueError("edge_attr must have one scalar per edge")
+    dev = feat.device
+    G, L = C * N, len(layer_packs)
+    lib = _lib.lib()
+    new = lambda w: torch.empty((G, w), dtype=torch.float32, device=dev)
+    hs = [new(H) for _ in range(L + 1)]
+    x4 = [new(4) for _ in range(L + 1)]
+    Ps = [new(H) for _ in range(L)]
+    Qs = [new(H) for _ in range(L)]
+    aggs = [new(H) for _ in range(L)]
+    x_out = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream()
+        _lib.check(lib.egspr_node_embed(_ptr(feat), _ptr(x), G, _ptr(embed_in_pack), _ptr(layer_packs[0]),
+                                        _ptr(hs[0]), _ptr(x4[0]), _ptr(Ps[0]), _ptr(Qs[0]), st), "egspr_node_embed")
+        for i in range(L):
+            last = i == L - 1
+            _lib.check(lib.egspr_egcl_forward(
+                _ptr(hs[i]), _ptr(x4[i]), _ptr(Ps[i]), _ptr(Qs[i]),
+                _ptr(graph.ptr), _ptr(graph.row), _ptr(graph.col), _ptr(graph.eid),
+                _ptr(edge_attr), float(edge_attr_const), G, graph.edges_per_cloud, N,
+                _ptr(layer_packs[i]), None if last else _ptr(layer_packs[i + 1]), None,
+                _ptr(hs[i + 1]), _ptr(x4[i + 1]), _ptr(x_out) if last else None,
+                None if last else _ptr(Ps[i + 1]), None if last else _ptr(Qs[i + 1]), _ptr(aggs[i]), 3, st),
+                "egspr_egcl_forward")
+    h_out = linear32_forward(hs[L], embed_out_pack) if embed_out_pack is not None else hs[L].clone()
+    saved = dict(feat=feat, hs=hs, x4=x4, Ps=Ps, Qs=Qs, aggs=aggs, edge_attr=edge_attr, edge_attr_const=float(edge_attr_const))
+    return h_out.view(C, N, H), x_out, saved
+
+
+def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_out, dx_out, need_dfeat=True):
+    """Backward of egnn_forward_saved.  dh_out [C,N,32], dx_out [C,N,3] (either may be None = zero).
+    Returns dfeat [C,N,32] | None, dx [C,N,3], layer grad packs (list), embed_in grad pack | None, embed_out grad pack | None."""
+    if graph.cptr is None:
+        raise ValueError("the backward pass needs graph.cptr / graph.ceid: call ops.with_csc(graph) first")
+    C, N = graph.clouds, graph.n
+    G, L = C * N, len(layer_packs)
+    dev = saved["feat"].device
+    lib = _lib.lib()
+    dh = torch.zeros((G, H), dtype=torch.float32, device=dev) if dh_out is None else _req(dh_out, "dh_out", torch.float32).reshape(G, H)
+    dx = torch.zeros((G, 3), dtype=torch.float32, device=dev) if dx_out is None else _req(dx_out, "dx_out", torch.float32).reshape(G, 3)
+    g_out = None
+    if embed_out_pack is not None:
+        dh, g_out = linear32_backward(saved["hs"][L], dh, embed_out_pack, need_dx=True)
+    E = C * graph.edges_per_cloud
+    ws_bytes = lib.egspr_egcl_backward_workspace_bytes(G, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    gpacks = [None] * L
+    with torch.cuda.device(dev):
+        st = _stream()
+        for i in range(L - 1, -1, -1):
+            gp = torch.zeros(layer_packs[i].numel(), dtype=torch.float32, device=dev)
+            dh_in = torch.empty((G, H), dtype=torch.float32, device=dev)
+            dx_in = torch.empty((G, 3), dtype=torch.float32, device=dev)
+            _lib.check(lib.egspr_egcl_backward(
+                _ptr(saved["hs"][i]), _ptr(saved["x4"][i]), _ptr(saved["Ps"][i]), _ptr(saved["Qs"][i]), _ptr(saved["aggs"][i]),
+                _ptr(graph.ptr), _ptr(graph.row), _ptr(graph.col), _ptr(graph.eid), _ptr(graph.cptr), _ptr(graph.ceid),
+                _ptr(saved["edge_attr"]), saved["edge_attr_const"], G, graph.edges_per_cloud, N, _ptr(layer_packs[i]),
+                _ptr(dh), _ptr(dx), _ptr(dh_in), _ptr(dx_in), _ptr(gp), _ptr(ws), ws_bytes, st), "egspr_egcl_backward")
+            gpacks[i] = gp
+            dh, dx = dh_in, dx_in
+    g_in, dfeat = None, dh
+    if embed_in_pack is not None:
+        dfeat, g_in = linear32_backward(saved["feat"].reshape(G, H), dh, embed_in_pack, need_dx=need_dfeat)
+    return (dfeat.view(C, N, H) if dfeat is not None else None), dx.view(C, N, 3), gpacks, g_in, g_out
+
+
+def head_train_backward(h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, dR, dt, dsim=None):
+    """Backward of head_train (3dm:696-758) -> dh_src, dh_tgt [B,n,32], dx_src, dx_tgt [B,n,3]."""
+    ts = [_req(v, nm, torch.float32, 3) for v, nm in
+          ((h_out_src, "h_out_src"), (h_out_tgt, "h_out_tgt"), (x_out_src, "x_out_src"), (x_out_tgt, "x_out_tgt"))]
+    B, n, _ = ts[0].shape
+    labels = _req(labels.to(torch.float32), "labels", torch.float32, 2)
+    dR = _req(dR.to(torch.float32), "dR", torch.float32, 3)
+    dt = _req(dt.to(torch.float32), "dt", torch.float32, 2)
+    if dsim is not None:
+        dsim = _req(dsim.to(torch.float32), "dsim", torch.float32, 2)
+    outs = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2]), torch.empty_like(ts[3])]
+    with torch.cuda.device(ts[0].device):
+        _lib.check(_lib.lib().egspr_head_train_backward(*[_ptr(v) for v in ts], _ptr(labels), _ptr(dR), _ptr(dt), _ptr(dsim),
+                                                        B, n, *[_ptr(o) for o in outs], _stream()), "egspr_head_train_backward")
+    return outs

@@ -1,0 +1,64 @@
+"""The training step of the reference's loop (src/3dmatch_train_egnn_with_batch.py:1092-1126) on the CUDA path,
+plus the data-parallel gradient exchange of BASELINE config 4.
+
+One process per GPU, every rank holds a replica and its own slice of the pair batch (a registration pair is an
+independent unit); the only collective is ONE all-reduce of the flat fp32 gradient (45,742 elements) per step, after
+which every rank applies the same optimizer update.  The reference itself has no distributed code."""
+import torch
+import torch.distributed as dist
+
+from .modules import pose_loss
+
+
+def training_loss(outputs, gt_pose):
+    """3dm:1094-1118: total = corr_loss.mean() + rot_loss.mean() + trans_loss.mean() (the similarity loss is inside
+    slot 2; egnn_equi_loss, slot 3, is returned by the model but not part of the total)."""
+    R, t, corr_loss = outputs[0], outputs[1], outputs[2]
+    rot, trans = pose_loss(R, t, gt_pose.to(R.dtype), delta=1.5)
+    return corr_loss.mean() + rot.mean() + trans.mean()
+
+
+def flat_gradient(params):
+    """One contiguous fp32 bucket holding every parameter's gradient (zeros where a parameter got none, e.g. the
+    dead modules of SURVEY F8) -> (flat, views) with views[i] aliasing flat."""
+    params = list(params)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+    views, off = [], 0
+    for p in params:
+        v = flat[off:off + p.numel()].view_as(p)
+        if p.grad is not None:
+            v.copy_(p.grad)
+        views.append(v)
+        off += p.numel()
+    return flat, views
+
+
+def allreduce_gradients(params, group=None, average=True):
+    """Sum (or mean) of the gradients over the ranks in a single bucket; writes the result back into .grad.
+    No-op without an initialised process group or with world size 1."""
+    params = [p for p in params if p.requires_grad]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    flat, views = flat_gradient(params)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.div_(dist.get_world_size(group))
+    for p, v in zip(params, views):
+        if p.grad is None:
+            p.grad = v.clone()
+        else:
+            p.grad.copy_(v)
+
+
+def train_step(model, optimizer, batch, group=None):
+    """One iteration of train_one_epoch (3dm:1092-1126): forward (train variant), loss, backward through the
+    gradient kernels, gradient all-reduce, optimizer step.  batch: the 11 forward inputs as a tuple / list.
+    Returns the detached loss."""
+    model.train()
+    optimizer.zero_grad(set_to_none=True)
+    outputs = model(*batch)
+    loss = training_loss(outputs, batch[10])
+    loss.backward()
+    allreduce_gradients(model.parameters(), group=group)
+    optimizer.step()
+    return loss.detach()

@@ -12,17 +12,14 @@ using namespace egspr::bwd;
 
 namespace {
 struct HostSink {
-    float v[V_COUNT][32];
     float c[C_COUNT][32];
-    float g[13];
-    template <int ID> void vec(const float (&x)[32]) { std::memcpy(v[ID], x, sizeof(x)); }
     template <int ID> void col(const float (&x)[32]) { std::memcpy(c[ID], x, sizeof(x)); }
-    void geo(const float (&x)[13]) { std::memcpy(g, x, sizeof(x)); }
 };
 }  // namespace
 
 // One E_GCL layer, forward (to obtain P, Q, agg) + backward.  row/col: global node ids per edge (any order).
 // edge_attr: per-edge scalar or NULL (= ea_const).  Outputs: dh_in [G][32], dx_in [G][3], gpack [7104] (+=).
+// pack must be 16-byte aligned.
 extern "C" void egcl_backward_host(const float *pack, int G, int E, const int32_t *row, const int32_t *col,
                                    const float *edge_attr, float ea_const, const float *h, const float *x,
                                    const float *dh_out, const float *dx_out, float *dh_in, float *dx_in,
@@ -40,18 +37,19 @@ extern "C" void egcl_backward_host(const float *pack, int G, int E, const int32_
         }
     const float zero32[32] = {0}, zero3[3] = {0, 0, 0};
     HostSink sink;
-    float dpre[32], dxr[3], dxc[3];
+    float rM[32], rDC1[32], rA1[32], rDU[32], rDPRE[32], geo[13], dxr[3], dxc[3];
     for (int e = 0; e < E; ++e) {   // forward: messages -> agg
         const int r = row[e], c = col[e];
-        edge_backward(pack, x + 3 * (size_t)r, x + 3 * (size_t)c, &P[(size_t)r * 32], &Q[(size_t)c * 32],
-                      edge_attr ? edge_attr[e] : ea_const, zero32, zero3, sink, dpre, dxr, dxc);
-        for (int o = 0; o < 32; ++o) agg[(size_t)r * 32 + o] += sink.v[V_M][o];
+        for (int o = 0; o < 32; ++o) rDPRE[o] = P[(size_t)r * 32 + o] + Q[(size_t)c * 32 + o];
+        edge_backward(pack, pack + B_WEA, x + 3 * (size_t)r, x + 3 * (size_t)c, edge_attr ? edge_attr[e] : ea_const,
+                      zero32, zero3, rM, rDC1, rA1, rDU, rDPRE, geo, sink, dxr, dxc);
+        for (int o = 0; o < 32; ++o) agg[(size_t)r * 32 + o] += rM[o];
     }
     std::vector<float> dagg((size_t)G * 32), dP((size_t)G * 32, 0.f), dQ((size_t)G * 32, 0.f);
     for (int n = 0; n < G; ++n) {   // node MLP backward
         float a[32], dz1[32];
         const float *hn = h + (size_t)n * 32, *an = &agg[(size_t)n * 32], *dn = dh_out + (size_t)n * 32;
-        node_backward(pack, hn, an, dn, dh_in + (size_t)n * 32, &dagg[(size_t)n * 32], a, dz1);
+        node_backward(pack, hn, an, dn, dn, a, dz1, dh_in + (size_t)n * 32, &dagg[(size_t)n * 32]);
         for (int i = 0; i < 32; ++i)
             for (int o = 0; o < 32; ++o) {
                 gpack[B_WN2T + 32 * i + o] += a[i] * dn[o];
@@ -63,20 +61,20 @@ extern "C" void egcl_backward_host(const float *pack, int G, int E, const int32_
     }
     for (int e = 0; e < E; ++e) {   // edge backward
         const int r = row[e], c = col[e];
-        edge_backward(pack, x + 3 * (size_t)r, x + 3 * (size_t)c, &P[(size_t)r * 32], &Q[(size_t)c * 32],
-                      edge_attr ? edge_attr[e] : ea_const, &dagg[(size_t)r * 32], dx_out + 3 * (size_t)r, sink, dpre, dxr, dxc);
-        for (int o = 0; o < 32; ++o) { dP[(size_t)r * 32 + o] += dpre[o]; dQ[(size_t)c * 32 + o] += dpre[o]; }
+        for (int o = 0; o < 32; ++o) rDPRE[o] = P[(size_t)r * 32 + o] + Q[(size_t)c * 32 + o];
+        edge_backward(pack, pack + B_WEA, x + 3 * (size_t)r, x + 3 * (size_t)c, edge_attr ? edge_attr[e] : ea_const,
+                      &dagg[(size_t)r * 32], dx_out + 3 * (size_t)r, rM, rDC1, rA1, rDU, rDPRE, geo, sink, dxr, dxc);
+        for (int o = 0; o < 32; ++o) { dP[(size_t)r * 32 + o] += rDPRE[o]; dQ[(size_t)c * 32 + o] += rDPRE[o]; }
         for (int i = 0; i < 3; ++i) { dx_in[(size_t)r * 3 + i] += dxr[i]; dx_in[(size_t)c * 3 + i] += dxc[i]; }
         for (int o = 0; o < 32; ++o)
-            for (int i = 0; i < 32; ++i) gpack[B_WC1 + 32 * o + i] += sink.v[V_DC1][o] * sink.v[V_M][i];
+            for (int i = 0; i < 32; ++i) gpack[B_WC1 + 32 * o + i] += rDC1[o] * rM[i];
         for (int hd = 0; hd < 4; ++hd)
             for (int i = 0; i < 8; ++i)
-                for (int o = 0; o < 8; ++o)
-                    gpack[B_W2P + 64 * hd + 8 * i + o] += sink.v[V_A1][8 * hd + i] * sink.v[V_DU][8 * hd + o];
+                for (int o = 0; o < 8; ++o) gpack[B_W2P + 64 * hd + 8 * i + o] += rA1[8 * hd + i] * rDU[8 * hd + o];
         for (int k = 0; k < 12; ++k)
-            for (int o = 0; o < 32; ++o) gpack[B_WG + 32 * k + o] += sink.g[k] * sink.v[V_DPRE][o];
+            for (int o = 0; o < 32; ++o) gpack[B_WG + 32 * k + o] += geo[k] * rDPRE[o];
         for (int o = 0; o < 32; ++o) {
-            gpack[B_WEA + o] += sink.g[12] * sink.v[V_DPRE][o];
+            gpack[B_WEA + o] += geo[12] * rDPRE[o];
             gpack[B_WC2 + o] += sink.c[C_DWC2][o];
             gpack[B_BC1 + o] += sink.c[C_DBC1][o];
             gpack[B_LNB + o] += sink.c[C_DLNB][o];

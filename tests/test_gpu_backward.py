@@ -1,0 +1,157 @@
+"""GPU: the backward kernels (egspr_egcl_backward, egspr_linear32_backward, egspr_head_train_backward) through the
+C ABI and the nn.Module API, against (i) the reference's own gradients (tests/golden/grads_b2_n256.pt, produced by
+tests/golden/make_golden_grads.py with the reference's classes + autograd) and (ii) torch autograd of the oracle on
+the same inputs.  Tolerance: |dg| <= 1e-3 * max|g| per tensor (the reference's fp32 run is 4e-5 from its fp64 run;
+our forward is 3xTF32 and the sums run in a different order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import se3_equi_graph_registration_b200 as P
+from se3_equi_graph_registration_b200 import ops, packing
+from oracle import egnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+G_TOL = 1e-3
+
+
+def edges_of(nbr):
+    return torch.stack([torch.stack(O.edges_from_nbr(n)) for n in nbr])
+
+
+def rel(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max() / (b.detach().abs().max().double() + 1e-30))
+
+
+def _model(golden_dir, temper=None):
+    m = P.build_model(os.path.join(golden_dir, "checkpoint-3dmatch.pth"), device=DEV, variant="train")
+    if temper is not None:
+        with torch.no_grad():
+            m.egnn.embedding_out.weight.mul_(temper)
+            m.egnn.embedding_out.bias.mul_(temper)
+    return m
+
+
+@pytest.mark.parametrize("per_edge_attr", [False, True])
+def test_egcl_layer_backward_matches_autograd(golden_dir, per_edge_attr):
+    """One E_GCL layer through the module API (E_GCL.forward 3dm:280-289) on an arbitrary user graph with duplicate
+    points: gradients w.r.t. h, coord and every parameter vs autograd of the oracle (fp64)."""
+    model = _model(golden_dir)
+    gcl = model.egnn.gcl_1
+    g = torch.Generator().manual_seed(3)
+    n, k = 700, 16
+    x = torch.rand(n, 3, generator=g) * 2
+    x[n // 2: n // 2 + 100] = x[:100]
+    d2 = ((x[:, None] - x[None]) ** 2).sum(-1)
+    nbr = d2.argsort(dim=1, stable=True)[:, :k]
+    row, col = O.edges_from_nbr(nbr)
+    extra = torch.randint(0, n, (2, 1000), generator=g)
+    row, col = torch.cat([row, extra[0]]), torch.cat([col, extra[1]])
+    E = row.numel()
+    h = torch.randn(n, 32, generator=g) * 0.5
+    ea = torch.rand(E, 1, generator=g) + 0.5 if per_edge_attr else torch.ones(E, 1)
+    dh = torch.randn(n, 32, generator=g); dx = torch.randn(n, 3, generator=g)
+    # oracle
+    sd = {"gcl_1." + k_: v.detach().cpu().double().requires_grad_(True) for k_, v in gcl.state_dict().items()}
+    h64, x64 = h.double().requires_grad_(True), x.double().requires_grad_(True)
+    h2r, x2r, _ = O.egcl_forward(sd, "gcl_1.", h64, x64, row, col, ea.double())
+    ((h2r * dh.double()).sum() + (x2r * dx.double()).sum()).backward()
+    # CUDA
+    hg, xg = h.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    for p in gcl.parameters():
+        p.grad = None
+    h2, x2, _ = gcl(hg, [row.to(DEV), col.to(DEV)], xg, edge_attr=ea.to(DEV))
+    assert rel(h2, h2r) < 1e-4 and float((x2.detach().cpu() - x2r.detach()).abs().max()) < 1e-4
+    ((h2 * dh.to(DEV)).sum() + (x2 * dx.to(DEV)).sum()).backward()
+    assert rel(hg.grad, h64.grad) < G_TOL, rel(hg.grad, h64.grad)
+    assert rel(xg.grad, x64.grad) < G_TOL, rel(xg.grad, x64.grad)
+    for name, p in gcl.named_parameters():
+        assert p.grad is not None, name
+        assert rel(p.grad, sd["gcl_1." + name].grad) < G_TOL, (name, rel(p.grad, sd["gcl_1." + name].grad))
+
+
+def test_head_train_backward_matches_autograd():
+    """egspr_head_train_backward vs autograd of the oracle's weights + Kabsch (3dm:696-758), incl. a pair whose
+    optimal alignment is a reflection (det < 0 branch, where the reference's own backward raises) and an empty pair."""
+    g = torch.Generator().manual_seed(11)
+    B, n = 4, 300
+    hs = torch.randn(B, n, 32, generator=g) * 0.25
+    ht = hs + 0.1 * torch.randn(B, n, 32, generator=g)
+    xs = torch.randn(B, n, 3, generator=g)
+    xt = torch.empty(B, n, 3)
+    for b in range(B):
+        Q = torch.linalg.qr(torch.randn(3, 3, generator=g))[0]
+        if (torch.det(Q) < 0) != (b == 2):
+            Q[:, 0] *= -1                                           # pair 2: a reflection
+        xt[b] = xs[b] @ Q.T + 0.05 * torch.randn(n, 3, generator=g) + torch.tensor([0.3, -0.2, 0.5])
+    labels = (torch.rand(B, n, generator=g) < 0.7).float()
+    labels[3] = 0                                                   # pair 3: no inliers -> R = I, t = 0, no gradient
+    dR = torch.randn(B, 3, 3, generator=g); dt = torch.randn(B, 3, generator=g); dsim = torch.randn(B, n, generator=g) * 0.1
+    leaves = [v.double().requires_grad_(True) for v in (hs, ht, xs, xt)]
+    loss = 0
+    for b in range(B):
+        w, valid = O.train_weights_one(leaves[0][b], leaves[1][b], labels[b])
+        R, t, _ = O.kabsch(leaves[2][b][valid], leaves[3][b][valid], w)
+        loss = loss + (R * dR[b].double()).sum() + (t * dt[b].double()).sum()
+    loss = loss + ((leaves[0] * leaves[1]).sum(-1) * dsim.double()).sum()
+    loss.backward()
+    outs = ops.head_train_backward(hs.to(DEV), ht.to(DEV), xs.to(DEV), xt.to(DEV), labels.to(DEV), dR.to(DEV), dt.to(DEV), dsim.to(DEV))
+    for o, l, name in zip(outs, leaves, ("dh_src", "dh_tgt", "dx_src", "dx_tgt")):
+        for b in range(B):
+            sc = float(l.grad[b].abs().max()) + 1e-12
+            err = float((o[b].cpu().double() - l.grad[b]).abs().max())
+            assert err <= 2e-4 * sc, (name, b, err, sc)
+
+
+@pytest.mark.parametrize("scenario", ["shipped", "tempered"])
+def test_training_step_gradients_match_reference_golden(golden_dir, scenario):
+    """The whole training step through the drop-in module (forward train variant -> the loop's loss -> backward)
+    against the gradients the reference's own classes + autograd produced for the same inputs."""
+    g = torch.load(os.path.join(golden_dir, "small_b2_n256.pt"), weights_only=False, map_location="cpu")
+    gg = torch.load(os.path.join(golden_dir, "grads_b2_n256.pt"), weights_only=False, map_location="cpu")
+    ref = gg[scenario + "_f32"]
+    model = _model(golden_dir, gg["meta"]["temper"] if scenario == "tempered" else None)
+    model.train()
+    inp = {k: v.to(DEV) for k, v in g["inputs"].items()}
+    es, et = edges_of(g["nbr_src"]).to(DEV), edges_of(g["nbr_tgt"]).to(DEV)
+    ea = torch.ones(es.shape[0], es.shape[-1], 1, device=DEV)
+    out = model(inp["src_feat"], inp["src_pts"], es, ea, inp["tgt_feat"], inp["tgt_pts"], et, ea, inp["corr"], inp["labels"], inp["gt_pose"])
+    if scenario == "shipped":
+        loss = out[2] + out[3]
+    else:
+        loss = P.train.training_loss(out, inp["gt_pose"])
+        assert float((out[0].cpu() - ref["R"]).abs().max()) < 1e-4 and float((out[1].cpu() - ref["t"]).abs().max()) < 1e-4
+    assert abs(float(loss.detach()) - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    loss.backward()
+    params = dict(model.named_parameters())
+    worst, n = 0.0, 0
+    for k, gref in ref["grads"].items():
+        if gref is None:
+            assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0, k
+            continue
+        assert params[k].grad is not None, k
+        e = rel(params[k].grad, gref)
+        worst = max(worst, e)
+        assert e < G_TOL, (k, e)
+        n += 1
+    assert n == 85
+    print(f"{scenario}: worst relative-to-max gradient error {worst:.2e}")
+
+
+def test_train_step_runs_and_reduces_the_loss(golden_dir):
+    """train.train_step (3dm:1092-1126) with Adam on a fixed batch: finite gradients, loss goes down, packs follow
+    the parameter updates."""
+    model = _model(golden_dir, 0.005)
+    data = P.synthetic.make_batch(21, 4, n=512)
+    nbr_s = ops.knn_build(data["src_pts"].to(DEV), 16); nbr_t = ops.knn_build(data["tgt_pts"].to(DEV), 16)
+    es, et = ops.nbr_to_edges(nbr_s), ops.nbr_to_edges(nbr_t)
+    ea = torch.ones(4, es.shape[-1], 1, device=DEV)
+    batch = (data["src_feat"].to(DEV), data["src_pts"].to(DEV), es, ea, data["tgt_feat"].to(DEV), data["tgt_pts"].to(DEV), et, ea,
+             data["corr"].to(DEV), data["labels"].to(DEV), data["gt_pose"].to(DEV))
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    losses = [float(P.train.train_step(model, opt, batch)) for _ in range(8)]
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses

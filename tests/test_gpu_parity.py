@@ -194,6 +194,7 @@ def test_per_layer_states_match_reference(golden_dir, model):
     assert ours <= 1e-5 * float(r64.abs().max())
 
 
+@torch.no_grad()
 def test_egnn_and_egcl_module_signatures(golden_dir, model):
     g, _ = load_case(golden_dir, "small_b2_n256")
     inp = g["inputs"]

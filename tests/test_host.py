@@ -169,3 +169,39 @@ def test_pair_sharding_two_ranks_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert (tmp_path / "r0.txt").read_text() == "0 5" and (tmp_path / "r1.txt").read_text() == "5 10"
+
+
+def test_gradient_allreduce_two_ranks_gloo(tmp_path):
+    """train.allreduce_gradients: ONE flat fp32 bucket over all parameters (BASELINE config 4's only collective);
+    after it every rank holds the mean gradient, parameters without a gradient (dead modules) included
+    as zeros, so identical optimizer steps keep the replicas identical."""
+    script = tmp_path / "g.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import se3_equi_graph_registration_b200 as P\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "torch.manual_seed(0)\n"
+        "egnn = P.EGNN(32, 32, 32, in_edge_nf=1, device='cpu', n_layers=3)\n"
+        "model = P.CrossAttentionPoseRegression(egnn, hidden_nf=32, device='cpu')\n"
+        "params = list(model.parameters())\n"
+        "for i, p in enumerate(params):\n"
+        "    if i % 7 != 3: p.grad = torch.full_like(p, float(r + 1) * (i + 1))\n"     # some parameters get no gradient
+        "flat, views = P.train.flat_gradient(params)\n"
+        "assert flat.numel() == sum(p.numel() for p in params) and views[0].data_ptr() == flat.data_ptr()\n"
+        "P.train.allreduce_gradients(params)\n"
+        "for i, p in enumerate(params):\n"
+        "    want = 0.0 if i % 7 == 3 else 1.5 * (i + 1)\n"
+        "    assert p.grad is not None and torch.all(p.grad == want), (i, p.grad.flatten()[0], want)\n"
+        "opt = torch.optim.Adam(params, lr=1e-3); opt.step()\n"
+        "chk = torch.cat([p.detach().flatten() for p in params]).double().sum().reshape(1)\n"
+        "both = [torch.zeros(1, dtype=torch.float64) for _ in range(w)]; dist.all_gather(both, chk)\n"
+        "assert both[0].item() == both[1].item()\n"
+        f"open(os.path.join({str(tmp_path)!r}, 'ok%d' % r), 'w').write('ok')\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -154,3 +154,44 @@ def test_feature_match_oracle_known_answers():
     # target 3 is equally close to sources 1 and 3 -> argmin over axis 0 picks source 1: (3,3) is not mutual
     assert corr_m.tolist() == [[0, 1], [1, 3], [2, 0]]
     assert D.dtype == np.float32
+
+
+# ---------------------------------------------------------------------------------------------
+# training step: autograd of the oracle restatement == the reference's own backward (golden gradients)
+# ---------------------------------------------------------------------------------------------
+def _train_loss(out, scenario, gt_pose):
+    if scenario == "shipped":
+        return out[2] + out[3]
+    rot, trans = O.pose_loss(out[0], out[1], gt_pose)
+    return out[2] + rot.mean() + trans.mean()                      # 3dm:1107-1118
+
+
+@pytest.mark.parametrize("scenario", ["shipped", "tempered"])
+def test_oracle_gradients_match_reference_golden(golden_dir, scenario):
+    g, sd = load_case(golden_dir, "small_b2_n256")
+    gg = torch.load(os.path.join(golden_dir, "grads_b2_n256.pt"), weights_only=False, map_location="cpu")
+    ref = gg[scenario + "_f32"]
+    sd = {k: v.clone() for k, v in sd.items()}
+    if scenario == "tempered":
+        sd["egnn.embedding_out.weight"] *= gg["meta"]["temper"]
+        sd["egnn.embedding_out.bias"] *= gg["meta"]["temper"]
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    inp = g["inputs"]
+    out = O.forward_train(sd, inp["src_feat"], inp["src_pts"], edges_of(g["nbr_src"]), inp["tgt_feat"], inp["tgt_pts"],
+                          edges_of(g["nbr_tgt"]), inp["labels"], inp["gt_pose"])
+    loss = _train_loss(out, scenario, inp["gt_pose"])
+    assert abs(float(loss.detach()) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    loss.backward()
+    n = 0
+    for k, gref in ref["grads"].items():
+        if gref is None:
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+            continue
+        err = float((sd[k].grad - gref).abs().max())
+        assert err <= 2e-3 * float(gref.abs().max()) + 1e-7, (k, err, float(gref.abs().max()))
+        n += 1
+    assert n == 85                                                  # 85 of 97 tensors get gradients
+    if scenario + "_f64" in gg:     # how far the reference's own fp32 gradients are from its fp64 run (calibrates the GPU bar)
+        r64 = gg[scenario + "_f64"]["grads"]
+        worst = max(float((ref["grads"][k] - r64[k]).abs().max() / r64[k].abs().max()) for k in r64 if r64[k] is not None)
+        assert worst < 1e-3
