@@ -7,6 +7,13 @@ import torch
 from . import ops, packing
 
 
+def _unpacker(module, fn, floats):
+    u = module.__dict__.get("_egspr_grad_unpacker")
+    if u is None:
+        u = module.__dict__["_egspr_grad_unpacker"] = packing.GradUnpacker(fn, floats, module)
+    return u
+
+
 def egnn_param_list(egnn_or_layers, embedding_in=None, embedding_out=None):
     """Flat parameter list in the order EGNNFunction returns gradients:
     [embedding_in.weight, .bias]? + [embedding_out.weight, .bias]? + every layer's parameters()."""
@@ -45,11 +52,11 @@ class EGNNFunction(torch.autograd.Function):
                                                            need_dfeat=need_dfeat or emb_in is None)
         grads = []
         if emb_in is not None:
-            grads += packing.unpack_linear32_grad(g_in, emb_in)
+            grads += _unpacker(emb_in, packing.unpack_linear32_grad, packing.EMBED_PACK)(g_in)
         if emb_out is not None:
-            grads += packing.unpack_linear32_grad(g_out, emb_out)
+            grads += _unpacker(emb_out, packing.unpack_linear32_grad, packing.EMBED_PACK)(g_out)
         for gcl, gp in zip(layers, gpacks):
-            grads += packing.unpack_layer_grad(gp, gcl)
+            grads += _unpacker(gcl, packing.unpack_layer_grad, packing.LAYER_PACK)(gp)
         ctx.saved = None
         return (None, dfeat if need_dfeat else None, dx, *grads)
 

@@ -35,7 +35,13 @@ enum ColId { C_DWC2 = 0, C_DBC1 = 1, C_DLNB = 2, C_DLNG = 3, C_DB2 = 4, C_COUNT 
 struct alignas(16) F4 { float x, y, z, w; };
 EGSPR_HD F4 ld4(const float *p) { return *reinterpret_cast<const F4 *>(p); }     // p 16-byte aligned (weights)
 
-EGSPR_HD float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+EGSPR_HD float sigmoidf_(float v) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(1.0f, 1.0f + __expf(-v));      // MUFU.EX2 + MUFU.RCP, ~2 ulp: far inside the gradient tolerance
+#else
+    return 1.0f / (1.0f + expf(-v));
+#endif
+}
 
 // cross product
 EGSPR_HD void cross3(const float *a, const float *b, float *o) {

@@ -273,6 +273,14 @@ class CrossAttentionPoseRegression(nn.Module):
 
     def _egnn_both(self, h_src, x_src, edges_src, edge_attr_src, h_tgt, x_tgt, edges_tgt, edge_attr_tgt):
         B, N, _ = h_src.shape
+        tensors = torch.is_tensor(edges_src) and torch.is_tensor(edges_tgt) and edges_src.shape == edges_tgt.shape
+        if tensors and (edge_attr_src is None) == (edge_attr_tgt is None):
+            # both cloud sets as ONE graph of 2B clouds: one launch sequence (sources = clouds 0..B-1, targets B..2B-1)
+            g = ops.csr_from_edges(torch.cat([edges_src, edges_tgt]).to(torch.int64), N)
+            ea = None if edge_attr_src is None else torch.cat([edge_attr_src, edge_attr_tgt])
+            h, x = self.egnn.forward_batch(torch.cat([h_src, h_tgt]).to(torch.float32), torch.cat([x_src, x_tgt]).to(torch.float32),
+                                           g, edge_attr=ea, edge_attr_const=0.0 if ea is not None else 1.0)
+            return h[:B], x[:B], h[B:], x[B:]
         g_src = edges_src if isinstance(edges_src, ops.BatchGraph) else ops.csr_from_edges(edges_src.to(torch.int64), N)
         g_tgt = edges_tgt if isinstance(edges_tgt, ops.BatchGraph) else ops.csr_from_edges(edges_tgt.to(torch.int64), N)
         hs, xs = self.egnn.forward_batch(h_src.to(torch.float32), x_src.to(torch.float32), g_src,

@@ -138,3 +138,26 @@ def unpack_layer_grad(gpack, gcl):
 def unpack_linear32_grad(gpack, lin):
     """gpack [EMBED_PACK] -> [d weight (32,32), d bias (32)] of an embedding Linear."""
     return [_g(gpack, 0, 32, 32).t().contiguous(), _g(gpack, 1024, 32).contiguous()]
+
+
+class GradUnpacker:
+    """unpack_*_grad as ONE gather: the pack -> parameter re-layout is a permutation, so its index map is obtained
+    once by unpacking an arange, and every later call is `flat = gpack[index]` + views (one kernel instead of ~40)."""
+
+    def __init__(self, unpack_fn, pack_floats, module):
+        probe = unpack_fn(torch.arange(pack_floats, dtype=torch.float32), module)
+        self.shapes = [tuple(t.shape) for t in probe]
+        self.sizes = [t.numel() for t in probe]
+        self.index_cpu = torch.cat([t.reshape(-1) for t in probe]).to(torch.int64)
+        self._index = {}
+
+    def __call__(self, gpack):
+        idx = self._index.get(gpack.device)
+        if idx is None:
+            idx = self._index[gpack.device] = self.index_cpu.to(gpack.device)
+        flat = gpack[idx]
+        out, off = [], 0
+        for shp, n in zip(self.shapes, self.sizes):
+            out.append(flat[off:off + n].view(shp))
+            off += n
+        return out

@@ -280,9 +280,6 @@ def test_forward_train_variant(golden_dir):
             assert float((model.last_aux["w"][b].cpu() - wref).abs().max()) <= 1e-3 * float(wref.max())
             assert float((model.last_aux["H"][b].cpu() - aux["H"][b]).abs().max()) <= 1e-3 * float(aux["H"][b].abs().max())
             assert abs(float(torch.det(out[0][b].cpu().double())) - 1.0) < 1e-4
-    with pytest.raises(NotImplementedError):
-        model.train()
-        model(inp["src_feat"], inp["src_pts"], es, None, inp["tgt_feat"], inp["tgt_pts"], et, None, inp["corr"], inp["labels"], inp["gt_pose"])
 
 
 # ---------------------------------------------------------------------------------------------
