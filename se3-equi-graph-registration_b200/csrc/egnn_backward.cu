@@ -72,7 +72,7 @@ __device__ __forceinline__ void outer8(float (&acc)[8], const float *__restrict_
         const float a = sIn[e * RS + i];
         const float *o = sOut + e * RS + ob;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = fmaf(a, o[q], acc[q]);
+        for (int q = 0; q < 8; q += 2) fma2(acc[q], acc[q + 1], a, a, o[q], o[q + 1]);
     }
 }
 // in_major: gradient matrix stored [in][out] (transposed packs) else [out][in]
@@ -316,41 +316,53 @@ __global__ void __launch_bounds__(BT) node_gather_backward_kernel(const GatherAr
     float colQ = 0.f;
     const int64_t G = a.num_nodes;
     const int64_t tiles = (G + BT - 1) / BT;
+    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;       // phase 1: 8 lanes per node, 4 features each
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        // phase 1: coalesced gathers (one 128-byte dpre row per 8 lanes) -> dP, dQ rows of the tile, dx_in
+        for (int ln = grp; ln < BT; ln += BT / 8) {
+            const int64_t n = tile * BT + ln;
+            float4 dp = make_float4(0.f, 0.f, 0.f, 0.f), dq = dp;
+            float dxa = 0.f;                                           // lanes 0..2 carry x, y, z
+            if (n < G) {
+                const int64_t ebase = (n / a.n_per_cloud) * a.edges_per_cloud;
+                for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; ++p) {   // edges with row == n
+                    const int64_t ge = ebase + __ldg(a.csr_eid + p);
+                    const float4 t = ldg4(a.dpre + ge * H + 4 * sub);
+                    dp.x += t.x; dp.y += t.y; dp.z += t.z; dp.w += t.w;
+                    if (sub < 3) dxa += __ldg(a.dxe + ge * 8 + sub);
+                }
+                for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; ++p) {   // edges with col == n
+                    const int64_t ge = ebase + __ldg(a.csc_eid + p);
+                    const float4 t = ldg4(a.dpre + ge * H + 4 * sub);
+                    dq.x += t.x; dq.y += t.y; dq.z += t.z; dq.w += t.w;
+                    if (sub < 3) dxa += __ldg(a.dxe + ge * 8 + 4 + sub);
+                }
+                if (sub < 3) a.dx_in[n * 3 + sub] = __ldg(a.dx_out + n * 3 + sub) + dxa;
+                const float4 hv = ldg4(a.h + n * H + 4 * sub);
+                float *rh = sH + ln * RS + 4 * sub;
+                rh[0] = hv.x; rh[1] = hv.y; rh[2] = hv.z; rh[3] = hv.w;
+            } else {
+                float *rh = sH + ln * RS + 4 * sub;
+                rh[0] = rh[1] = rh[2] = rh[3] = 0.f;
+            }
+            float *rp = sDp + ln * RS + 4 * sub, *rq = sDq + ln * RS + 4 * sub;
+            rp[0] = dp.x; rp[1] = dp.y; rp[2] = dp.z; rp[3] = dp.w;
+            rq[0] = dq.x; rq[1] = dq.y; rq[2] = dq.z; rq[3] = dq.w;
+        }
+        __syncthreads();
+        // phase 2: thread = node: P/Q halves of the first edge Linear back to dh
         const int64_t n = tile * BT + threadIdx.x;
-        float *rH = sH + threadIdx.x * RS, *rP = sDp + threadIdx.x * RS, *rQ = sDq + threadIdx.x * RS;
         float dq[32];
-        if (n < G) {
-            const int64_t ebase = (n / a.n_per_cloud) * a.edges_per_cloud;
-            float dp[32];
-            float dx[3] = {__ldg(a.dx_out + n * 3), __ldg(a.dx_out + n * 3 + 1), __ldg(a.dx_out + n * 3 + 2)};
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { dp[j] = 0.f; dq[j] = 0.f; }
-            for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; ++p) {   // edges with row == n
-                const int64_t ge = ebase + __ldg(a.csr_eid + p);
-                add_row32g(dp, a.dpre + ge * H);
-                const float4 t = ldg4(a.dxe + ge * 8);
-                dx[0] += t.x; dx[1] += t.y; dx[2] += t.z;
-            }
-            for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; ++p) {   // edges with col == n
-                const int64_t ge = ebase + __ldg(a.csc_eid + p);
-                add_row32g(dq, a.dpre + ge * H);
-                const float4 t = ldg4(a.dxe + ge * 8 + 4);
-                dx[0] += t.x; dx[1] += t.y; dx[2] += t.z;
-            }
-            a.dx_in[n * 3] = dx[0]; a.dx_in[n * 3 + 1] = dx[1]; a.dx_in[n * 3 + 2] = dx[2];
+        for (int j = 0; j < 32; ++j) dq[j] = sDq[threadIdx.x * RS + j];
+        if (n < G) {
+            float dp[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dp[j] = sDp[threadIdx.x * RS + j];
             linear32_backward_input(sw, dp, a.dh_in + n * H, true);
             linear32_backward_input(sw + 1024, dq, a.dh_in + n * H, true);
-            float hv[32];
-            load_row32g(hv, a.h + n * H);
-            stash_row(rH, hv); stash_row(rP, dp);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { dq[j] = 0.f; rH[j] = 0.f; rP[j] = 0.f; }
         }
-        stash_row(rQ, dq);
         colQ += warp_colsum32(dq);
-        __syncthreads();
         outer8(accP, sH, sDp);      // dWPT[i][o] += h[i] dP[o]
         outer8(accQ, sH, sDq);
         __syncthreads();

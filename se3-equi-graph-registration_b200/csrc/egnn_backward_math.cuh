@@ -35,6 +35,19 @@ enum ColId { C_DWC2 = 0, C_DBC1 = 1, C_DLNB = 2, C_DLNG = 3, C_DB2 = 4, C_COUNT 
 struct alignas(16) F4 { float x, y, z, w; };
 EGSPR_HD F4 ld4(const float *p) { return *reinterpret_cast<const F4 *>(p); }     // p 16-byte aligned (weights)
 
+// (c0, c1) += (a0, a1) * (b0, b1), each lane rounded like fmaf: one FFMA2 issue slot on sm_100
+EGSPR_HD void fma2(float &c0, float &c1, float a0, float a1, float b0, float b1) {
+#ifdef __CUDA_ARCH__
+    asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rd, {%0, %1};\n"
+        "fma.rn.f32x2 rd, ra, rb, rd;\nmov.b64 {%0, %1}, rd;\n}"
+        : "+f"(c0), "+f"(c1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+#else
+    c0 = fmaf(a0, b0, c0);
+    c1 = fmaf(a1, b1, c1);
+#endif
+}
+
 EGSPR_HD float sigmoidf_(float v) {
 #ifdef __CUDA_ARCH__
     return __fdividef(1.0f, 1.0f + __expf(-v));      // MUFU.EX2 + MUFU.RCP, ~2 ulp: far inside the gradient tolerance
@@ -146,7 +159,7 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             const F4 wv = ld4(w + B_WG + 32 * k + o4);
-            p0 = fmaf(wv.x, gk[k], p0); p1 = fmaf(wv.y, gk[k], p1); p2 = fmaf(wv.z, gk[k], p2); p3 = fmaf(wv.w, gk[k], p3);
+            fma2(p0, p1, wv.x, wv.y, gk[k], gk[k]); fma2(p2, p3, wv.z, wv.w, gk[k], gk[k]);
         }
         const float pr[4] = {p0, p1, p2, p3};
 #pragma unroll
@@ -170,8 +183,8 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
             const float av = rA1[8 * hd + i];
             const F4 w0 = ld4(w + B_W2P + 64 * hd + 8 * i), w1 = ld4(w + B_W2P + 64 * hd + 8 * i + 4);
             float *u = uh + 8 * hd;
-            u[0] = fmaf(w0.x, av, u[0]); u[1] = fmaf(w0.y, av, u[1]); u[2] = fmaf(w0.z, av, u[2]); u[3] = fmaf(w0.w, av, u[3]);
-            u[4] = fmaf(w1.x, av, u[4]); u[5] = fmaf(w1.y, av, u[5]); u[6] = fmaf(w1.z, av, u[6]); u[7] = fmaf(w1.w, av, u[7]);
+            fma2(u[0], u[1], w0.x, w0.y, av, av); fma2(u[2], u[3], w0.z, w0.w, av, av);
+            fma2(u[4], u[5], w1.x, w1.y, av, av); fma2(u[6], u[7], w1.z, w1.w, av, av);
         }
     }
     float mean = 0.f;
@@ -199,8 +212,8 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
                 const F4 w0 = ld4(w + B_WC1 + 32 * o + i), w1 = ld4(w + B_WC1 + 32 * o + i + 4);
-                c0 = fmaf(w0.x, m[i], c0); c1 = fmaf(w0.y, m[i + 1], c1); c0 = fmaf(w0.z, m[i + 2], c0); c1 = fmaf(w0.w, m[i + 3], c1);
-                c0 = fmaf(w1.x, m[i + 4], c0); c1 = fmaf(w1.y, m[i + 5], c1); c0 = fmaf(w1.z, m[i + 6], c0); c1 = fmaf(w1.w, m[i + 7], c1);
+                fma2(c0, c1, w0.x, w0.y, m[i], m[i + 1]); fma2(c0, c1, w0.z, w0.w, m[i + 2], m[i + 3]);
+                fma2(c0, c1, w1.x, w1.y, m[i + 4], m[i + 5]); fma2(c0, c1, w1.z, w1.w, m[i + 6], m[i + 7]);
             }
             const float c = c0 + c1;
             const float sg = sigmoidf_(c);
@@ -230,8 +243,7 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             const F4 wv = ld4(w + B_WC1 + 32 * o + i);
-            dm[i] = fmaf(wv.x, dc, dm[i]); dm[i + 1] = fmaf(wv.y, dc, dm[i + 1]);
-            dm[i + 2] = fmaf(wv.z, dc, dm[i + 2]); dm[i + 3] = fmaf(wv.w, dc, dm[i + 3]);
+            fma2(dm[i], dm[i + 1], wv.x, wv.y, dc, dc); fma2(dm[i + 2], dm[i + 3], wv.z, wv.w, dc, dc);
         }
     }
     sink.template col<C_DLNB>(dm);
@@ -260,25 +272,27 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
         for (int i = 0; i < 8; ++i) {
             const F4 w0 = ld4(w + B_W2P + 64 * hd + 8 * i), w1 = ld4(w + B_W2P + 64 * hd + 8 * i + 4);
             const float *du = dm + 8 * hd;
-            float t = w0.x * du[0];
-            t = fmaf(w0.y, du[1], t); t = fmaf(w0.z, du[2], t); t = fmaf(w0.w, du[3], t);
-            t = fmaf(w1.x, du[4], t); t = fmaf(w1.y, du[5], t); t = fmaf(w1.z, du[6], t); t = fmaf(w1.w, du[7], t);
-            rDPRE[8 * hd + i] *= t;
+            float t0 = 0.f, t1 = 0.f;
+            fma2(t0, t1, w0.x, w0.y, du[0], du[1]); fma2(t0, t1, w0.z, w0.w, du[2], du[3]);
+            fma2(t0, t1, w1.x, w1.y, du[4], du[5]); fma2(t0, t1, w1.z, w1.w, du[6], du[7]);
+            rDPRE[8 * hd + i] *= (t0 + t1);
         }
     }
     // geometry backward (+ the coordinate update's own use of coord_diff)
-    float gg[12];
+    float gg[12], gh[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) gg[k] = 0.f;
+    for (int k = 0; k < 12; ++k) { gg[k] = 0.f; gh[k] = 0.f; }
 #pragma unroll 1
     for (int o4 = 0; o4 < 32; o4 += 4) {
         const float d0 = rDPRE[o4], d1 = rDPRE[o4 + 1], d2 = rDPRE[o4 + 2], d3 = rDPRE[o4 + 3];
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             const F4 wv = ld4(w + B_WG + 32 * k + o4);
-            gg[k] = fmaf(wv.x, d0, gg[k]); gg[k] = fmaf(wv.y, d1, gg[k]); gg[k] = fmaf(wv.z, d2, gg[k]); gg[k] = fmaf(wv.w, d3, gg[k]);
+            fma2(gg[k], gh[k], wv.x, wv.y, d0, d1); fma2(gg[k], gh[k], wv.z, wv.w, d2, d3);
         }
     }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) gg[k] += gh[k];
     const float gde[3] = {s * dxo[0], s * dxo[1], s * dxo[2]};
     edge_geometry_backward(xr, xc, g, gg, gde, dxr, dxc);
 }
@@ -303,8 +317,7 @@ EGSPR_HD void node_backward(const float *w, const float *rH, const float *rAgg, 
 #pragma unroll
         for (int o4 = 0; o4 < 32; o4 += 4) {
             const F4 wv = ld4(w + B_WN1T + 32 * i + o4);
-            z[o4] = fmaf(wv.x, v, z[o4]); z[o4 + 1] = fmaf(wv.y, v, z[o4 + 1]);
-            z[o4 + 2] = fmaf(wv.z, v, z[o4 + 2]); z[o4 + 3] = fmaf(wv.w, v, z[o4 + 3]);
+            fma2(z[o4], z[o4 + 1], wv.x, wv.y, v, v); fma2(z[o4 + 2], z[o4 + 3], wv.z, wv.w, v, v);
         }
     }
 #pragma unroll
@@ -319,8 +332,7 @@ EGSPR_HD void node_backward(const float *w, const float *rH, const float *rAgg, 
 #pragma unroll
         for (int o4 = 0; o4 < 32; o4 += 4) {
             const F4 wv = ld4(w + B_WN2T + 32 * i + o4);
-            t0 = fmaf(wv.x, dout[o4], t0); t1 = fmaf(wv.y, dout[o4 + 1], t1);
-            t0 = fmaf(wv.z, dout[o4 + 2], t0); t1 = fmaf(wv.w, dout[o4 + 3], t1);
+            fma2(t0, t1, wv.x, wv.y, dout[o4], dout[o4 + 1]); fma2(t0, t1, wv.z, wv.w, dout[o4 + 2], dout[o4 + 3]);
         }
         rZ[i] *= (t0 + t1);
     }
@@ -332,8 +344,7 @@ EGSPR_HD void node_backward(const float *w, const float *rH, const float *rAgg, 
 #pragma unroll
         for (int o4 = 0; o4 < 32; o4 += 4) {
             const F4 wv = ld4(w + B_WN1T + 32 * i + o4);
-            t0 = fmaf(wv.x, z[o4], t0); t1 = fmaf(wv.y, z[o4 + 1], t1);
-            t0 = fmaf(wv.z, z[o4 + 2], t0); t1 = fmaf(wv.w, z[o4 + 3], t1);
+            fma2(t0, t1, wv.x, wv.y, z[o4], z[o4 + 1]); fma2(t0, t1, wv.z, wv.w, z[o4 + 2], z[o4 + 3]);
         }
         if (i < 32) dh[i] = rDout[i] + (t0 + t1);
         else dagg[i - 32] = t0 + t1;
@@ -349,8 +360,7 @@ EGSPR_HD void linear32_backward_input(const float *wt, const float *dy, float *d
 #pragma unroll
         for (int o4 = 0; o4 < 32; o4 += 4) {
             const F4 wv = ld4(wt + 32 * i + o4);
-            t0 = fmaf(wv.x, dy[o4], t0); t1 = fmaf(wv.y, dy[o4 + 1], t1);
-            t0 = fmaf(wv.z, dy[o4 + 2], t0); t1 = fmaf(wv.w, dy[o4 + 3], t1);
+            fma2(t0, t1, wv.x, wv.y, dy[o4], dy[o4 + 1]); fma2(t0, t1, wv.z, wv.w, dy[o4 + 2], dy[o4 + 3]);
         }
         dx[i] = (accumulate ? dx[i] : 0.f) + (t0 + t1);
     }

@@ -73,6 +73,7 @@ class BatchGraph:
     cptr: torch.Tensor = None   # [G+1] i32  the same edges grouped by col (backward pass only, see with_csc)
     ceid: torch.Tensor = None   # [E] i32
     edges: torch.Tensor = None  # the [C,2,E] i64 edge tensor the graph was built from (kept for with_csc)
+    nbr: torch.Tensor = None    # ... or the k-NN ids it was built from
 
     def check(self):
         if int(self.err.item()) != 0:
@@ -99,6 +100,7 @@ def csr_from_nbr(nbr):
     with torch.cuda.device(nbr.device):
         _lib.check(_lib.lib().egspr_csr_from_nbr(_ptr(nbr), C, N, k, _ptr(g.ptr), _ptr(g.row), _ptr(g.col), _ptr(g.eid),
                                                  _ptr(ws), ws_bytes, _ptr(g.err), _stream()), "egspr_csr_from_nbr")
+    g.nbr = nbr
     return g
 
 
@@ -123,6 +125,7 @@ def with_csc(graph, nbr=None):
     tensor with its two rows swapped.  Graphs built from k-NN ids pass `nbr` (the edge tensor is rebuilt from it)."""
     if graph.cptr is not None:
         return graph
+    nbr = nbr if nbr is not None else graph.nbr
     edges = graph.edges if graph.edges is not None else (nbr_to_edges(nbr) if nbr is not None else None)
     if edges is None:
         raise ValueError("with_csc needs the edge tensor (or the k-NN ids) the graph was built from")
