@@ -317,17 +317,23 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
     with torch.no_grad():
         model.egnn.embedding_out.weight.mul_(TRAIN_TEMPER)
         model.egnn.embedding_out.bias.mul_(TRAIN_TEMPER)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)     # same update rule as 3dm:1619, one launch
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, capturable=True)     # same update rule as 3dm:1619
     B = TRAIN_PAIRS_PER_GPU
-    batches = [{k: v.to(dev) for k, v in P.synthetic.make_batch(500 + rank * 4 + i, B, n=N_POINTS).items()} for i in range(4)]
-    ones = torch.ones(B, N_POINTS * K_NEIGH, 1, device=dev)
+    keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
+    batches = [tuple(v.to(dev) for v in (P.synthetic.make_batch(500 + rank * 4 + i, B, n=N_POINTS)[k] for k in keys)) for i in range(4)]
+    mode = "cuda graph"
+    try:
+        graphed = P.train.GraphedTrainStep(model, opt, batches[0], k=K_NEIGH)
+        step = lambda i: graphed(batches[i % 4])
+    except Exception as e:                                   # capture refused (e.g. a collective that cannot be captured)
+        mode = f"eager ({type(e).__name__})"
+        torch.cuda.synchronize()
+        ones = torch.ones(B, N_POINTS * K_NEIGH, 1, device=dev)
 
-    def step(i):
-        d = batches[i % 4]
-        es = P.knn_graph_batch(d["src_pts"], K_NEIGH)                 # 3dm:1003-1013, one launch sequence per cloud set
-        et = P.knn_graph_batch(d["tgt_pts"], K_NEIGH)
-        return P.train.train_step(model, opt, (d["src_feat"], d["src_pts"], es, ones, d["tgt_feat"], d["tgt_pts"], et, ones,
-                                               d["corr"], d["labels"], d["gt_pose"]))
+        def step(i):
+            sf, sp, tf, tp, corr, labels, gt = batches[i % 4]
+            es, et = P.knn_graph_batch(sp, K_NEIGH), P.knn_graph_batch(tp, K_NEIGH)      # 3dm:1003-1013
+            return P.train.train_step(model, opt, (sf, sp, es, ones, tf, tp, et, ones, corr, labels, gt))
 
     for i in range(warmup):
         loss = step(i)
@@ -344,7 +350,7 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
     return {"workload": "BASELINE configs[3]: 3DMatch training step, fwd + bwd + Adam, 16 pairs/GPU x 2 clouds x 2048 pts, "
                         "k-NN graph build included; gradient all-reduce (one flat fp32 bucket, NCCL) when n_gpus > 1",
             "pairs_per_gpu": B, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": "pairs/s (training)",
-            "steps": steps, "loss_finite": finite, "embedding_out_scale": TRAIN_TEMPER}
+            "steps": steps, "loss_finite": finite, "embedding_out_scale": TRAIN_TEMPER, "launch_mode": mode}
 
 
 def eng_layer_time(eng, reps=20):

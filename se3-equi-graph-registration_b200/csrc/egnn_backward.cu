@@ -180,7 +180,9 @@ struct EdgeBwdArgs {
 };
 
 constexpr int EB_W_N = EDGE_PART + 32;     // edge part of the pack + the edge_attr column
-constexpr size_t EB_SMEM = sizeof(float) * (EB_W_N + V_COUNT * BT * RS + BT * 13);
+// shared memory: weights | M, A1 edge-major [BT][RS] | DC1, DU, DPRE feature-major [32][BT] | geo [BT][16 (13 used)]
+constexpr int GS = 17;                     // geo row stride (odd: conflict-free own-row writes)
+constexpr size_t EB_SMEM = sizeof(float) * (EB_W_N + 2 * BT * RS + 3 * 32 * BT + BT * GS);
 
 struct DevSink {
     float colacc[C_COUNT];
@@ -192,21 +194,28 @@ struct DevSink {
     }
 };
 
-__global__ void __launch_bounds__(BT) edge_backward_kernel(const EdgeBwdArgs a) {
+__global__ void __launch_bounds__(BT, 2) edge_backward_kernel(const EdgeBwdArgs a) {
     extern __shared__ __align__(16) float smem[];
     float *sw = smem;                          // [0,1824) edge part, [1824,1856) edge_attr column
-    float *sV = smem + EB_W_N;                 // V_COUNT stashes of [BT][RS]
-    float *sGeo = sV + V_COUNT * BT * RS;      // [BT][13]
+    float *sM = smem + EB_W_N, *sA1 = sM + BT * RS;                              // "in" rows of the outer products
+    float *sDC1 = sA1 + BT * RS, *sDU = sDC1 + 32 * BT, *sDPRE = sDU + 32 * BT;  // "out" rows, feature-major
+    float *sGeo = sDPRE + 32 * BT;
     for (int i = threadIdx.x; i < EDGE_PART; i += BT) sw[i] = __ldg(a.pack + i);
     if (threadIdx.x < 32) sw[EDGE_PART + threadIdx.x] = __ldg(a.pack + B_WEA + threadIdx.x);
     __syncthreads();
     const int tid = threadIdx.x;
     DevSink sink;
-    float *rM = sV + V_M * BT * RS + tid * RS, *rDC1 = sV + V_DC1 * BT * RS + tid * RS, *rA1 = sV + V_A1 * BT * RS + tid * RS,
-          *rDU = sV + V_DU * BT * RS + tid * RS, *rDPRE = sV + V_DPRE * BT * RS + tid * RS, *rGeo = sGeo + tid * 13;
+    float *rM = sM + tid * RS, *rA1 = sA1 + tid * RS, *rDC1 = sDC1 + tid, *rDU = sDU + tid, *rDPRE = sDPRE + tid,
+          *rGeo = sGeo + tid * GS;
 #pragma unroll
     for (int c = 0; c < C_COUNT; ++c) sink.colacc[c] = 0.f;
-    float accWc1[8] = {0}, accW2[2] = {0, 0}, accWg[4] = {0, 0, 0, 0};
+    float accWc1[16], accW2[4], accWg[8];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) accWc1[q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) accW2[q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) accWg[q] = 0.f;
     const int64_t E = __ldg(a.csr_ptr + a.num_nodes);
     const int64_t tiles = (E + BT - 1) / BT;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -223,7 +232,8 @@ __global__ void __launch_bounds__(BT) edge_backward_kernel(const EdgeBwdArgs a) 
             float pq[32];
             load_row32g(pq, a.P + (int64_t)r * H);
             add_row32g(pq, a.Q + (int64_t)c * H);
-            stash_row(rDPRE, pq);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rDPRE[j * BT] = pq[j];
         }
         float dagg[32], dxo[3];
         if (valid) {
@@ -235,52 +245,75 @@ __global__ void __launch_bounds__(BT) edge_backward_kernel(const EdgeBwdArgs a) 
             dxo[0] = dxo[1] = dxo[2] = 0.f;
         }
         float dxr[3], dxc[3];
-        edge_backward(sw, sw + EDGE_PART, xr, xc, ea, dagg, dxo, rM, rDC1, rA1, rDU, rDPRE, rGeo, sink, dxr, dxc);
+        edge_backward<BT>(sw, sw + EDGE_PART, xr, xc, ea, dagg, dxo, rM, rDC1, rA1, rDU, rDPRE, rGeo, sink, dxr, dxc);
         if (valid) {
             float dpre[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dpre[j] = rDPRE[j];
+            for (int j = 0; j < 32; ++j) dpre[j] = rDPRE[j * BT];
             store_row32g(a.dpre + ge * H, dpre);
             *reinterpret_cast<float4 *>(a.dxe + ge * 8) = make_float4(dxr[0], dxr[1], dxr[2], 0.f);
             *reinterpret_cast<float4 *>(a.dxe + ge * 8 + 4) = make_float4(dxc[0], dxc[1], dxc[2], 0.f);
         }
         __syncthreads();
-        // weight gradients of this tile
-        outer8(accWc1, sV + V_M * BT * RS, sV + V_DC1 * BT * RS);          // dWc1[o][i] += dc1[o] m[i]
+        // ---- weight gradients of this tile: "in" rows read per edge, "out" rows four edges per 128-bit load ----
         {
-            const int idx = 2 * tid, hb = (idx >> 6) * 8, ii = (idx >> 3) & 7, oo = idx & 7;   // dW2P[hd][i][o] += a1 du
-            const float *sA1 = sV + V_A1 * BT * RS + hb + ii, *sDu = sV + V_DU * BT * RS + hb + oo;
-#pragma unroll 4
-            for (int e = 0; e < BT; ++e) {
-                const float av = sA1[e * RS];
-                accW2[0] = fmaf(av, sDu[e * RS], accW2[0]);
-                accW2[1] = fmaf(av, sDu[e * RS + 1], accW2[1]);
+            const int i = tid & 31, ob = (tid >> 5) * 8;                      // dWc1[o][i] += dc1[o] m[i], o = ob + q
+            const float *in = sM + i;
+#pragma unroll 2
+            for (int e = 0; e < BT; e += 4) {
+                const float m0 = in[e * RS], m1 = in[(e + 1) * RS], m2 = in[(e + 2) * RS], m3 = in[(e + 3) * RS];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 ov = *reinterpret_cast<const float4 *>(sDC1 + (ob + q) * BT + e);
+                    fma2(accWc1[2 * q], accWc1[2 * q + 1], m0, m1, ov.x, ov.y);
+                    fma2(accWc1[2 * q], accWc1[2 * q + 1], m2, m3, ov.z, ov.w);
+                }
             }
         }
         {
-            const int o = tid & 31, gb = tid >> 5;                             // dWg[k][o] += geo[k] dpre[o], k = gb + 4 j
-            const float *sDp = sV + V_DPRE * BT * RS + o;
-#pragma unroll 4
-            for (int e = 0; e < BT; ++e) {
-                const float dv = sDp[e * RS];
-                const float *gr = sGeo + e * 13 + gb;
-                accWg[0] = fmaf(gr[0], dv, accWg[0]);
-                accWg[1] = fmaf(gr[4], dv, accWg[1]);
-                accWg[2] = fmaf(gr[8], dv, accWg[2]);
-                if (gb == 0) accWg[3] = fmaf(gr[12], dv, accWg[3]);
+            const int idx = 2 * tid, hb = (idx >> 6) * 8, ii = (idx >> 3) & 7, oo = idx & 7;   // dW2P[hd][i][o] += a1 du
+            const float *in = sA1 + hb + ii;
+            const float *o0 = sDU + (hb + oo) * BT, *o1 = o0 + BT;
+#pragma unroll 2
+            for (int e = 0; e < BT; e += 4) {
+                const float a0 = in[e * RS], a1 = in[(e + 1) * RS], a2 = in[(e + 2) * RS], a3 = in[(e + 3) * RS];
+                const float4 u = *reinterpret_cast<const float4 *>(o0 + e), v = *reinterpret_cast<const float4 *>(o1 + e);
+                fma2(accW2[0], accW2[1], a0, a1, u.x, u.y); fma2(accW2[0], accW2[1], a2, a3, u.z, u.w);
+                fma2(accW2[2], accW2[3], a0, a1, v.x, v.y); fma2(accW2[2], accW2[3], a2, a3, v.z, v.w);
+            }
+        }
+        {
+            const int k = tid & 15, ob = (tid >> 4) * 4;                      // dWg[k][o] += geo[k] dpre[o], o = ob + q
+            if (k < 13) {
+                const float *in = sGeo + k;
+#pragma unroll 2
+                for (int e = 0; e < BT; e += 4) {
+                    const float g0 = in[e * GS], g1 = in[(e + 1) * GS], g2 = in[(e + 2) * GS], g3 = in[(e + 3) * GS];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 ov = *reinterpret_cast<const float4 *>(sDPRE + (ob + q) * BT + e);
+                        fma2(accWg[2 * q], accWg[2 * q + 1], g0, g1, ov.x, ov.y);
+                        fma2(accWg[2 * q], accWg[2 * q + 1], g2, g3, ov.z, ov.w);
+                    }
+                }
             }
         }
         __syncthreads();
     }
-    flush8(accWc1, a.gpack + B_WC1, false);
-    atomicAdd(a.gpack + B_W2P + 2 * tid, accW2[0]);
-    atomicAdd(a.gpack + B_W2P + 2 * tid + 1, accW2[1]);
     {
-        const int o = tid & 31, gb = tid >> 5;
-        atomicAdd(a.gpack + B_WG + 32 * gb + o, accWg[0]);
-        atomicAdd(a.gpack + B_WG + 32 * (gb + 4) + o, accWg[1]);
-        atomicAdd(a.gpack + B_WG + 32 * (gb + 8) + o, accWg[2]);
-        if (gb == 0) atomicAdd(a.gpack + B_WEA + o, accWg[3]);
+        const int i = tid & 31, ob = (tid >> 5) * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(a.gpack + B_WC1 + 32 * (ob + q) + i, accWc1[2 * q] + accWc1[2 * q + 1]);
+    }
+    atomicAdd(a.gpack + B_W2P + 2 * tid, accW2[0] + accW2[1]);
+    atomicAdd(a.gpack + B_W2P + 2 * tid + 1, accW2[2] + accW2[3]);
+    {
+        const int k = tid & 15, ob = (tid >> 4) * 4;
+        if (k < 13) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                atomicAdd(a.gpack + (k < 12 ? B_WG + 32 * k : B_WEA) + ob + q, accWg[2 * q] + accWg[2 * q + 1]);
+        }
     }
     const int lane = tid & 31;
     atomicAdd(a.gpack + B_WC2 + lane, sink.colacc[C_DWC2]);
@@ -325,17 +358,36 @@ __global__ void __launch_bounds__(BT) node_gather_backward_kernel(const GatherAr
             float dxa = 0.f;                                           // lanes 0..2 carry x, y, z
             if (n < G) {
                 const int64_t ebase = (n / a.n_per_cloud) * a.edges_per_cloud;
-                for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; ++p) {   // edges with row == n
-                    const int64_t ge = ebase + __ldg(a.csr_eid + p);
-                    const float4 t = ldg4(a.dpre + ge * H + 4 * sub);
-                    dp.x += t.x; dp.y += t.y; dp.z += t.z; dp.w += t.w;
-                    if (sub < 3) dxa += __ldg(a.dxe + ge * 8 + sub);
+                // eight edges per step: the group's lanes fetch the ids (one coalesced load), then all eight row loads
+                // are issued before any is used; sums stay in ascending list order
+                const unsigned gmask = 0xffu << (threadIdx.x & 24);
+                for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; p += 8) {   // edges with row == n
+                    const int mine = p + sub < pe ? __ldg(a.csr_eid + p + sub) : -1;
+                    float4 t[8];
+                    float tx[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int ej = __shfl_sync(gmask, mine, j, 8);
+                        const int64_t ge = ebase + (ej < 0 ? 0 : ej);
+                        t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
+                        tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + sub);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { dp.x += t[j].x; dp.y += t[j].y; dp.z += t[j].z; dp.w += t[j].w; dxa += tx[j]; }
                 }
-                for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; ++p) {   // edges with col == n
-                    const int64_t ge = ebase + __ldg(a.csc_eid + p);
-                    const float4 t = ldg4(a.dpre + ge * H + 4 * sub);
-                    dq.x += t.x; dq.y += t.y; dq.z += t.z; dq.w += t.w;
-                    if (sub < 3) dxa += __ldg(a.dxe + ge * 8 + 4 + sub);
+                for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; p += 8) {   // edges with col == n
+                    const int mine = p + sub < pe ? __ldg(a.csc_eid + p + sub) : -1;
+                    float4 t[8];
+                    float tx[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int ej = __shfl_sync(gmask, mine, j, 8);
+                        const int64_t ge = ebase + (ej < 0 ? 0 : ej);
+                        t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
+                        tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + 4 + sub);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { dq.x += t[j].x; dq.y += t[j].y; dq.z += t[j].z; dq.w += t[j].w; dxa += tx[j]; }
                 }
                 if (sub < 3) a.dx_in[n * 3 + sub] = __ldg(a.dx_out + n * 3 + sub) + dxa;
                 const float4 hv = ldg4(a.h + n * H + 4 * sub);

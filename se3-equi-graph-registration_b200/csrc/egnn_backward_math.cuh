@@ -136,11 +136,13 @@ EGSPR_HD void edge_geometry_backward(const float *xr, const float *xc, const Edg
 //            wea = the edge_attr column (pack + B_WEA)
 //   xr, xc   coordinates of row / col endpoint;  ea = edge_attr value
 //   dagg     d loss / d agg[row]  (32 floats)    dxo = d loss / d coord_out[row]  (3)
-//   rows     rDPRE holds P[row] + Q[col] on entry.  On return: rM = message m, rDC1 = d loss / d (coord_mlp.0 output),
+//   rows     rM, rA1: contiguous 32-float rows; rDC1, rDU, rDPRE: element j lives at [j * OS] (the device keeps these
+//            three feature-major, OS = tile size, so that the tile reduction reads 4 edges per 128-bit load).
+//            rDPRE holds P[row] + Q[col] on entry.  On return: rM = message m, rDC1 = d loss / d (coord_mlp.0 output),
 //            rA1 = SiLU output of the first edge Linear, rDU = d loss / d (LayerNorm input), rDPRE = d loss / d (first
 //            Linear output) = the gradient of P[row] and of Q[col];  geo[13] = [radial, dist, dot, so3(9), edge_attr]
 // Outputs: dxr[3], dxc[3] (coordinate gradients of the two endpoints).
-template <class Sink>
+template <int OS, class Sink>
 EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, const float *xc, float ea,
                             const float *dagg, const float *dxo, float *rM, float *rDC1, float *rA1, float *rDU,
                             float *rDPRE, float *geo, Sink &sink, float *dxr, float *dxc) {
@@ -151,11 +153,11 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
 #pragma unroll
     for (int k = 0; k < 12; ++k) gk[k] = geo[k];
     // first edge Linear, P/Q factorised (bias folded in Q), + SiLU.  rDPRE: pq -> d silu / d pre
-#pragma unroll 1
+#pragma unroll 2
     for (int o4 = 0; o4 < 32; o4 += 4) {
         const F4 we = ld4(wea + o4);
-        float p0 = fmaf(we.x, ea, rDPRE[o4]), p1 = fmaf(we.y, ea, rDPRE[o4 + 1]), p2 = fmaf(we.z, ea, rDPRE[o4 + 2]),
-              p3 = fmaf(we.w, ea, rDPRE[o4 + 3]);
+        float p0 = fmaf(we.x, ea, rDPRE[(o4) * OS]), p1 = fmaf(we.y, ea, rDPRE[(o4 + 1) * OS]), p2 = fmaf(we.z, ea, rDPRE[(o4 + 2) * OS]),
+              p3 = fmaf(we.w, ea, rDPRE[(o4 + 3) * OS]);
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             const F4 wv = ld4(w + B_WG + 32 * k + o4);
@@ -166,7 +168,7 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
         for (int q = 0; q < 4; ++q) {
             const float sg = sigmoidf_(pr[q]);
             rA1[o4 + q] = pr[q] * sg;
-            rDPRE[o4 + q] = sg * (1.0f + pr[q] * (1.0f - sg));
+            rDPRE[(o4 + q) * OS] = sg * (1.0f + pr[q] * (1.0f - sg));
         }
     }
     // per-head second Linear (block diagonal) + LayerNorm(32), eps 1e-5, biased variance  (:245-249)
@@ -178,7 +180,7 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
     }
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd) {
-#pragma unroll 1
+#pragma unroll 2
         for (int i = 0; i < 8; ++i) {
             const float av = rA1[8 * hd + i];
             const F4 w0 = ld4(w + B_W2P + 64 * hd + 8 * i), w1 = ld4(w + B_W2P + 64 * hd + 8 * i + 4);
@@ -206,7 +208,7 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
             m[o] = fmaf(uh[o], w[B_LNG + o], w[B_LNB + o]);
             rM[o] = m[o];
         }
-#pragma unroll 1
+#pragma unroll 2
         for (int o = 0; o < 32; ++o) {
             float c0 = w[B_BC1 + o], c1 = 0.f;
 #pragma unroll
@@ -220,17 +222,17 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
             const float a2 = c * sg;
             const float wc = w[B_WC2 + o];
             s = fmaf(wc, a2, s);
-            rDU[o] = a2 * dsc;                                              // scratch: rows of the wc2 gradient
-            rDC1[o] = wc * dsc * (sg * (1.0f + c * (1.0f - sg)));
+            rDU[(o) * OS] = a2 * dsc;                                              // scratch: rows of the wc2 gradient
+            rDC1[(o) * OS] = wc * dsc * (sg * (1.0f + c * (1.0f - sg)));
         }
     }
     {
         float v[32];
 #pragma unroll
-        for (int o = 0; o < 32; ++o) v[o] = rDU[o];
+        for (int o = 0; o < 32; ++o) v[o] = rDU[(o) * OS];
         sink.template col<C_DWC2>(v);
 #pragma unroll
-        for (int o = 0; o < 32; ++o) v[o] = rDC1[o];
+        for (int o = 0; o < 32; ++o) v[o] = rDC1[(o) * OS];
         sink.template col<C_DBC1>(v);
     }
     // message gradient: from the node aggregate and from the coord MLP
@@ -239,7 +241,7 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
     for (int i = 0; i < 32; ++i) dm[i] = dagg[i];
 #pragma unroll 1
     for (int o = 0; o < 32; ++o) {
-        const float dc = rDC1[o];
+        const float dc = rDC1[(o) * OS];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             const F4 wv = ld4(w + B_WC1 + 32 * o + i);
@@ -262,20 +264,20 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
         s1 *= (1.0f / 32.0f);
         s2 *= (1.0f / 32.0f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { dm[i] = rstd * (dm[i] - s1 - uh[i] * s2); rDU[i] = dm[i]; }   // dm is now du
+        for (int i = 0; i < 32; ++i) { dm[i] = rstd * (dm[i] - s1 - uh[i] * s2); rDU[(i) * OS] = dm[i]; }   // dm is now du
     }
     sink.template col<C_DB2>(dm);
     // second Linear backward + SiLU backward.  rDPRE: d silu / d pre -> dpre
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd) {
-#pragma unroll 1
+#pragma unroll 2
         for (int i = 0; i < 8; ++i) {
             const F4 w0 = ld4(w + B_W2P + 64 * hd + 8 * i), w1 = ld4(w + B_W2P + 64 * hd + 8 * i + 4);
             const float *du = dm + 8 * hd;
             float t0 = 0.f, t1 = 0.f;
             fma2(t0, t1, w0.x, w0.y, du[0], du[1]); fma2(t0, t1, w0.z, w0.w, du[2], du[3]);
             fma2(t0, t1, w1.x, w1.y, du[4], du[5]); fma2(t0, t1, w1.z, w1.w, du[6], du[7]);
-            rDPRE[8 * hd + i] *= (t0 + t1);
+            rDPRE[(8 * hd + i) * OS] *= (t0 + t1);
         }
     }
     // geometry backward (+ the coordinate update's own use of coord_diff)
@@ -284,7 +286,7 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
     for (int k = 0; k < 12; ++k) { gg[k] = 0.f; gh[k] = 0.f; }
 #pragma unroll 1
     for (int o4 = 0; o4 < 32; o4 += 4) {
-        const float d0 = rDPRE[o4], d1 = rDPRE[o4 + 1], d2 = rDPRE[o4 + 2], d3 = rDPRE[o4 + 3];
+        const float d0 = rDPRE[(o4) * OS], d1 = rDPRE[(o4 + 1) * OS], d2 = rDPRE[(o4 + 2) * OS], d3 = rDPRE[(o4 + 3) * OS];
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             const F4 wv = ld4(w + B_WG + 32 * k + o4);

@@ -41,7 +41,7 @@ extern "C" void egcl_backward_host(const float *pack, int G, int E, const int32_
     for (int e = 0; e < E; ++e) {   // forward: messages -> agg
         const int r = row[e], c = col[e];
         for (int o = 0; o < 32; ++o) rDPRE[o] = P[(size_t)r * 32 + o] + Q[(size_t)c * 32 + o];
-        edge_backward(pack, pack + B_WEA, x + 3 * (size_t)r, x + 3 * (size_t)c, edge_attr ? edge_attr[e] : ea_const,
+        edge_backward<1>(pack, pack + B_WEA, x + 3 * (size_t)r, x + 3 * (size_t)c, edge_attr ? edge_attr[e] : ea_const,
                       zero32, zero3, rM, rDC1, rA1, rDU, rDPRE, geo, sink, dxr, dxc);
         for (int o = 0; o < 32; ++o) agg[(size_t)r * 32 + o] += rM[o];
     }
@@ -62,7 +62,7 @@ extern "C" void egcl_backward_host(const float *pack, int G, int E, const int32_
     for (int e = 0; e < E; ++e) {   // edge backward
         const int r = row[e], c = col[e];
         for (int o = 0; o < 32; ++o) rDPRE[o] = P[(size_t)r * 32 + o] + Q[(size_t)c * 32 + o];
-        edge_backward(pack, pack + B_WEA, x + 3 * (size_t)r, x + 3 * (size_t)c, edge_attr ? edge_attr[e] : ea_const,
+        edge_backward<1>(pack, pack + B_WEA, x + 3 * (size_t)r, x + 3 * (size_t)c, edge_attr ? edge_attr[e] : ea_const,
                       &dagg[(size_t)r * 32], dx_out + 3 * (size_t)r, rM, rDC1, rA1, rDU, rDPRE, geo, sink, dxr, dxc);
         for (int o = 0; o < 32; ++o) { dP[(size_t)r * 32 + o] += rDPRE[o]; dQ[(size_t)c * 32 + o] += rDPRE[o]; }
         for (int i = 0; i < 3; ++i) { dx_in[(size_t)r * 3 + i] += dxr[i]; dx_in[(size_t)c * 3 + i] += dxc[i]; }

@@ -155,3 +155,36 @@ def test_train_step_runs_and_reduces_the_loss(golden_dir):
     losses = [float(P.train.train_step(model, opt, batch)) for _ in range(8)]
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < losses[0], losses
+
+
+def test_graphed_train_step_equals_eager(golden_dir):
+    """train.GraphedTrainStep (the whole step captured as one CUDA graph) follows the eager train_step: same losses
+    over several optimizer updates (the weight packs are rebuilt inside the graph from the live parameters)."""
+    keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
+    batches = [tuple(P.synthetic.make_batch(40 + i, 2, n=512)[k].to(DEV) for k in keys) for i in range(3)]
+    ones = torch.ones(2, 512 * 16, 1, device=DEV)
+    losses = {}
+    for mode in ("eager", "graph"):
+        model = _model(golden_dir, 0.005)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+        out = []
+        if mode == "graph":
+            w0 = [p.detach().clone() for p in model.parameters()]
+            step = P.train.GraphedTrainStep(model, opt, batches[0], k=16, warmup=2)
+            with torch.no_grad():                                    # undo the warm-up / capture updates
+                for p, w in zip(model.parameters(), w0):
+                    p.copy_(w)
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            for i in range(6):
+                out.append(float(step(batches[i % 3])))
+        else:
+            for i in range(6):
+                sf, sp, tf, tp, corr, labels, gt = batches[i % 3]
+                es, et = P.knn_graph_batch(sp, 16), P.knn_graph_batch(tp, 16)
+                out.append(float(P.train.train_step(model, opt, (sf, sp, es, ones, tf, tp, et, ones, corr, labels, gt))))
+        losses[mode] = out
+    assert np.all(np.isfinite(losses["graph"]))
+    assert np.allclose(losses["eager"], losses["graph"], rtol=2e-3), losses
