@@ -317,7 +317,7 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
     with torch.no_grad():
         model.egnn.embedding_out.weight.mul_(TRAIN_TEMPER)
         model.egnn.embedding_out.bias.mul_(TRAIN_TEMPER)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5, capturable=True)     # same update rule as 3dm:1619
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, capturable=True, fused=True)     # same update rule as 3dm:1619, one launch
     B = TRAIN_PAIRS_PER_GPU
     keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
     batches = [tuple(v.to(dev) for v in (P.synthetic.make_batch(500 + rank * 4 + i, B, n=N_POINTS)[k] for k in keys)) for i in range(4)]

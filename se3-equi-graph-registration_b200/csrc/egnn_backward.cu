@@ -336,92 +336,101 @@ struct GatherArgs {
     float *dh_in, *dx_in;      // dh_in holds the node-MLP part on entry
     float *gpack;
 };
-constexpr int GB_W_LO = B_WPT, GB_W_N = 2048;
-constexpr size_t GB_SMEM = sizeof(float) * (GB_W_N + 3 * BT * RS);
+// One CTA = 1024 threads = a tile of 128 nodes, 8 lanes per node (4 features each): every node's two edge lists are
+// walked concurrently (the kernel is a chain of dependent loads per node -- id, then row -- so its time is the chain
+// length times the number of waves, not the bytes), rows move as coalesced 128-byte lines, sums in list order.
+constexpr int GT = 1024;
+constexpr size_t GB_SMEM = sizeof(float) * (2048 + 3 * BT * RS);
 
-__global__ void __launch_bounds__(BT) node_gather_backward_kernel(const GatherArgs a) {
+__global__ void __launch_bounds__(GT, 1) node_gather_backward_kernel(const GatherArgs a) {
     extern __shared__ __align__(16) float smem[];
-    float *sw = smem;
-    float *sH = smem + GB_W_N, *sDp = sH + BT * RS, *sDq = sDp + BT * RS;
-    for (int i = threadIdx.x; i < GB_W_N; i += BT) sw[i] = __ldg(a.pack + GB_W_LO + i);
-    __syncthreads();
-    float accP[8] = {0}, accQ[8] = {0};
-    float colQ = 0.f;
+    float *swT = smem;                                   // W_P and W_Q as [out][in] (transposed packs): float4 over "in"
+    float *sH = smem + 2048, *sDp = sH + BT * RS, *sDq = sDp + BT * RS;
+    for (int i = threadIdx.x; i < 2048; i += GT) {
+        const int m = i >> 10, o = (i >> 5) & 31, in = i & 31;
+        swT[i] = __ldg(a.pack + B_WPT + 1024 * m + 32 * in + o);
+    }
+    const int sub = threadIdx.x & 7, ln = threadIdx.x >> 3;          // node of the tile, 4-feature slice
+    const int ai = threadIdx.x & 31, ao = threadIdx.x >> 5;          // weight-gradient entry [in = ai][out = ao]
+    float accP = 0.f, accQ = 0.f, colQ = 0.f;
     const int64_t G = a.num_nodes;
     const int64_t tiles = (G + BT - 1) / BT;
-    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;       // phase 1: 8 lanes per node, 4 features each
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    __syncthreads();
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        // phase 1: coalesced gathers (one 128-byte dpre row per 8 lanes) -> dP, dQ rows of the tile, dx_in
-        for (int ln = grp; ln < BT; ln += BT / 8) {
-            const int64_t n = tile * BT + ln;
-            float4 dp = make_float4(0.f, 0.f, 0.f, 0.f), dq = dp;
-            float dxa = 0.f;                                           // lanes 0..2 carry x, y, z
-            if (n < G) {
-                const int64_t ebase = (n / a.n_per_cloud) * a.edges_per_cloud;
-                // eight edges per step: the group's lanes fetch the ids (one coalesced load), then all eight row loads
-                // are issued before any is used; sums stay in ascending list order
-                const unsigned gmask = 0xffu << (threadIdx.x & 24);
-                for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; p += 8) {   // edges with row == n
-                    const int mine = p + sub < pe ? __ldg(a.csr_eid + p + sub) : -1;
-                    float4 t[8];
-                    float tx[8];
+        const int64_t n = tile * BT + ln;
+        float4 dp = make_float4(0.f, 0.f, 0.f, 0.f), dq = dp, hv = dp;
+        float dxa = 0.f;                                               // lanes 0..2 carry x, y, z
+        if (n < G) {
+            const int64_t ebase = (n / a.n_per_cloud) * a.edges_per_cloud;
+            for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; p += 8) {   // edges with row == n
+                const int mine = p + sub < pe ? __ldg(a.csr_eid + p + sub) : -1;
+                float4 t[8];
+                float tx[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int ej = __shfl_sync(gmask, mine, j, 8);
-                        const int64_t ge = ebase + (ej < 0 ? 0 : ej);
-                        t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
-                        tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + sub);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { dp.x += t[j].x; dp.y += t[j].y; dp.z += t[j].z; dp.w += t[j].w; dxa += tx[j]; }
+                for (int j = 0; j < 8; ++j) {
+                    const int ej = __shfl_sync(gmask, mine, j, 8);
+                    const int64_t ge = ebase + (ej < 0 ? 0 : ej);
+                    t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
+                    tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + sub);
                 }
-                for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; p += 8) {   // edges with col == n
-                    const int mine = p + sub < pe ? __ldg(a.csc_eid + p + sub) : -1;
-                    float4 t[8];
-                    float tx[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int ej = __shfl_sync(gmask, mine, j, 8);
-                        const int64_t ge = ebase + (ej < 0 ? 0 : ej);
-                        t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
-                        tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + 4 + sub);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { dq.x += t[j].x; dq.y += t[j].y; dq.z += t[j].z; dq.w += t[j].w; dxa += tx[j]; }
-                }
-                if (sub < 3) a.dx_in[n * 3 + sub] = __ldg(a.dx_out + n * 3 + sub) + dxa;
-                const float4 hv = ldg4(a.h + n * H + 4 * sub);
-                float *rh = sH + ln * RS + 4 * sub;
-                rh[0] = hv.x; rh[1] = hv.y; rh[2] = hv.z; rh[3] = hv.w;
-            } else {
-                float *rh = sH + ln * RS + 4 * sub;
-                rh[0] = rh[1] = rh[2] = rh[3] = 0.f;
+                for (int j = 0; j < 8; ++j) { dp.x += t[j].x; dp.y += t[j].y; dp.z += t[j].z; dp.w += t[j].w; dxa += tx[j]; }
             }
-            float *rp = sDp + ln * RS + 4 * sub, *rq = sDq + ln * RS + 4 * sub;
+            for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; p += 8) {   // edges with col == n
+                const int mine = p + sub < pe ? __ldg(a.csc_eid + p + sub) : -1;
+                float4 t[8];
+                float tx[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ej = __shfl_sync(gmask, mine, j, 8);
+                    const int64_t ge = ebase + (ej < 0 ? 0 : ej);
+                    t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
+                    tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + 4 + sub);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { dq.x += t[j].x; dq.y += t[j].y; dq.z += t[j].z; dq.w += t[j].w; dxa += tx[j]; }
+            }
+            if (sub < 3) a.dx_in[n * 3 + sub] = __ldg(a.dx_out + n * 3 + sub) + dxa;
+            hv = ldg4(a.h + n * H + 4 * sub);
+        }
+        {
+            float *rh = sH + ln * RS + 4 * sub, *rp = sDp + ln * RS + 4 * sub, *rq = sDq + ln * RS + 4 * sub;
+            rh[0] = hv.x; rh[1] = hv.y; rh[2] = hv.z; rh[3] = hv.w;
             rp[0] = dp.x; rp[1] = dp.y; rp[2] = dp.z; rp[3] = dp.w;
             rq[0] = dq.x; rq[1] = dq.y; rq[2] = dq.z; rq[3] = dq.w;
         }
         __syncthreads();
-        // phase 2: thread = node: P/Q halves of the first edge Linear back to dh
-        const int64_t n = tile * BT + threadIdx.x;
-        float dq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dq[j] = sDq[threadIdx.x * RS + j];
+        // P/Q halves of the first edge Linear back to dh: this lane's 4 inputs i = 4 sub .. 4 sub + 3
         if (n < G) {
-            float dp[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dp[j] = sDp[threadIdx.x * RS + j];
-            linear32_backward_input(sw, dp, a.dh_in + n * H, true);
-            linear32_backward_input(sw + 1024, dq, a.dh_in + n * H, true);
+            float4 acc = *reinterpret_cast<const float4 *>(a.dh_in + n * H + 4 * sub);
+            const float *rp = sDp + ln * RS, *rq = sDq + ln * RS;
+#pragma unroll 4
+            for (int o = 0; o < 32; ++o) {
+                const float pv = rp[o], qv = rq[o];
+                const float4 wp = *reinterpret_cast<const float4 *>(swT + 32 * o + 4 * sub);
+                const float4 wq = *reinterpret_cast<const float4 *>(swT + 1024 + 32 * o + 4 * sub);
+                acc.x = fmaf(wp.x, pv, acc.x); acc.y = fmaf(wp.y, pv, acc.y); acc.z = fmaf(wp.z, pv, acc.z); acc.w = fmaf(wp.w, pv, acc.w);
+                acc.x = fmaf(wq.x, qv, acc.x); acc.y = fmaf(wq.y, qv, acc.y); acc.z = fmaf(wq.z, qv, acc.z); acc.w = fmaf(wq.w, qv, acc.w);
+            }
+            *reinterpret_cast<float4 *>(a.dh_in + n * H + 4 * sub) = acc;
         }
-        colQ += warp_colsum32(dq);
-        outer8(accP, sH, sDp);      // dWPT[i][o] += h[i] dP[o]
-        outer8(accQ, sH, sDq);
+        // weight gradients: dWPT[i][o] += h[i] dP[o], dWQT[i][o] += h[i] dQ[o], dbq[o] += dQ[o]; one entry per thread
+#pragma unroll 4
+        for (int e = 0; e < BT; ++e) {
+            const float hvv = sH[e * RS + ai];
+            accP = fmaf(hvv, sDp[e * RS + ao], accP);
+            accQ = fmaf(hvv, sDq[e * RS + ao], accQ);
+        }
+        if (threadIdx.x < 32) {
+#pragma unroll 4
+            for (int e = 0; e < BT; ++e) colQ += sDq[e * RS + threadIdx.x];
+        }
         __syncthreads();
     }
-    flush8(accP, a.gpack + B_WPT, true);
-    flush8(accQ, a.gpack + B_WQT, true);
-    atomicAdd(a.gpack + B_BQ + (threadIdx.x & 31), colQ);
+    atomicAdd(a.gpack + B_WPT + 32 * ai + ao, accP);
+    atomicAdd(a.gpack + B_WQT + 32 * ai + ao, accQ);
+    if (threadIdx.x < 32) atomicAdd(a.gpack + B_BQ + threadIdx.x, colQ);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -482,9 +491,9 @@ __global__ void __launch_bounds__(BT) linear32_backward_kernel(const float *__re
 }
 
 template <class K>
-static int prep_kernel(K kernel, size_t smem, int &ctas_per_sm) {
+static int prep_kernel(K kernel, size_t smem, int &ctas_per_sm, int threads = BT) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EGSPR_E_LAUNCH;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, BT, smem) != cudaSuccess || ctas_per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, threads, smem) != cudaSuccess || ctas_per_sm < 1)
         ctas_per_sm = 1;
     return EGSPR_OK;
 }
@@ -524,7 +533,7 @@ extern "C" int egspr_egcl_backward(const float *h, const float *x4, const float 
     if (!occ_node) {
         if (int e = prep_kernel(node_mlp_backward_kernel, NB_SMEM, occ_node)) return e;
         if (int e = prep_kernel(edge_backward_kernel, EB_SMEM, occ_edge)) return e;
-        if (int e = prep_kernel(node_gather_backward_kernel, GB_SMEM, occ_gather)) return e;
+        if (int e = prep_kernel(node_gather_backward_kernel, GB_SMEM, occ_gather, GT)) return e;
     }
     const int64_t ntiles = (num_nodes + BT - 1) / BT, etiles = (E + BT - 1) / BT;
     node_mlp_backward_kernel<<<grid_for(ntiles, occ_node), BT, NB_SMEM, st>>>(h, agg, dh_out, num_nodes, layer_pack, dh_in, dagg, grad_pack);
@@ -535,7 +544,7 @@ extern "C" int egspr_egcl_backward(const float *h, const float *x4, const float 
     EGSPR_CHECK_LAUNCH();
     GatherArgs ga{h, csr_ptr, csr_eid, csc_ptr, csc_eid, num_nodes, edges_per_cloud, n_per_cloud, layer_pack, dpre, dxe,
                   dx_out, dh_in, dx_in, grad_pack};
-    node_gather_backward_kernel<<<grid_for(ntiles, occ_gather), BT, GB_SMEM, st>>>(ga);
+    node_gather_backward_kernel<<<grid_for(ntiles, occ_gather), GT, GB_SMEM, st>>>(ga);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
