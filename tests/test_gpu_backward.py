@@ -188,3 +188,43 @@ def test_graphed_train_step_equals_eager(golden_dir):
         losses[mode] = out
     assert np.all(np.isfinite(losses["graph"]))
     assert np.allclose(losses["eager"], losses["graph"], rtol=2e-3), losses
+
+
+def test_backward_on_irregular_graph_hub_rows_isolated_nodes(golden_dir):
+    """EGNN.forward through all 3 layers + both embeddings on user-supplied edge lists with a 700-edge hub row (spans
+    several 128-edge tiles; its lists take many 8-edge steps in the gather kernel), nodes without any edge (empty
+    row and col lists), multi-edges, several clouds, per-edge edge_attr: every gradient vs autograd of the oracle."""
+    model = _model(golden_dir)
+    g = torch.Generator().manual_seed(5)
+    C, N = 2, 300
+    rows, cols = [], []
+    for c in range(C):
+        r = torch.cat([torch.full((700,), 7 + c, dtype=torch.int64), torch.randint(0, N // 2, (900,), generator=g),
+                       torch.full((130,), N // 2 - 1, dtype=torch.int64)])
+        cc = torch.randint(0, N - 20, (r.numel(),), generator=g)            # nodes N-20.. have no edge at all
+        perm = torch.randperm(r.numel(), generator=g)
+        rows.append(r[perm]); cols.append(cc[perm])
+    E = rows[0].numel()
+    feat = torch.randn(C, N, 32, generator=g) * 0.5
+    x = torch.rand(C, N, 3, generator=g) * 2
+    ea = torch.rand(C, E, 1, generator=g) + 0.5
+    dh = torch.randn(C, N, 32, generator=g); dx = torch.randn(C, N, 3, generator=g)
+    sd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in model.egnn.state_dict().items()}
+    f64, x64 = feat.double().requires_grad_(True), x.double().requires_grad_(True)
+    loss = 0
+    for c in range(C):
+        ho, xo = O.egnn_forward(sd, f64[c], x64[c], rows[c], cols[c], ea[c].double())
+        loss = loss + (ho * dh[c].double()).sum() + (xo * dx[c].double()).sum()
+    loss.backward()
+    for p in model.parameters():
+        p.grad = None
+    edges = torch.stack([torch.stack([rows[c], cols[c]]) for c in range(C)]).to(DEV)
+    graph = ops.csr_from_edges(edges, N)
+    fg, xg = feat.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    ho, xo = model.egnn.forward_batch(fg, xg, graph, edge_attr=ea.to(DEV), edge_attr_const=0.0)
+    ((ho * dh.to(DEV)).sum() + (xo * dx.to(DEV)).sum()).backward()
+    assert rel(fg.grad, f64.grad) < G_TOL and rel(xg.grad, x64.grad) < G_TOL, (rel(fg.grad, f64.grad), rel(xg.grad, x64.grad))
+    assert float(xg.grad[:, N - 20:].abs().max()) == float(dx[:, N - 20:].abs().max())      # isolated nodes: identity
+    for name, p in model.egnn.named_parameters():
+        assert p.grad is not None, name
+        assert rel(p.grad, sd[name].grad) < G_TOL, (name, rel(p.grad, sd[name].grad))
