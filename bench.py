@@ -347,10 +347,43 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
     barrier()
     ms = max(max_over_ranks(e0.elapsed_time(e1), dev), max_over_ranks((time.perf_counter() - t0) * 1e3, dev)) / steps
     finite = bool(torch.isfinite(loss).item())
+    cpu = cpu_train_baseline() if rank == 0 else None
     return {"workload": "BASELINE configs[3]: 3DMatch training step, fwd + bwd + Adam, 16 pairs/GPU x 2 clouds x 2048 pts, "
                         "k-NN graph build included; gradient all-reduce (one flat fp32 bucket, NCCL) when n_gpus > 1",
             "pairs_per_gpu": B, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": "pairs/s (training)",
-            "steps": steps, "loss_finite": finite, "embedding_out_scale": TRAIN_TEMPER, "launch_mode": mode}
+            "steps": steps, "loss_finite": finite, "embedding_out_scale": TRAIN_TEMPER, "launch_mode": mode, "cpu_baseline": cpu}
+
+
+def cpu_train_baseline(pairs=2, reps=2):
+    """The reference's training step on the host cores (oracle port: train-variant forward, the loop's loss,
+    torch autograd backward; no optimizer), `pairs` pairs per step -- a bounded sample of the 16-pair step."""
+    from oracle import egnn_oracle as O
+    from oracle import knn_oracle
+    import se3_equi_graph_registration_b200.synthetic as synthetic
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    knn_oracle.build()
+    sd = torch.load(CKPT, map_location="cpu", weights_only=True)["cross_attention_state_dict"]
+    sd = {k: v.clone() for k, v in sd.items()}
+    sd["egnn.embedding_out.weight"] *= TRAIN_TEMPER
+    sd["egnn.embedding_out.bias"] *= TRAIN_TEMPER
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    t_tot = 0.0
+    for r in range(reps + 1):
+        d = synthetic.make_batch(900 + r, pairs, n=N_POINTS)
+        t0 = time.perf_counter()
+        es = torch.stack([torch.stack(O.edges_from_nbr(torch.from_numpy(knn_oracle.knn(d["src_pts"][b].numpy(), K_NEIGH, threads=threads)))) for b in range(pairs)])
+        et = torch.stack([torch.stack(O.edges_from_nbr(torch.from_numpy(knn_oracle.knn(d["tgt_pts"][b].numpy(), K_NEIGH, threads=threads)))) for b in range(pairs)])
+        out = O.forward_train(sd, d["src_feat"], d["src_pts"], es, d["tgt_feat"], d["tgt_pts"], et, d["labels"], d["gt_pose"])
+        rot, trans = O.pose_loss(out[0], out[1], d["gt_pose"])
+        (out[2] + rot.mean() + trans.mean()).backward()
+        for v in sd.values():
+            if v.is_floating_point():
+                v.grad = None
+        if r > 0:
+            t_tot += time.perf_counter() - t0
+    return {"value": pairs * reps / t_tot, "unit": "pairs/s (training)", "cores": threads, "kind": "port",
+            "sample": f"{reps} steps of {pairs} pairs (of the 16-pair step), forward + loss + autograd backward, k-NN included, no optimizer"}
 
 
 def eng_layer_time(eng, reps=20):

@@ -210,13 +210,14 @@ EGSPR_HD void edge_backward(const float *w, const float *wea, const float *xr, c
         }
 #pragma unroll 2
         for (int o = 0; o < 32; ++o) {
-            float c0 = w[B_BC1 + o], c1 = 0.f;
+            float c0 = w[B_BC1 + o], c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;   // 4 independent FFMA2 chains
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
                 const F4 w0 = ld4(w + B_WC1 + 32 * o + i), w1 = ld4(w + B_WC1 + 32 * o + i + 4);
-                fma2(c0, c1, w0.x, w0.y, m[i], m[i + 1]); fma2(c0, c1, w0.z, w0.w, m[i + 2], m[i + 3]);
-                fma2(c0, c1, w1.x, w1.y, m[i + 4], m[i + 5]); fma2(c0, c1, w1.z, w1.w, m[i + 6], m[i + 7]);
+                fma2(c0, c1, w0.x, w0.y, m[i], m[i + 1]); fma2(c2, c3, w0.z, w0.w, m[i + 2], m[i + 3]);
+                fma2(c4, c5, w1.x, w1.y, m[i + 4], m[i + 5]); fma2(c6, c7, w1.z, w1.w, m[i + 6], m[i + 7]);
             }
+            c0 += c2; c1 += c3; c4 += c6; c5 += c7; c0 += c4; c1 += c5;
             const float c = c0 + c1;
             const float sg = sigmoidf_(c);
             const float a2 = c * sg;
