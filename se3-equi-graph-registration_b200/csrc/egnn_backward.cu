@@ -180,9 +180,11 @@ struct EdgeBwdArgs {
 };
 
 constexpr int EB_W_N = EDGE_PART + 32;     // edge part of the pack + the edge_attr column
-// shared memory: weights | M, A1 edge-major [BT][RS] | DC1, DU, DPRE feature-major [32][BT] | geo [BT][16 (13 used)]
+// shared memory: weights | M, A1 edge-major [BT][RS] | DC1, DU, DPRE feature-major [32][OS] | geo [BT][GS (13 used)]
 constexpr int GS = 17;                     // geo row stride (odd: conflict-free own-row writes)
-constexpr size_t EB_SMEM = sizeof(float) * (EB_W_N + 2 * BT * RS + 3 * 32 * BT + BT * GS);
+constexpr int OS = BT + 4;                 // feature-major row stride: 16-byte aligned rows, and rows o, o+2, o+4, o+6 (or o, o+4) that one
+                                           // 128-bit load instruction touches start 8 (16) banks apart
+constexpr size_t EB_SMEM = sizeof(float) * (EB_W_N + 2 * BT * RS + 3 * 32 * OS + BT * GS);
 
 struct DevSink {
     float colacc[C_COUNT];
@@ -198,8 +200,8 @@ __global__ void __launch_bounds__(BT, 2) edge_backward_kernel(const EdgeBwdArgs 
     extern __shared__ __align__(16) float smem[];
     float *sw = smem;                          // [0,1824) edge part, [1824,1856) edge_attr column
     float *sM = smem + EB_W_N, *sA1 = sM + BT * RS;                              // "in" rows of the outer products
-    float *sDC1 = sA1 + BT * RS, *sDU = sDC1 + 32 * BT, *sDPRE = sDU + 32 * BT;  // "out" rows, feature-major
-    float *sGeo = sDPRE + 32 * BT;
+    float *sDC1 = sA1 + BT * RS, *sDU = sDC1 + 32 * OS, *sDPRE = sDU + 32 * OS;  // "out" rows, feature-major
+    float *sGeo = sDPRE + 32 * OS;
     for (int i = threadIdx.x; i < EDGE_PART; i += BT) sw[i] = __ldg(a.pack + i);
     if (threadIdx.x < 32) sw[EDGE_PART + threadIdx.x] = __ldg(a.pack + B_WEA + threadIdx.x);
     __syncthreads();
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(BT, 2) edge_backward_kernel(const EdgeBwdArgs 
             load_row32g(pq, a.P + (int64_t)r * H);
             add_row32g(pq, a.Q + (int64_t)c * H);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rDPRE[j * BT] = pq[j];
+            for (int j = 0; j < 32; ++j) rDPRE[j * OS] = pq[j];
         }
         float dagg[32], dxo[3];
         if (valid) {
@@ -245,11 +247,11 @@ __global__ void __launch_bounds__(BT, 2) edge_backward_kernel(const EdgeBwdArgs 
             dxo[0] = dxo[1] = dxo[2] = 0.f;
         }
         float dxr[3], dxc[3];
-        edge_backward<BT>(sw, sw + EDGE_PART, xr, xc, ea, dagg, dxo, rM, rDC1, rA1, rDU, rDPRE, rGeo, sink, dxr, dxc);
+        edge_backward<OS>(sw, sw + EDGE_PART, xr, xc, ea, dagg, dxo, rM, rDC1, rA1, rDU, rDPRE, rGeo, sink, dxr, dxc);
         if (valid) {
             float dpre[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dpre[j] = rDPRE[j * BT];
+            for (int j = 0; j < 32; ++j) dpre[j] = rDPRE[j * OS];
             store_row32g(a.dpre + ge * H, dpre);
             *reinterpret_cast<float4 *>(a.dxe + ge * 8) = make_float4(dxr[0], dxr[1], dxr[2], 0.f);
             *reinterpret_cast<float4 *>(a.dxe + ge * 8 + 4) = make_float4(dxc[0], dxc[1], dxc[2], 0.f);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(BT, 2) edge_backward_kernel(const EdgeBwdArgs 
                 const float m0 = in[e * RS], m1 = in[(e + 1) * RS], m2 = in[(e + 2) * RS], m3 = in[(e + 3) * RS];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float4 ov = *reinterpret_cast<const float4 *>(sDC1 + (ob + q) * BT + e);
+                    const float4 ov = *reinterpret_cast<const float4 *>(sDC1 + (ob + q) * OS + e);
                     fma2(accWc1[2 * q], accWc1[2 * q + 1], m0, m1, ov.x, ov.y);
                     fma2(accWc1[2 * q], accWc1[2 * q + 1], m2, m3, ov.z, ov.w);
                 }
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(BT, 2) edge_backward_kernel(const EdgeBwdArgs 
         {
             const int idx = 2 * tid, hb = (idx >> 6) * 8, ii = (idx >> 3) & 7, oo = idx & 7;   // dW2P[hd][i][o] += a1 du
             const float *in = sA1 + hb + ii;
-            const float *o0 = sDU + (hb + oo) * BT, *o1 = o0 + BT;
+            const float *o0 = sDU + (hb + oo) * OS, *o1 = o0 + OS;
 #pragma unroll 2
             for (int e = 0; e < BT; e += 4) {
                 const float a0 = in[e * RS], a1 = in[(e + 1) * RS], a2 = in[(e + 2) * RS], a3 = in[(e + 3) * RS];
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(BT, 2) edge_backward_kernel(const EdgeBwdArgs 
                     const float g0 = in[e * GS], g1 = in[(e + 1) * GS], g2 = in[(e + 2) * GS], g3 = in[(e + 3) * GS];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 ov = *reinterpret_cast<const float4 *>(sDPRE + (ob + q) * BT + e);
+                        const float4 ov = *reinterpret_cast<const float4 *>(sDPRE + (ob + q) * OS + e);
                         fma2(accWg[2 * q], accWg[2 * q + 1], g0, g1, ov.x, ov.y);
                         fma2(accWg[2 * q], accWg[2 * q + 1], g2, g3, ov.z, ov.w);
                     }
