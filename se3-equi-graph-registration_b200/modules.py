@@ -228,6 +228,16 @@ def pose_loss(pred_rot, pred_translation, gt_pose, delta=1.5):
     return rl, torch.arccos(torch.clamp(cos, min=-1, max=1))
 
 
+def compute_losses(rot, translation, h_src_norm, x_src, h_tgt_norm, x_tgt, gt_labels):
+    """3dm:799-858 (logged by the training loop, 3dm:1094): mean inlier point error under the predicted pose and the
+    mean feature distance over the inliers -> (point_error, feature_loss)."""
+    xs = torch.matmul(rot, x_src.transpose(1, 2)).transpose(1, 2) + translation.unsqueeze(1)
+    dist = torch.norm(xs - x_tgt, dim=-1) * gt_labels
+    per_pair = dist.sum(dim=1) / torch.clamp(gt_labels.sum(dim=1), min=1)
+    sel = gt_labels == 1
+    return per_pair.mean(), torch.norm(h_src_norm[sel] - h_tgt_norm[sel], dim=-1).mean()
+
+
 # ---------------------------------------------------------------------------------------------
 # CrossAttentionPoseRegression
 # ---------------------------------------------------------------------------------------------

@@ -205,3 +205,21 @@ def test_gradient_allreduce_two_ranks_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_compute_losses_matches_reference():
+    """modules.compute_losses == the reference's compute_losses (3dm:799-858) when /root/reference is present,
+    else against a direct restatement."""
+    from oracle import ref_loader
+    g = torch.Generator().manual_seed(0)
+    R = torch.linalg.qr(torch.randn(3, 3, 3, generator=g))[0]; t = torch.randn(3, 3, generator=g)
+    hs, ht = torch.randn(3, 50, 32, generator=g), torch.randn(3, 50, 32, generator=g)
+    xs, xt = torch.randn(3, 50, 3, generator=g), torch.randn(3, 50, 3, generator=g)
+    lab = (torch.rand(3, 50, generator=g) < 0.6).float(); lab[2] = 0
+    got = P.compute_losses(R, t, hs, xs, ht, xt, lab)
+    if ref_loader.reference_available():
+        want = ref_loader.load("train")["compute_losses"](R, t, hs, xs, ht, xt, lab)
+    else:
+        d = (torch.einsum("bij,bnj->bni", R, xs) + t[:, None] - xt).norm(dim=-1) * lab
+        want = ((d.sum(1) / lab.sum(1).clamp(min=1)).mean(), (hs[lab == 1] - ht[lab == 1]).norm(dim=-1).mean())
+    assert torch.allclose(got[0], want[0]) and torch.allclose(got[1], want[1])
