@@ -14,6 +14,13 @@ def _unpacker(module, fn, floats):
     return u
 
 
+def _linear_pack(lin):
+    c = lin.__dict__.get("_egspr_pack_cache")
+    if c is None:
+        c = lin.__dict__["_egspr_pack_cache"] = packing.PackCache(lambda: list(lin.parameters()), lambda: packing.pack_linear32(lin))
+    return c.get()
+
+
 def egnn_param_list(egnn_or_layers, embedding_in=None, embedding_out=None):
     """Flat parameter list in the order EGNNFunction returns gradients:
     [embedding_in.weight, .bias]? + [embedding_out.weight, .bias]? + every layer's parameters()."""
@@ -34,8 +41,8 @@ class EGNNFunction(torch.autograd.Function):
     def forward(ctx, spec, feat, x, *params):
         layers, emb_in, emb_out, graph, edge_attr, edge_attr_const = spec
         layer_packs = [g.layer_pack() for g in layers]
-        pin = packing.pack_linear32(emb_in) if emb_in is not None else None
-        pout = packing.pack_linear32(emb_out) if emb_out is not None else None
+        pin = _linear_pack(emb_in) if emb_in is not None else None
+        pout = _linear_pack(emb_out) if emb_out is not None else None
         h_out, x_out, saved = ops.egnn_forward_saved(feat, x, graph, layer_packs, pin, pout, edge_attr=edge_attr,
                                                      edge_attr_const=edge_attr_const)
         ctx.spec = spec

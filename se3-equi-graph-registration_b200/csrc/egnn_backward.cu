@@ -342,19 +342,21 @@ struct GatherArgs {
 // walked concurrently (the kernel is a chain of dependent loads per node -- id, then row -- so its time is the chain
 // length times the number of waves, not the bytes), rows move as coalesced 128-byte lines, sums in list order.
 constexpr int GT = 1024;
-constexpr size_t GB_SMEM = sizeof(float) * (2048 + 3 * BT * RS);
+constexpr int GOS = BT + 4;          // feature-major row stride of the dP / dQ tiles (as OS in the edge kernel)
+constexpr size_t GB_SMEM = sizeof(float) * (2048 + BT * RS + 2 * 32 * GOS);
 
 __global__ void __launch_bounds__(GT, 1) node_gather_backward_kernel(const GatherArgs a) {
     extern __shared__ __align__(16) float smem[];
     float *swT = smem;                                   // W_P and W_Q as [out][in] (transposed packs): float4 over "in"
-    float *sH = smem + 2048, *sDp = sH + BT * RS, *sDq = sDp + BT * RS;
+    float *sH = smem + 2048;                             // h rows, node-major [BT][RS]
+    float *sDp = sH + BT * RS, *sDq = sDp + 32 * GOS;    // dP, dQ feature-major [32][GOS]: four nodes per 128-bit load
     for (int i = threadIdx.x; i < 2048; i += GT) {
         const int m = i >> 10, o = (i >> 5) & 31, in = i & 31;
         swT[i] = __ldg(a.pack + B_WPT + 1024 * m + 32 * in + o);
     }
     const int sub = threadIdx.x & 7, ln = threadIdx.x >> 3;          // node of the tile, 4-feature slice
     const int ai = threadIdx.x & 31, ao = threadIdx.x >> 5;          // weight-gradient entry [in = ai][out = ao]
-    float accP = 0.f, accQ = 0.f, colQ = 0.f;
+    float accP0 = 0.f, accP1 = 0.f, accQ0 = 0.f, accQ1 = 0.f, colQ = 0.f;
     const int64_t G = a.num_nodes;
     const int64_t tiles = (G + BT - 1) / BT;
     const unsigned gmask = 0xffu << (threadIdx.x & 24);
@@ -397,19 +399,19 @@ __global__ void __launch_bounds__(GT, 1) node_gather_backward_kernel(const Gathe
             hv = ldg4(a.h + n * H + 4 * sub);
         }
         {
-            float *rh = sH + ln * RS + 4 * sub, *rp = sDp + ln * RS + 4 * sub, *rq = sDq + ln * RS + 4 * sub;
+            float *rh = sH + ln * RS + 4 * sub, *rp = sDp + (4 * sub) * GOS + ln, *rq = sDq + (4 * sub) * GOS + ln;
             rh[0] = hv.x; rh[1] = hv.y; rh[2] = hv.z; rh[3] = hv.w;
-            rp[0] = dp.x; rp[1] = dp.y; rp[2] = dp.z; rp[3] = dp.w;
-            rq[0] = dq.x; rq[1] = dq.y; rq[2] = dq.z; rq[3] = dq.w;
+            rp[0] = dp.x; rp[GOS] = dp.y; rp[2 * GOS] = dp.z; rp[3 * GOS] = dp.w;
+            rq[0] = dq.x; rq[GOS] = dq.y; rq[2 * GOS] = dq.z; rq[3 * GOS] = dq.w;
         }
         __syncthreads();
         // P/Q halves of the first edge Linear back to dh: this lane's 4 inputs i = 4 sub .. 4 sub + 3
         if (n < G) {
             float4 acc = *reinterpret_cast<const float4 *>(a.dh_in + n * H + 4 * sub);
-            const float *rp = sDp + ln * RS, *rq = sDq + ln * RS;
+            const float *rp = sDp + ln, *rq = sDq + ln;
 #pragma unroll 4
             for (int o = 0; o < 32; ++o) {
-                const float pv = rp[o], qv = rq[o];
+                const float pv = rp[o * GOS], qv = rq[o * GOS];
                 const float4 wp = *reinterpret_cast<const float4 *>(swT + 32 * o + 4 * sub);
                 const float4 wq = *reinterpret_cast<const float4 *>(swT + 1024 + 32 * o + 4 * sub);
                 acc.x = fmaf(wp.x, pv, acc.x); acc.y = fmaf(wp.y, pv, acc.y); acc.z = fmaf(wp.z, pv, acc.z); acc.w = fmaf(wp.w, pv, acc.w);
@@ -417,21 +419,30 @@ __global__ void __launch_bounds__(GT, 1) node_gather_backward_kernel(const Gathe
             }
             *reinterpret_cast<float4 *>(a.dh_in + n * H + 4 * sub) = acc;
         }
-        // weight gradients: dWPT[i][o] += h[i] dP[o], dWQT[i][o] += h[i] dQ[o], dbq[o] += dQ[o]; one entry per thread
-#pragma unroll 4
-        for (int e = 0; e < BT; ++e) {
-            const float hvv = sH[e * RS + ai];
-            accP = fmaf(hvv, sDp[e * RS + ao], accP);
-            accQ = fmaf(hvv, sDq[e * RS + ao], accQ);
+        // weight gradients: dWPT[i][o] += h[i] dP[o], dWQT[i][o] += h[i] dQ[o], dbq[o] += dQ[o]; one entry per thread,
+        // four nodes per 128-bit load of the dP / dQ rows (broadcast: `ao` is the warp index)
+        {
+            const float *in = sH + ai, *op = sDp + ao * GOS, *oq = sDq + ao * GOS;
+#pragma unroll 2
+            for (int e = 0; e < BT; e += 4) {
+                const float h0 = in[e * RS], h1 = in[(e + 1) * RS], h2 = in[(e + 2) * RS], h3 = in[(e + 3) * RS];
+                const float4 pv = *reinterpret_cast<const float4 *>(op + e), qv = *reinterpret_cast<const float4 *>(oq + e);
+                fma2(accP0, accP1, h0, h1, pv.x, pv.y); fma2(accP0, accP1, h2, h3, pv.z, pv.w);
+                fma2(accQ0, accQ1, h0, h1, qv.x, qv.y); fma2(accQ0, accQ1, h2, h3, qv.z, qv.w);
+            }
         }
         if (threadIdx.x < 32) {
+            const float *oq = sDq + threadIdx.x * GOS;
 #pragma unroll 4
-            for (int e = 0; e < BT; ++e) colQ += sDq[e * RS + threadIdx.x];
+            for (int e = 0; e < BT; e += 4) {
+                const float4 qv = *reinterpret_cast<const float4 *>(oq + e);
+                colQ += (qv.x + qv.y) + (qv.z + qv.w);
+            }
         }
         __syncthreads();
     }
-    atomicAdd(a.gpack + B_WPT + 32 * ai + ao, accP);
-    atomicAdd(a.gpack + B_WQT + 32 * ai + ao, accQ);
+    atomicAdd(a.gpack + B_WPT + 32 * ai + ao, accP0 + accP1);
+    atomicAdd(a.gpack + B_WQT + 32 * ai + ao, accQ0 + accQ1);
     if (threadIdx.x < 32) atomicAdd(a.gpack + B_BQ + threadIdx.x, colQ);
 }
 

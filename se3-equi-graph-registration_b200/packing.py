@@ -81,19 +81,49 @@ def pack_head(mlp):
 
 
 class PackCache:
-    """Rebuilds a pack only when one of the source parameters changed (data_ptr or _version)."""
+    """Rebuilds a pack only when one of the source parameters changed (data_ptr or _version).
+
+    The re-layout is a fixed permutation of the parameters' elements (plus zero padding), so after the first build
+    its index map is known (the build function is run once more on a copy of the parameters holding their own
+    element numbers) and every later rebuild -- one per optimizer step in training -- is `cat(params)[index]`:
+    two kernels instead of ~25 slice copies."""
 
     def __init__(self, params_fn, build_fn):
         self._params_fn = params_fn
         self._build_fn = build_fn
         self._key = None
         self._val = None
+        self._index = None      # (device, LongTensor [pack]) into cat([0], params...)
+
+    def _make_index(self, params):
+        saved = [p.data for p in params]
+        off = 1                                              # element 0 of the gather source is the constant 0
+        try:
+            for p in params:
+                p.data = torch.arange(off, off + p.numel(), dtype=torch.float32, device=p.device).view_as(p)
+                off += p.numel()
+            idx = self._build_fn()
+        finally:
+            for p, d in zip(params, saved):
+                p.data = d
+        if off >= 1 << 24:
+            return None                                      # element numbers no longer exact in fp32
+        return idx.round().to(torch.int64)
 
     def get(self):
-        key = tuple((p.data_ptr(), p._version, p.device) for p in self._params_fn())
+        params = list(self._params_fn())
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
         if key != self._key:
             with torch.no_grad():
-                self._val = self._build_fn()
+                dev = params[0].device
+                if self._index is None or self._index[0] != dev:
+                    self._index = (dev, self._make_index(params))
+                if self._index[1] is None:
+                    self._val = self._build_fn()
+                else:
+                    src = torch.cat([torch.zeros(1, dtype=torch.float32, device=dev)] +
+                                    [p.detach().reshape(-1).to(torch.float32) for p in params])
+                    self._val = src[self._index[1]]
             self._key = key
         return self._val
 
