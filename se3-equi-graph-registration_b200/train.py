@@ -70,15 +70,14 @@ class GraphedTrainStep:
     static buffers; the weight packs are rebuilt from the live parameters inside the graph, so optimizer updates are
     seen by the next replay.  The optimizer must be built with capturable=True (torch.optim.Adam(..., capturable=True)).
 
-    batch = (src_feat, src_pts, tgt_feat, tgt_pts, corr, labels, gt_pose); the k-NN graphs and the ones edge_attr
-    (3dm:1003-1089) are built inside the step."""
+    batch = (src_feat, src_pts, tgt_feat, tgt_pts, corr, labels, gt_pose); the k-NN graphs (3dm:1003-1089) are built
+    inside the step; edge_attr is passed as None = the reference's all-ones (get_edges_batch, 3dm:387) without a
+    per-edge gather."""
 
     def __init__(self, model, optimizer, example_batch, k=16, group=None, warmup=3):
         from . import modules
         self.model, self.opt, self.k, self.group = model, optimizer, k, group
         self.static = [t.clone() for t in example_batch]
-        B, N = self.static[1].shape[:2]
-        self.ones = torch.ones(B, N * k, 1, device=self.static[1].device)
         self._knn = modules.knn_graph_batch
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -97,7 +96,7 @@ class GraphedTrainStep:
         es, et = self._knn(sp, self.k), self._knn(tp, self.k)
         self.model.train()
         self.opt.zero_grad(set_to_none=True)
-        out = self.model(sf, sp, es, self.ones, tf, tp, et, self.ones, corr, labels, gt)
+        out = self.model(sf, sp, es, None, tf, tp, et, None, corr, labels, gt)
         loss = training_loss(out, gt)
         loss.backward()
         allreduce_gradients(self.model.parameters(), group=self.group)

@@ -145,6 +145,24 @@ def test_training_step_gradients_match_reference_golden(golden_dir, scenario):
     print(f"{scenario}: worst relative-to-max gradient error {worst:.2e}")
 
 
+def test_edge_attr_none_equals_ones(golden_dir):
+    """edge_attr=None (constant 1 folded into the kernels) gives the same loss and gradients as the reference's explicit
+    ones tensor (get_edges_batch, 3dm:387), which goes through the per-edge gather."""
+    g = torch.load(os.path.join(golden_dir, "small_b2_n256.pt"), weights_only=False, map_location="cpu")
+    inp = {k: v.to(DEV) for k, v in g["inputs"].items()}
+    es, et = edges_of(g["nbr_src"]).to(DEV), edges_of(g["nbr_tgt"]).to(DEV)
+    grads = []
+    for ea in (None, torch.ones(es.shape[0], es.shape[-1], 1, device=DEV)):
+        model = _model(golden_dir, 0.005)
+        model.train()
+        out = model(inp["src_feat"], inp["src_pts"], es, ea, inp["tgt_feat"], inp["tgt_pts"], et, ea, inp["corr"], inp["labels"], inp["gt_pose"])
+        P.train.training_loss(out, inp["gt_pose"]).backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) == 85
+    for k in grads[0]:
+        assert rel(grads[0][k], grads[1][k]) < 1e-5, k
+
+
 def test_train_step_runs_and_reduces_the_loss(golden_dir):
     """train.train_step (3dm:1092-1126) with Adam on a fixed batch: finite gradients, loss goes down, packs follow
     the parameter updates."""
