@@ -64,7 +64,6 @@ class EGNNFunction(torch.autograd.Function):
             grads += _unpacker(emb_out, packing.unpack_linear32_grad, packing.EMBED_PACK)(g_out)
         for gcl, gp in zip(layers, gpacks):
             grads += _unpacker(gcl, packing.unpack_layer_grad, packing.LAYER_PACK)(gp)
-        ctx.saved = None
         return (None, dfeat if need_dfeat else None, dx, *grads)
 
 
