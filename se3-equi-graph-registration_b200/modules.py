@@ -62,6 +62,18 @@ def get_edges_batch(graph_idx, n_nodes, batch_size):
     return [torch.cat(rows), torch.cat(cols)], edge_attr
 
 
+def get_edges_from_idx(graph_idx):
+    """3dm:372-378: [2,E] graph index -> [src, dst]."""
+    return [graph_idx[0], graph_idx[1]]
+
+
+def unsorted_segment_mean(data, segment_ids, num_segments):
+    """3dm:351-358 (the commented-out mean variant of coord_model, 3dm:266): segment sums / max(count, 1)."""
+    s = unsorted_segment_sum(data, segment_ids, num_segments)
+    cnt = torch.bincount(segment_ids, minlength=num_segments).clamp(min=1).to(s.dtype)
+    return s / cnt[:, None]
+
+
 def unsorted_segment_sum(data, segment_ids, num_segments):
     """3dm:343-348, deterministic (ascending edge order) instead of atomics."""
     import ctypes
@@ -341,29 +353,36 @@ class CrossAttentionPoseRegression(nn.Module):
 # ---------------------------------------------------------------------------------------------
 # checkpoints (3dm:1310-1395)
 # ---------------------------------------------------------------------------------------------
-def save_checkpoint(save_dir, epoch, egnn, cross_attention, optimizer=None, pointnet=None, best=False):
+def save_checkpoint(epoch, pointnet, egnn, cross_attention, optimizer, save_dir="./checkpoints2", is_best=False, use_pointnet=False):
+    """Same signature, dict layout and file names as 3dm:1310-1349: `model_epoch_{epoch}.pth` (+ `best_checkpoint` when
+    is_best) holding epoch / egnn_state_dict / cross_attention_state_dict / optimizer_state_dict (/ pointnet_state_dict).
+    Returns the path written (the reference returns None)."""
     os.makedirs(save_dir, exist_ok=True)
     ck = {"epoch": epoch, "egnn_state_dict": egnn.state_dict(),
           "cross_attention_state_dict": cross_attention.state_dict()}
     if optimizer is not None:
         ck["optimizer_state_dict"] = optimizer.state_dict()
-    if pointnet is not None:
+    if use_pointnet and pointnet is not None:
         ck["pointnet_state_dict"] = pointnet.state_dict()
-    path = os.path.join(save_dir, "best_checkpoint.pth" if best else f"model_epoch_{epoch}.pth")
+    path = os.path.join(save_dir, f"model_epoch_{epoch}.pth")
     torch.save(ck, path)
+    if is_best:
+        torch.save(ck, os.path.join(save_dir, "best_checkpoint"))
     return path
 
 
-def load_checkpoint(checkpoint_path, pointnet, egnn, cross_attention, optimizer=None, use_pointnet=False, device='cuda:0'):
-    """Same contract as 3dm:1351-1395: strict load of 'egnn_state_dict' and
-    'cross_attention_state_dict' (+ optional pointnet / optimizer); returns (checkpoint, epoch)."""
-    if not os.path.isfile(checkpoint_path):
-        raise FileNotFoundError(f"Checkpoint file not found at: {checkpoint_path}")
+def load_checkpoint(checkpoint_path, pointnet=None, egnn=None, cross_attention=None, optimizer=None, use_pointnet=False, device='cuda:0'):
+    """Same contract as 3dm:1351-1395: strict load of 'egnn_state_dict' and 'cross_attention_state_dict' (+ optional
+    pointnet / optimizer) for the modules that are given; returns (checkpoint, epoch)."""
+    if not os.path.exists(checkpoint_path):
+        raise FileNotFoundError(f"Checkpoint file {checkpoint_path} not found.")
     ck = torch.load(checkpoint_path, map_location=device, weights_only=True)
-    egnn.load_state_dict(ck["egnn_state_dict"])
-    cross_attention.load_state_dict(ck["cross_attention_state_dict"])
     if use_pointnet and pointnet is not None and "pointnet_state_dict" in ck:
         pointnet.load_state_dict(ck["pointnet_state_dict"])
+    if egnn is not None and "egnn_state_dict" in ck:
+        egnn.load_state_dict(ck["egnn_state_dict"])
+    if cross_attention is not None and "cross_attention_state_dict" in ck:
+        cross_attention.load_state_dict(ck["cross_attention_state_dict"])
     if optimizer is not None and "optimizer_state_dict" in ck:
         optimizer.load_state_dict(ck["optimizer_state_dict"])
     return ck, ck.get("epoch", 0)

@@ -57,7 +57,8 @@ def test_checkpoint_loads_unchanged(golden_dir, ck):
 
 def test_checkpoint_round_trip(tmp_path, golden_dir):
     model = P.build_model(os.path.join(golden_dir, "checkpoint-3dmatch.pth"), device="cpu")
-    path = P.save_checkpoint(str(tmp_path), 3, model.egnn, model, torch.optim.Adam(model.parameters()))
+    path = P.save_checkpoint(3, None, model.egnn, model, torch.optim.Adam(model.parameters()), save_dir=str(tmp_path), is_best=True)   # 3dm:1310 signature
+    assert os.path.exists(os.path.join(str(tmp_path), "best_checkpoint"))
     m2 = P.build_model(None, device="cpu")
     _, ep = P.load_checkpoint(path, None, m2.egnn, m2, device="cpu")
     assert ep == 3
