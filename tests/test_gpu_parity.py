@@ -282,6 +282,24 @@ def test_forward_train_variant(golden_dir):
             assert abs(float(torch.det(out[0][b].cpu().double())) - 1.0) < 1e-4
 
 
+def test_forward_train_variant_kitti_top_k(golden_dir):
+    """kit:616-766 is the train-variant body with top_k = 2048 (= every point at the KITTI loader's size): here
+    top_k = N on the 256-point fixture -- slot 2 (BCE over ALL points + similarity loss) against the oracle."""
+    g, ck = load_case(golden_dir, "small_b2_n256")
+    model = P.build_model(ck, device=DEV, variant="train")
+    model.top_k = 256
+    inp = {k: v.to(DEV) for k, v in g["inputs"].items()}
+    es, et = P.knn_graph_batch(inp["src_pts"], 16), P.knn_graph_batch(inp["tgt_pts"], 16)
+    with torch.no_grad():
+        out = model(inp["src_feat"], inp["src_pts"], es, None, inp["tgt_feat"], inp["tgt_pts"], et, None,
+                    inp["corr"], inp["labels"], inp["gt_pose"])
+    sd = torch.load(ck, map_location="cpu", weights_only=True)["cross_attention_state_dict"]
+    ref = O.forward_train(sd, g["inputs"]["src_feat"], g["inputs"]["src_pts"], es.cpu(), g["inputs"]["tgt_feat"],
+                          g["inputs"]["tgt_pts"], et.cpu(), g["inputs"]["labels"], g["inputs"]["gt_pose"], top_k=256)
+    assert abs(float(out[2]) - float(ref[2])) <= 2e-4 * abs(float(ref[2]))
+    assert abs(float(out[3]) - float(ref[3])) <= 1e-4 * abs(float(ref[3]))
+
+
 # ---------------------------------------------------------------------------------------------
 # Kabsch (a15)
 # ---------------------------------------------------------------------------------------------
