@@ -65,7 +65,6 @@ class RegistrationEngine:
         self._graph_key = [None, None]
         self.impl = 0
         self.launches_per_step = 0
-        self._side = None
 
     def _bind_inputs(self, s):
         self._set = s
@@ -94,16 +93,6 @@ class RegistrationEngine:
         head = self.model._pack_head.get()
         st = ops._stream()
         n_launch = 0
-        # fork: embedding_in + layer-0 P/Q (need only the features / coordinates) run on a side stream beside the graph
-        # construction (k-NN build + query, CSR transpose); joined before the first layer.  Captured as two branches
-        # of the CUDA graph.
-        main = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            _lib.check(lib.egspr_node_embed(p(self.feat), p(self.x), G, p(pin), p(layers[0]), p(self.h[0]), p(self.x4[0]),
-                                            p(self.P[0]), p(self.Q[0]), ops._stream()), "egspr_node_embed"); n_launch += 1
         if self.knn_brute_force:
             _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), None, 0, st), "egspr_knn_build"); n_launch += 1
         else:
@@ -113,7 +102,8 @@ class RegistrationEngine:
                                           p(self.csr_eid), p(self.ws), self.ws_bytes, p(self.err), st), "egspr_csr_from_nbr")
         # csr: one fused launch for small clouds (csr.cu: shared-memory build), else count/scan/fill/emit
         n_launch += 1 if (4 * (2 * N + 1 + N * k) <= 200 * 1024 and C >= 16) else 4
-        main.wait_stream(self._side)
+        _lib.check(lib.egspr_node_embed(p(self.feat), p(self.x), G, p(pin), p(layers[0]), p(self.h[0]), p(self.x4[0]),
+                                        p(self.P[0]), p(self.Q[0]), st), "egspr_node_embed"); n_launch += 1
         cur = 0
         L = len(layers)
         for i in range(L):
