@@ -203,6 +203,13 @@ int egspr_head_train_backward(const float *h_out_src, const float *h_out_tgt, co
                               const float *dsim, int pairs, int n, float *dh_src, float *dh_tgt,
                               float *dx_src, float *dx_tgt, void *stream);
 
+/* ---- a16: pose_loss(pred_rot, pred_translation, gt_pose) 3dm:896-962 (the two returned losses): per pair
+ * rot_loss = acos(clamp((trace(R^T R_gt) - 1) / 2, -1, 1)), trans_loss = acos(clamp(cos(t, t_gt), -1, 1)), and
+ * (optional) their gradients grad_R [pairs][9] = d rot_loss / d R, grad_t [pairs][3] = d trans_loss / d t, so that
+ * the backward pass is one multiply by the upstream gradient.  R [pairs][9], t [pairs][3], gt_pose [pairs][16]. */
+int egspr_pose_loss(const float *R, const float *t, const float *gt_pose, int pairs, float *rot_loss,
+                    float *trans_loss, float *grad_R, float *grad_t, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

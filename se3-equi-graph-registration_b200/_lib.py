@@ -45,6 +45,7 @@ SIGNATURES = {
     "egspr_linear32_forward": (_i, [_p, _l, _p, _p, _p]),
     "egspr_linear32_backward": (_i, [_p, _p, _l, _p, _p, _p, _p]),
     "egspr_head_train_backward": (_i, [_p] * 8 + [_i, _i] + [_p] * 5),
+    "egspr_pose_loss": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p]),
 }
 
 

@@ -88,3 +88,21 @@ class HeadTrainFunction(torch.autograd.Function):
             dt = torch.zeros((B, 3), dtype=torch.float32, device=hs.device)
         dhs, dht, dxs, dxt = ops.head_train_backward(hs, ht, xs, xt, labels_f, dR, dt, dsim)
         return dhs, dht, dxs, dxt, None, None
+
+
+class PoseLossFunction(torch.autograd.Function):
+    """pose_loss (3dm:896-962) as one kernel: (R, t, gt_pose) -> (rot_loss [B], trans_loss [B]); the kernel also
+    returns the two local gradients, so backward is a broadcast multiply."""
+
+    @staticmethod
+    def forward(ctx, R, t, gt_pose):
+        rl, tl, gR, gt = ops.pose_loss(R, t, gt_pose, need_grad=True)
+        ctx.save_for_backward(gR, gt)
+        return rl, tl
+
+    @staticmethod
+    def backward(ctx, d_rl, d_tl):
+        gR, gt = ctx.saved_tensors
+        dR = gR * d_rl.view(-1, 1, 1) if d_rl is not None else None
+        dt = gt * d_tl.view(-1, 1) if d_tl is not None else None
+        return dR, dt, None

@@ -657,6 +657,44 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(con
     }
 }
 
+// ---- pose_loss (3dm:896-962): rotation loss = acos(clamp((trace(R^T R_gt) - 1) / 2, -1, 1)), translation loss =
+// acos(clamp(cos(t, t_gt), -1, 1)) per pair, together with their gradients w.r.t. R and t (what autograd would
+// return for a unit upstream gradient; clamp passes the gradient on [-1, 1] inclusive like torch.clamp). ----
+__global__ void pose_loss_kernel(const float *__restrict__ R, const float *__restrict__ t, const float *__restrict__ gt_pose,
+                                 int pairs, float *__restrict__ rot_loss, float *__restrict__ trans_loss,
+                                 float *__restrict__ gR, float *__restrict__ gt_) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pairs) return;
+    const float *Rb = R + b * 9, *G = gt_pose + b * 16;
+    float tr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tr = fmaf(Rb[i * 3 + j], G[i * 4 + j], tr);        // trace(R^T R_gt) = sum_ij R_ij Rgt_ij
+    const float c = (tr - 1.0f) * 0.5f;
+    const float cc = fminf(fmaxf(c, -1.0f), 1.0f);
+    rot_loss[b] = acosf(cc);
+    if (gR) {
+        const float k = (c < -1.0f || c > 1.0f) ? 0.f : -0.5f / sqrtf(1.0f - cc * cc);   // d acos(c)/dc * dc/dtr
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) gR[b * 9 + i * 3 + j] = k * G[i * 4 + j];
+    }
+    const float t0 = t[b * 3], t1 = t[b * 3 + 1], t2 = t[b * 3 + 2], g0 = G[3], g1 = G[7], g2 = G[11];
+    const float dot = t0 * g0 + t1 * g1 + t2 * g2;
+    const float nt = sqrtf(t0 * t0 + t1 * t1 + t2 * t2), ng = sqrtf(g0 * g0 + g1 * g1 + g2 * g2);
+    const float cs = dot / (nt * ng);
+    const float cl = fminf(fmaxf(cs, -1.0f), 1.0f);
+    trans_loss[b] = acosf(cl);
+    if (gt_) {
+        const float k = (cs < -1.0f || cs > 1.0f) ? 0.f : -1.0f / sqrtf(1.0f - cl * cl);
+        // d cos / d t = g / (|t||g|) - cos * t / |t|^2
+        const float a = 1.0f / (nt * ng), bb = cs / (nt * nt);
+        gt_[b * 3] = k * (g0 * a - bb * t0); gt_[b * 3 + 1] = k * (g1 * a - bb * t1); gt_[b * 3 + 2] = k * (g2 * a - bb * t2);
+    }
+}
+
 static int head_threads(int n) {
     static const int forced = getenv("EGSPR_HEAD_THREADS") ? atoi(getenv("EGSPR_HEAD_THREADS")) : 0;   // developer switch
     if (forced == 256 || forced == 512 || forced == 1024) return forced;
@@ -740,7 +778,16 @@ extern "C" int egspr_head_train_backward(const float *h_out_src, const float *h_
     return EGSPR_OK;
 }
 
-extern "C" int egspr_version(void) { return 101; }
+extern "C" int egspr_pose_loss(const float *R, const float *t, const float *gt_pose, int pairs, float *rot_loss,
+                               float *trans_loss, float *grad_R, float *grad_t, void *stream) {
+    using namespace egspr;
+    if (!R || !t || !gt_pose || !rot_loss || !trans_loss || pairs <= 0) return EGSPR_E_INVALID;
+    pose_loss_kernel<<<(pairs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, t, gt_pose, pairs, rot_loss, trans_loss, grad_R, grad_t);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_version(void) { return 102; }
 
 extern "C" const char *egspr_error_string(int code) {
     switch (code) {

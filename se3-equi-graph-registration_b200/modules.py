@@ -231,13 +231,9 @@ def egnn_equi_loss(h_src, x_src, h_tgt, x_tgt, R_gt, t_gt, labels):
 
 
 def pose_loss(pred_rot, pred_translation, gt_pose, delta=1.5):
-    """3dm:896-962 -> (rotation_loss [B], translation_loss [B])."""
-    gt_t, gt_R = gt_pose[:, :3, 3], gt_pose[:, :3, :3]
-    Rd = torch.matmul(pred_rot.transpose(-1, -2), gt_R)
-    tr = Rd.diagonal(dim1=-2, dim2=-1).sum(-1)
-    rl = torch.arccos(torch.clamp((tr - 1) / 2, min=-1, max=1))
-    cos = (pred_translation * gt_t).sum(-1) / (pred_translation.norm(dim=-1) * gt_t.norm(dim=-1))
-    return rl, torch.arccos(torch.clamp(cos, min=-1, max=1))
+    """3dm:896-962 -> (rotation_loss [B], translation_loss [B]); one kernel (egspr_pose_loss) on CUDA tensors,
+    differentiable w.r.t. pred_rot and pred_translation."""
+    return _ag.PoseLossFunction.apply(pred_rot.to(torch.float32), pred_translation.to(torch.float32), gt_pose.to(torch.float32))
 
 
 def compute_losses(rot, translation, h_src_norm, x_src, h_tgt_norm, x_tgt, gt_labels):

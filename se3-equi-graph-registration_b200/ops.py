@@ -417,3 +417,19 @@ def head_train_backward(h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, dR, 
         _lib.check(_lib.lib().egspr_head_train_backward(*[_ptr(v) for v in ts], _ptr(labels), _ptr(dR), _ptr(dt), _ptr(dsim),
                                                         B, n, *[_ptr(o) for o in outs], _stream()), "egspr_head_train_backward")
     return outs
+
+
+def pose_loss(R, t, gt_pose, need_grad=True):
+    """pose_loss (3dm:896-962) for a batch -> rot_loss [B], trans_loss [B], d rot_loss / d R [B,3,3] | None,
+    d trans_loss / d t [B,3] | None."""
+    R = _req(R, "R", torch.float32, 3); t = _req(t, "t", torch.float32, 2)
+    gt_pose = _req(gt_pose.to(torch.float32), "gt_pose", torch.float32, 3)
+    B = R.shape[0]
+    rl = torch.empty(B, dtype=torch.float32, device=R.device)
+    tl = torch.empty(B, dtype=torch.float32, device=R.device)
+    gR = torch.empty((B, 3, 3), dtype=torch.float32, device=R.device) if need_grad else None
+    gt = torch.empty((B, 3), dtype=torch.float32, device=R.device) if need_grad else None
+    with torch.cuda.device(R.device):
+        _lib.check(_lib.lib().egspr_pose_loss(_ptr(R), _ptr(t), _ptr(gt_pose), B, _ptr(rl), _ptr(tl), _ptr(gR), _ptr(gt), _stream()),
+                   "egspr_pose_loss")
+    return rl, tl, gR, gt

@@ -250,3 +250,26 @@ def test_backward_on_irregular_graph_hub_rows_isolated_nodes(golden_dir):
     for name, p in model.egnn.named_parameters():
         assert p.grad is not None, name
         assert rel(p.grad, sd[name].grad) < G_TOL, (name, rel(p.grad, sd[name].grad))
+
+
+def test_pose_loss_kernel_matches_reference_function():
+    """egspr_pose_loss (values + local gradients) vs the oracle's pose_loss (3dm:896-962) and its autograd."""
+    g = torch.Generator().manual_seed(4)
+    B = 37
+    R = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    R = R + 0.05 * torch.randn(B, 3, 3, generator=g)               # not exactly orthogonal: the loss must not assume it
+    t = torch.randn(B, 3, generator=g)
+    gt = torch.eye(4).repeat(B, 1, 1)
+    gt[:, :3, :3] = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    gt[:, :3, 3] = torch.randn(B, 3, generator=g)
+    gt[0, :3, :3] = R[0] * 1.5                                      # trace term > 1: clamped, zero gradient
+    Rr, tr = R.double().requires_grad_(True), t.double().requires_grad_(True)
+    rl_ref, tl_ref = O.pose_loss(Rr, tr, gt.double())
+    wr, wt = torch.randn(B, generator=g).double(), torch.randn(B, generator=g).double()
+    ((rl_ref * wr).sum() + (tl_ref * wt).sum()).backward()
+    Rg, tg = R.to(DEV).requires_grad_(True), t.to(DEV).requires_grad_(True)
+    rl, tl = P.pose_loss(Rg, tg, gt.to(DEV))
+    ((rl * wr.float().to(DEV)).sum() + (tl * wt.float().to(DEV)).sum()).backward()
+    assert torch.allclose(rl.detach().cpu().double(), rl_ref.detach(), atol=2e-6) and torch.allclose(tl.detach().cpu().double(), tl_ref.detach(), atol=2e-6)
+    assert rel(Rg.grad, Rr.grad) < 1e-5 and rel(tg.grad, tr.grad) < 1e-5
+    assert float(Rg.grad[0].abs().max()) == 0.0
