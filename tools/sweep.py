@@ -68,11 +68,27 @@ for label, shape, n, k, B in CONFIGS:
     knn_ms = tm(lambda: ops.knn_build(eng.x, k))
     eng.use_graph = False
     edge_ms = bench.eng_layer_time(eng, reps=5)
+    # training step (BASELINE configs[3]) at this shape: a quarter of the pairs, whole step as one CUDA graph
+    train_ms = None
+    if shape != "cube" and n <= 8192:
+        Bt = max(1, B // 4)
+        tm_model = P.build_model(bench.CKPT, device="cuda:0", variant="train")
+        with torch.no_grad():
+            tm_model.egnn.embedding_out.weight.mul_(bench.TRAIN_TEMPER); tm_model.egnn.embedding_out.bias.mul_(bench.TRAIN_TEMPER)
+        tkeys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
+        tb = tuple(data[kk][:Bt].cuda() for kk in tkeys)
+        step = P.train.GraphedTrainStep(tm_model, torch.optim.Adam(tm_model.parameters(), lr=1e-5, capturable=True, fused=True), tb, k=k)
+        train_ms = tm(lambda: step(tb), r=10)
+        train_pairs = Bt
+        del step, tm_model
     E = 2 * B * n * k
     alg = E * (2 * 32 * 4 + 2 * 12 + 4) + 2 * B * n * (32 * 4 + 12)
     print(json.dumps({"config": label, "shape": shape, "points": n, "k": k, "pairs": B, "ms_per_step": round(ms, 3),
                       "pairs_per_s": round(B / ms * 1e3, 1), "points_per_s": round(2 * B * n / ms * 1e3),
                       "knn_ms": round(knn_ms, 3), "edge_kernel_ms": round(edge_ms, 3),
-                      "edge_alg_GBs": round(alg / edge_ms / 1e6, 1), "knn_ids_equal_brute_force": exact, "finite": finite}), flush=True)
+                      "edge_alg_GBs": round(alg / edge_ms / 1e6, 1), "knn_ids_equal_brute_force": exact, "finite": finite,
+                      "train_pairs": None if train_ms is None else train_pairs,
+                      "train_ms_per_step": None if train_ms is None else round(train_ms, 3),
+                      "train_pairs_per_s": None if train_ms is None else round(train_pairs / train_ms * 1e3, 1)}), flush=True)
     del eng
     torch.cuda.empty_cache()
