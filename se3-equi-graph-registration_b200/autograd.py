@@ -106,3 +106,25 @@ class PoseLossFunction(torch.autograd.Function):
         dR = gR * d_rl.view(-1, 1, 1) if d_rl is not None else None
         dt = gt * d_tl.view(-1, 1) if d_tl is not None else None
         return dR, dt, None
+
+
+class EquiLossFunction(torch.autograd.Function):
+    """egnn_equi_loss (3dm:860-893, slot 3 of the forward's 9-tuple) without its forward cost: the value comes from the
+    partial sums the head kernel already produced; the gradient -- only needed when the caller adds this slot to the
+    training loss, which the reference loop does not (3dm:1118) -- is computed on demand."""
+
+    @staticmethod
+    def forward(ctx, loss_fn, hs, xs, ht, xt, R_gt, t_gt, labels_f, loss_parts):
+        ctx.loss_fn = loss_fn
+        ctx.save_for_backward(hs, xs, ht, xt, R_gt, t_gt, labels_f)
+        B, N = labels_f.shape
+        return loss_parts.sum(0).sum() / (B * N)
+
+    @staticmethod
+    def backward(ctx, g):
+        hs, xs, ht, xt, R_gt, t_gt, labels_f = ctx.saved_tensors
+        with torch.enable_grad():
+            leaves = [v.detach().requires_grad_(True) for v in (hs, xs, ht, xt)]
+            loss = ctx.loss_fn(leaves[0], leaves[1], leaves[2], leaves[3], R_gt, t_gt, labels_f)
+            grads = torch.autograd.grad(loss, leaves, g)
+        return (None, *grads, None, None, None, None)

@@ -324,8 +324,8 @@ class CrossAttentionPoseRegression(nn.Module):
         grad = _needs_grad(self, h_src, h_tgt, x_src, x_tgt)
         if grad:
             R, t, sim, w, Hm, lp = _ag.HeadTrainFunction.apply(hs, ht, xs, xt, labels_f, gt_pose.to(torch.float32))
-            total_loss = egnn_equi_loss(hs, xs, ht, xt, gt_pose[:, :3, :3].to(torch.float32),
-                                        gt_pose[:, :3, -1].to(torch.float32), labels_f)      # 3dm:677, differentiable
+            total_loss = _ag.EquiLossFunction.apply(egnn_equi_loss, hs, xs, ht, xt, gt_pose[:, :3, :3].to(torch.float32),
+                                                    gt_pose[:, :3, -1].to(torch.float32), labels_f, lp)   # 3dm:677, differentiable
         else:
             R, t, w, sim, Hm, lp = ops.head_train(hs, ht, xs, xt, labels_f, gt_pose)
             total_loss = lp.sum(0).sum() / (B * N)                                           # 3dm:677
