@@ -965,6 +965,63 @@ __global__ void __launch_bounds__(BT) linear32_backward_kernel(const float *__re
     atomicAdd(gpack + 1024 + (threadIdx.x & 31), colDy);
 }
 
+// Linear(32,32) backward, 8 lanes per row (the default; same layout ideas as node_mlp_backward_wide_kernel)
+constexpr size_t LW_SMEM = sizeof(float) * (1024 + BT * RS + 32 * NOS);
+
+__global__ void __launch_bounds__(NT, 1) linear32_backward_wide_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                                        int64_t rows, const float *__restrict__ pack,
+                                                                        float *__restrict__ dx, float *__restrict__ gpack) {
+    extern __shared__ __align__(16) float smem[];
+    float *sWo = smem, *sX = smem + 1024, *sDy = sX + BT * RS;       // W as [out][in]; x node-major; dy feature-major
+    for (int i = threadIdx.x; i < 1024; i += NT) sWo[(i & 31) * 32 + (i >> 5)] = __ldg(pack + i);
+    const int sub = threadIdx.x & 7, ln = threadIdx.x >> 3, c0 = 4 * sub;
+    const int ai = threadIdx.x & 31, ao = threadIdx.x >> 5;
+    float acc[2] = {0.f, 0.f}, colDy = 0.f;
+    const int64_t tiles = (rows + BT - 1) / BT;
+    __syncthreads();
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t n = tile * BT + ln;
+        const bool valid = n < rows;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv = xv;
+        if (valid) { xv = ldg4(x + n * H + c0); dv = ldg4(dy + n * H + c0); }
+        float *rX = sX + ln * RS, *rD = sDy + ln;
+        rX[c0] = xv.x; rX[c0 + 1] = xv.y; rX[c0 + 2] = xv.z; rX[c0 + 3] = xv.w;
+        rD[c0 * NOS] = dv.x; rD[(c0 + 1) * NOS] = dv.y; rD[(c0 + 2) * NOS] = dv.z; rD[(c0 + 3) * NOS] = dv.w;
+        __syncwarp();
+        if (dx && valid) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int o = 0; o < 32; ++o) {
+                const float v = rD[o * NOS];
+                const float4 w = *reinterpret_cast<const float4 *>(sWo + 32 * o + c0);
+                fma2(g.x, g.y, w.x, w.y, v, v); fma2(g.z, g.w, w.z, w.w, v, v);
+            }
+            *reinterpret_cast<float4 *>(dx + n * H + c0) = g;
+        }
+        __syncthreads();
+        {
+            const float *in = sX + ai, *od = sDy + ao * NOS;
+#pragma unroll 2
+            for (int e = 0; e < BT; e += 4) {
+                const float4 dd = *reinterpret_cast<const float4 *>(od + e);
+                fma2(acc[0], acc[1], in[e * RS], in[(e + 1) * RS], dd.x, dd.y);
+                fma2(acc[0], acc[1], in[(e + 2) * RS], in[(e + 3) * RS], dd.z, dd.w);
+            }
+        }
+        if (threadIdx.x < 32) {
+            const float *o = sDy + threadIdx.x * NOS;
+#pragma unroll 4
+            for (int e = 0; e < BT; e += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(o + e);
+                colDy += (v.x + v.y) + (v.z + v.w);
+            }
+        }
+        __syncthreads();
+    }
+    atomicAdd(gpack + 32 * ai + ao, acc[0] + acc[1]);
+    if (threadIdx.x < 32) atomicAdd(gpack + 1024 + threadIdx.x, colDy);
+}
+
 template <class K>
 static int prep_kernel(K kernel, size_t smem, int &ctas_per_sm, int threads = BT) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EGSPR_E_LAUNCH;
@@ -1042,12 +1099,16 @@ extern "C" int egspr_linear32_backward(const float *x, const float *dy, int64_t 
                                        float *grad_pack, void *stream) {
     using namespace egspr;
     if (!x || !dy || !embed_pack || !grad_pack || rows <= 0) return EGSPR_E_INVALID;
-    static int occ = 0;
+    static int occ = 0, occ_wide = 0;
     if (!occ) {
         if (int e = prep_kernel(linear32_backward_kernel, LB_SMEM, occ)) return e;
+        if (int e = prep_kernel(linear32_backward_wide_kernel, LW_SMEM, occ_wide, NT)) return e;
     }
     const int64_t tiles = (rows + BT - 1) / BT;
-    linear32_backward_kernel<<<grid_for(tiles, occ), BT, LB_SMEM, (cudaStream_t)stream>>>(x, dy, rows, embed_pack, dx, grad_pack);
+    if (getenv("EGSPR_EDGE_BWD_FULL") != nullptr)
+        linear32_backward_kernel<<<grid_for(tiles, occ), BT, LB_SMEM, (cudaStream_t)stream>>>(x, dy, rows, embed_pack, dx, grad_pack);
+    else
+        linear32_backward_wide_kernel<<<grid_for(tiles, occ_wide), NT, LW_SMEM, (cudaStream_t)stream>>>(x, dy, rows, embed_pack, dx, grad_pack);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
