@@ -165,126 +165,8 @@ __global__ void __launch_bounds__(BT) node_mlp_backward_kernel(const float *__re
     atomicAdd(gpack + B_BN1 + lane, colDz);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// node MLP backward, 8 lanes per node (the default): CTA = 1024 threads = a tile of 128 nodes, every lane owns 4 of the
-// 32 channels of each matvec (weights as 128-bit rows, the node's vectors broadcast from its shared-memory rows), rows
-// move as coalesced 128-byte lines.  Same arithmetic as node_backward() in egnn_backward_math.cuh.  The thread-per-node
-// kernel above runs a chain of ~200 dependent iterations per tile on 4 warps per CTA; here a tile is 32 warps wide.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int NT = 1024;
-constexpr int NOS = BT + 4;          // feature-major row stride of the "out" tiles (dout, dz1)
-// smem: WN1T [64][32] | W1o [32][64] (transposed) | W2o [32][32] (node_mlp.2.weight as stored [out][in]) | bn1 [32] |
-//       h, agg, a node-major [BT][RS] | dout, dz1 feature-major [32][NOS]
-constexpr size_t NW_SMEM = sizeof(float) * (2048 + 2048 + 1024 + 32 + 3 * BT * RS + 2 * 32 * NOS);
-
-__global__ void __launch_bounds__(NT, 1) node_mlp_backward_wide_kernel(const float *__restrict__ h, const float *__restrict__ agg,
-                                                                        const float *__restrict__ dh_out, int64_t G,
-                                                                        const float *__restrict__ pack, float *__restrict__ dh_in,
-                                                                        float *__restrict__ dagg, float *__restrict__ gpack) {
-    extern __shared__ __align__(16) float smem[];
-    float *sW1 = smem, *sW1o = sW1 + 2048, *sW2o = sW1o + 2048, *sB1 = sW2o + 1024;
-    float *sH = sB1 + 32, *sAgg = sH + BT * RS, *sA = sAgg + BT * RS;
-    float *sDout = sA + BT * RS, *sDz = sDout + 32 * NOS;
-    for (int i = threadIdx.x; i < 2048; i += NT) {
-        const float w = __ldg(pack + B_WN1T + i);                    // [in i>>5][out i&31]
-        sW1[i] = w;
-        sW1o[(i & 31) * 64 + (i >> 5)] = w;                          // [out][in]
-    }
-    for (int i = threadIdx.x; i < 1024; i += NT) sW2o[(i & 31) * 32 + (i >> 5)] = __ldg(pack + B_WN2T + i);   // WN2T [in][out] -> [out][in]
-    if (threadIdx.x < 32) sB1[threadIdx.x] = __ldg(pack + B_BN1 + threadIdx.x);
-    const int sub = threadIdx.x & 7, ln = threadIdx.x >> 3, c0 = 4 * sub;      // node of the tile, this lane's channels c0..c0+3
-    const int ai = threadIdx.x & 31, ao = threadIdx.x >> 5;                    // weight-gradient entry [in = ai][out = ao]
-    float accW2[2] = {0.f, 0.f}, accW1h[2] = {0.f, 0.f}, accW1a[2] = {0.f, 0.f}, colDout = 0.f, colDz = 0.f;
-    const int64_t tiles = (G + BT - 1) / BT;
-    __syncthreads();
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t n = tile * BT + ln;
-        const bool valid = n < G;
-        float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), av = hv, dv = hv;
-        if (valid) { hv = ldg4(h + n * H + c0); av = ldg4(agg + n * H + c0); dv = ldg4(dh_out + n * H + c0); }
-        float *rH = sH + ln * RS, *rG = sAgg + ln * RS, *rA = sA + ln * RS, *rD = sDout + ln, *rZ = sDz + ln;
-        rH[c0] = hv.x; rH[c0 + 1] = hv.y; rH[c0 + 2] = hv.z; rH[c0 + 3] = hv.w;
-        rG[c0] = av.x; rG[c0 + 1] = av.y; rG[c0 + 2] = av.z; rG[c0 + 3] = av.w;
-        rD[c0 * NOS] = dv.x; rD[(c0 + 1) * NOS] = dv.y; rD[(c0 + 2) * NOS] = dv.z; rD[(c0 + 3) * NOS] = dv.w;
-        __syncwarp();
-        // z = Wn1 [h|agg] + bn1 (own 4 outputs), a = SiLU(z)
-        float z0 = sB1[c0], z1 = sB1[c0 + 1], z2 = sB1[c0 + 2], z3 = sB1[c0 + 3];
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const float v = rH[i], u = rG[i];
-            const float4 w = *reinterpret_cast<const float4 *>(sW1 + 32 * i + c0);
-            const float4 x = *reinterpret_cast<const float4 *>(sW1 + 32 * (32 + i) + c0);
-            fma2(z0, z1, w.x, w.y, v, v); fma2(z2, z3, w.z, w.w, v, v);
-            fma2(z0, z1, x.x, x.y, u, u); fma2(z2, z3, x.z, x.w, u, u);
-        }
-        float ds[4];
-        {
-            const float zz[4] = {z0, z1, z2, z3};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float sg = sigmoidf_(zz[q]);
-                rA[c0 + q] = zz[q] * sg;
-                ds[q] = sg * (1.0f + zz[q] * (1.0f - sg));
-            }
-        }
-        // da = Wn2^T dout (own 4 inputs of the second Linear), dz1 = da * silu'
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll 4
-        for (int o = 0; o < 32; ++o) {
-            const float v = rD[o * NOS];
-            const float4 w = *reinterpret_cast<const float4 *>(sW2o + 32 * o + c0);
-            fma2(d0, d1, w.x, w.y, v, v); fma2(d2, d3, w.z, w.w, v, v);
-        }
-        d0 *= ds[0]; d1 *= ds[1]; d2 *= ds[2]; d3 *= ds[3];
-        rZ[c0 * NOS] = d0; rZ[(c0 + 1) * NOS] = d1; rZ[(c0 + 2) * NOS] = d2; rZ[(c0 + 3) * NOS] = d3;
-        __syncwarp();
-        // dh = dout + Wn1[:, :32]^T dz1,  dagg = Wn1[:, 32:]^T dz1 (own 4 inputs of each half)
-        float4 gh = dv, ga = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int o = 0; o < 32; ++o) {
-            const float v = rZ[o * NOS];
-            const float4 w = *reinterpret_cast<const float4 *>(sW1o + 64 * o + c0);
-            const float4 x = *reinterpret_cast<const float4 *>(sW1o + 64 * o + 32 + c0);
-            fma2(gh.x, gh.y, w.x, w.y, v, v); fma2(gh.z, gh.w, w.z, w.w, v, v);
-            fma2(ga.x, ga.y, x.x, x.y, v, v); fma2(ga.z, ga.w, x.z, x.w, v, v);
-        }
-        if (valid) {
-            *reinterpret_cast<float4 *>(dh_in + n * H + c0) = gh;
-            *reinterpret_cast<float4 *>(dagg + n * H + c0) = ga;
-        }
-        __syncthreads();
-        // weight gradients, one entry of each matrix per thread, four nodes per 128-bit load of the out rows
-        {
-            const float *inA = sA + ai, *inH = sH + ai, *inG = sAgg + ai, *od = sDout + ao * NOS, *oz = sDz + ao * NOS;
-#pragma unroll 2
-            for (int e = 0; e < BT; e += 4) {
-                const float4 dd = *reinterpret_cast<const float4 *>(od + e), zz = *reinterpret_cast<const float4 *>(oz + e);
-                fma2(accW2[0], accW2[1], inA[e * RS], inA[(e + 1) * RS], dd.x, dd.y);
-                fma2(accW2[0], accW2[1], inA[(e + 2) * RS], inA[(e + 3) * RS], dd.z, dd.w);
-                fma2(accW1h[0], accW1h[1], inH[e * RS], inH[(e + 1) * RS], zz.x, zz.y);
-                fma2(accW1h[0], accW1h[1], inH[(e + 2) * RS], inH[(e + 3) * RS], zz.z, zz.w);
-                fma2(accW1a[0], accW1a[1], inG[e * RS], inG[(e + 1) * RS], zz.x, zz.y);
-                fma2(accW1a[0], accW1a[1], inG[(e + 2) * RS], inG[(e + 3) * RS], zz.z, zz.w);
-            }
-        }
-        if (threadIdx.x < 64) {                                     // bias gradients: column sums of dout (warp 0), dz1 (warp 1)
-            const float *o = (threadIdx.x < 32 ? sDout : sDz) + (threadIdx.x & 31) * NOS;
-            float c = 0.f;
-#pragma unroll 4
-            for (int e = 0; e < BT; e += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(o + e);
-                c += (v.x + v.y) + (v.z + v.w);
-            }
-            if (threadIdx.x < 32) colDout += c; else colDz += c;
-        }
-        __syncthreads();
-    }
-    atomicAdd(gpack + B_WN2T + 32 * ai + ao, accW2[0] + accW2[1]);
-    atomicAdd(gpack + B_WN1T + 32 * ai + ao, accW1h[0] + accW1h[1]);
-    atomicAdd(gpack + B_WN1T + 1024 + 32 * ai + ao, accW1a[0] + accW1a[1]);
-    if (threadIdx.x < 32) atomicAdd(gpack + B_BN2 + threadIdx.x, colDout);
-    else if (threadIdx.x < 64) atomicAdd(gpack + B_BN1 + (threadIdx.x & 31), colDz);
-}
+constexpr int NT = 1024;            // threads of the 8-lanes-per-row kernels
+constexpr int NOS = BT + 4;         // feature-major row stride of their "out" tiles
 
 // ---------------------------------------------------------------------------------------------------------------
 // edge backward
@@ -965,7 +847,10 @@ __global__ void __launch_bounds__(BT) linear32_backward_kernel(const float *__re
     atomicAdd(gpack + 1024 + (threadIdx.x & 31), colDy);
 }
 
-// Linear(32,32) backward, 8 lanes per row (the default; same layout ideas as node_mlp_backward_wide_kernel)
+// Linear(32,32) backward, 8 lanes per row (the default): CTA = 1024 threads = 128 rows, every lane owns 4 of the 32
+// channels, rows move as coalesced 128-byte lines, dy tile feature-major so the reduction reads 4 rows per 128-bit load
+// (34 us per launch vs 64 us for the thread-per-row kernel; the same restructuring of the node-MLP backward measured
+// SLOWER than its thread-per-node kernel, 106 vs 91 us, and was dropped)
 constexpr size_t LW_SMEM = sizeof(float) * (1024 + BT * RS + 32 * NOS);
 
 __global__ void __launch_bounds__(NT, 1) linear32_backward_wide_kernel(const float *__restrict__ x, const float *__restrict__ dy,
@@ -1061,18 +946,16 @@ extern "C" int egspr_egcl_backward(const float *h, const float *x4, const float 
     float *dagg = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     float *dpre = dagg + (size_t)num_nodes * 32;
     float *dxe = dpre + (size_t)E * 32;
-    static int occ_node = 0, occ_edge = 0, occ_gather = 0, occ_half = 0, occ_wide = 0;
+    static int occ_node = 0, occ_edge = 0, occ_gather = 0, occ_half = 0;
     const bool full_thread = getenv("EGSPR_EDGE_BWD_FULL") != nullptr;     // switch (read per call): the one-thread-per-edge / per-node kernels
     if (!occ_node) {
         if (int e = prep_kernel(node_mlp_backward_kernel, NB_SMEM, occ_node)) return e;
         if (int e = prep_kernel(edge_backward_kernel, EB_SMEM, occ_edge)) return e;
         if (int e = prep_kernel(edge_backward_half_kernel, EH_SMEM, occ_half)) return e;
-        if (int e = prep_kernel(node_mlp_backward_wide_kernel, NW_SMEM, occ_wide, NT)) return e;
         if (int e = prep_kernel(node_gather_backward_kernel, GB_SMEM, occ_gather, GT)) return e;
     }
     const int64_t ntiles = (num_nodes + BT - 1) / BT, etiles = (E + BT - 1) / BT;
-    if (full_thread) node_mlp_backward_kernel<<<grid_for(ntiles, occ_node), BT, NB_SMEM, st>>>(h, agg, dh_out, num_nodes, layer_pack, dh_in, dagg, grad_pack);
-    else node_mlp_backward_wide_kernel<<<grid_for(ntiles, occ_wide), NT, NW_SMEM, st>>>(h, agg, dh_out, num_nodes, layer_pack, dh_in, dagg, grad_pack);
+    node_mlp_backward_kernel<<<grid_for(ntiles, occ_node), BT, NB_SMEM, st>>>(h, agg, dh_out, num_nodes, layer_pack, dh_in, dagg, grad_pack);
     EGSPR_CHECK_LAUNCH();
     EdgeBwdArgs ea{x4, P, Q, csr_ptr, csr_row, csr_col, csr_eid, edge_attr, edge_attr_const, num_nodes, edges_per_cloud,
                    n_per_cloud, layer_pack, dagg, dx_out, dpre, dxe, grad_pack};
