@@ -224,3 +224,32 @@ def test_compute_losses_matches_reference():
         d = (torch.einsum("bij,bnj->bni", R, xs) + t[:, None] - xt).norm(dim=-1) * lab
         want = ((d.sum(1) / lab.sum(1).clamp(min=1)).mean(), (hs[lab == 1] - ht[lab == 1]).norm(dim=-1).mean())
     assert torch.allclose(got[0], want[0]) and torch.allclose(got[1], want[1])
+
+
+def test_pack_cache_and_grad_unpacker_gather_paths(golden_dir):
+    """PackCache rebuilds packs as `cat(params)[index]` and GradUnpacker maps gradient packs back with one gather: both
+    must equal the direct re-layout (pack_layer / unpack_layer_grad), also after parameter updates and for a layer
+    without an edge_attr column (76-wide edge input)."""
+    model = P.build_model(os.path.join(golden_dir, "checkpoint-3dmatch.pth"), device="cpu")
+    for i in range(3):
+        gcl = model.egnn._modules["gcl_%d" % i]
+        assert torch.equal(gcl.layer_pack(), packing.pack_layer(gcl))
+        with torch.no_grad():
+            gcl.coord_mlp[0].weight.add_(0.5); gcl.edge_mlps[2][0].bias.mul_(3.0)
+        assert torch.equal(gcl.layer_pack(), packing.pack_layer(gcl))            # second build = the gather path
+        gp = torch.randn(packing.LAYER_PACK)
+        fast = packing.GradUnpacker(packing.unpack_layer_grad, packing.LAYER_PACK, gcl)(gp)
+        for a, b, prm in zip(fast, packing.unpack_layer_grad(gp, gcl), gcl.parameters()):
+            assert torch.equal(a, b) and a.shape == prm.shape
+    layers, pin, pout = model.egnn.packs()
+    assert torch.equal(pin, packing.pack_linear32(model.egnn.embedding_in)) and torch.equal(pout, packing.pack_linear32(model.egnn.embedding_out))
+    assert torch.equal(model._pack_head.get(), packing.pack_head(model.mlp))
+    g0 = P.E_GCL(32, 32, 32, edges_in_d=0, num_heads=4, device="cpu")
+    with torch.no_grad():
+        g0.layer_norm.weight.mul_(2.0)
+    assert torch.equal(g0.layer_pack(), packing.pack_layer(g0))
+    with torch.no_grad():
+        g0.layer_norm.bias.add_(1.0)
+    assert torch.equal(g0.layer_pack(), packing.pack_layer(g0))
+    got = packing.GradUnpacker(packing.unpack_layer_grad, packing.LAYER_PACK, g0)(torch.arange(packing.LAYER_PACK, dtype=torch.float32))
+    assert [tuple(t.shape) for t in got] == [tuple(p.shape) for p in g0.parameters()]
