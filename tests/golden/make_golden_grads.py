@@ -2,9 +2,10 @@
 (ast-extracted from /root/reference by oracle/ref_loader.py; src/3dmatch_train_egnn_with_batch.py:634-796 forward,
 :896-962 pose_loss, :1094-1125 loss assembly + loss.backward()).  Build container only.
 
-    python tests/golden/make_golden_grads.py        -> tests/golden/grads_b2_n256.pt
+    python tests/golden/make_golden_grads.py        -> tests/golden/grads_b2_n256.pt, grads_dup_b2_n512.pt
 
-Two scenarios on the inputs of the small_b2_n256 fixture:
+Two scenarios on the inputs of the small_b2_n256 fixture and of the duplicate-heavy dup_b2_n512 fixture (30 % repeated
+points: zero-length edges, identity frames):
   shipped   the shipped checkpoint; loss = slot 2 (corr_loss + sim_loss) + slot 3 (egnn_equi_loss).  The pose terms
             are left out because with these weights the train-variant H is ~1e-6 I and the SVD gradient
             is not defined.
@@ -62,8 +63,13 @@ def run(scenario, g, dtype):
 
 def main():
     assert ref_loader.reference_available(), "needs /root/reference"
-    g = torch.load(os.path.join(HERE, "small_b2_n256.pt"), weights_only=False, map_location="cpu")
-    out = {"meta": {"case": "small_b2_n256", "temper": TEMPER}}
+    for case, fname in (("small_b2_n256", "grads_b2_n256.pt"), ("dup_b2_n512", "grads_dup_b2_n512.pt")):
+        make(case, fname)
+
+
+def make(case, fname):
+    g = torch.load(os.path.join(HERE, case + ".pt"), weights_only=False, map_location="cpu")
+    out = {"meta": {"case": case, "temper": TEMPER}}
     for scenario in ("shipped", "tempered"):
         for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
             try:
@@ -75,7 +81,7 @@ def main():
             n_none = sum(v is None for v in r["grads"].values())
             gmax = max(float(v.abs().max()) for v in r["grads"].values() if v is not None)
             print(scenario, tag, "loss", r["loss"], "params without grad", n_none, "max |grad|", gmax)
-    path = os.path.join(HERE, "grads_b2_n256.pt")
+    path = os.path.join(HERE, fname)
     torch.save(out, path)
     print(os.path.getsize(path) // 1024, "KiB")
 

@@ -110,12 +110,14 @@ def test_head_train_backward_matches_autograd():
             assert err <= 2e-4 * sc, (name, b, err, sc)
 
 
+@pytest.mark.parametrize("case,gfile", [("small_b2_n256", "grads_b2_n256.pt"), ("dup_b2_n512", "grads_dup_b2_n512.pt")])
 @pytest.mark.parametrize("scenario", ["shipped", "tempered"])
-def test_training_step_gradients_match_reference_golden(golden_dir, scenario):
+def test_training_step_gradients_match_reference_golden(golden_dir, scenario, case, gfile):
     """The whole training step through the drop-in module (forward train variant -> the loop's loss -> backward)
-    against the gradients the reference's own classes + autograd produced for the same inputs."""
-    g = torch.load(os.path.join(golden_dir, "small_b2_n256.pt"), weights_only=False, map_location="cpu")
-    gg = torch.load(os.path.join(golden_dir, "grads_b2_n256.pt"), weights_only=False, map_location="cpu")
+    against the gradients the reference's own classes + autograd produced for the same inputs; the second fixture is
+    duplicate-heavy (30 % repeated points: zero-length edges, identity frames, twin nodes)."""
+    g = torch.load(os.path.join(golden_dir, case + ".pt"), weights_only=False, map_location="cpu")
+    gg = torch.load(os.path.join(golden_dir, gfile), weights_only=False, map_location="cpu")
     ref = gg[scenario + "_f32"]
     model = _model(golden_dir, gg["meta"]["temper"] if scenario == "tempered" else None)
     model.train()
@@ -142,7 +144,7 @@ def test_training_step_gradients_match_reference_golden(golden_dir, scenario):
         assert e < G_TOL, (k, e)
         n += 1
     assert n == 85
-    print(f"{scenario}: worst relative-to-max gradient error {worst:.2e}")
+    print(f"{case} {scenario}: worst relative-to-max gradient error {worst:.2e}")
 
 
 def test_edge_attr_none_equals_ones(golden_dir):

@@ -166,10 +166,14 @@ def _train_loss(out, scenario, gt_pose):
     return out[2] + rot.mean() + trans.mean()                      # 3dm:1107-1118
 
 
+GRAD_CASES = [("small_b2_n256", "grads_b2_n256.pt"), ("dup_b2_n512", "grads_dup_b2_n512.pt")]
+
+
+@pytest.mark.parametrize("case,gfile", GRAD_CASES)
 @pytest.mark.parametrize("scenario", ["shipped", "tempered"])
-def test_oracle_gradients_match_reference_golden(golden_dir, scenario):
-    g, sd = load_case(golden_dir, "small_b2_n256")
-    gg = torch.load(os.path.join(golden_dir, "grads_b2_n256.pt"), weights_only=False, map_location="cpu")
+def test_oracle_gradients_match_reference_golden(golden_dir, scenario, case, gfile):
+    g, sd = load_case(golden_dir, case)
+    gg = torch.load(os.path.join(golden_dir, gfile), weights_only=False, map_location="cpu")
     ref = gg[scenario + "_f32"]
     sd = {k: v.clone() for k, v in sd.items()}
     if scenario == "tempered":
