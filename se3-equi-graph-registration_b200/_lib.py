@@ -9,9 +9,10 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.environ.get("EGSPR_LIB_PATH") or os.path.join(_HERE, "libegspr_b200.so")   # override: developer A/B builds
+LIB_PATH = os.path.join(_HERE, "libegspr_b200.so")
 SOURCES = ["knn.cu", "csr.cu", "egnn_layer.cu", "egnn_edge_ts.cu", "egnn_node_ts.cu", "head.cu", "feature_match.cu",
-           "egnn_backward.cu"]
+           "egnn_backward.cu", "egnn_edge_bwd_tc.cu"]
+HEADERS = ["egspr_common.cuh", "egnn_layer.cuh", "tcgen05.cuh", "egnn_backward_math.cuh", "egnn_backward.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -57,8 +58,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(_CSRC, "egspr_common.cuh"), os.path.join(_CSRC, "egnn_layer.cuh"), os.path.join(_CSRC, "tcgen05.cuh"), os.path.join(_CSRC, "egnn_backward_math.cuh"),
-                        os.path.join(_HERE, "..", "include", "egspr_b200.h")]
+    deps = sources() + [os.path.join(_CSRC, h) for h in HEADERS] + [os.path.join(_HERE, "..", "include", "egspr_b200.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 

@@ -260,15 +260,9 @@ static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, 
     if (clouds > 65535 || E >= (int64_t)0x7fffffff || G >= (int64_t)0x7fffffff) return EGSPR_E_UNSUPPORTED;
     if (ws_bytes < egspr_csr_workspace_bytes(G, E)) return EGSPR_E_WORKSPACE;
     {   // small clouds, enough of them to fill the GPU: fused single-launch build in shared memory
-        static const bool generic = getenv("EGSPR_CSR_GENERIC") != nullptr;     // developer switch
         const size_t smem = sizeof(int32_t) * (size_t)(2 * (int64_t)n + 1 + epc);
-        if (!generic && smem <= CF_MAX_SMEM && clouds >= 16) {
-            static bool configured = false;
-            if (!configured) {
-                if (cudaFuncSetAttribute(csr_fused_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF_MAX_SMEM) != cudaSuccess)
-                    return EGSPR_E_LAUNCH;
-                configured = true;
-            }
+        if (smem <= CF_MAX_SMEM && clouds >= 16) {
+            if (!opt_in_smem(csr_fused_kernel<Src>, CF_MAX_SMEM)) return EGSPR_E_LAUNCH;
             csr_fused_kernel<Src><<<clouds, CF_THREADS, smem, st>>>(src, n, epc, clouds, csr_ptr, csr_row, csr_col, csr_eid, err_flag);
             EGSPR_CHECK_LAUNCH();
             return EGSPR_OK;

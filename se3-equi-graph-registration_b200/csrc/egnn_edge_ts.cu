@@ -535,13 +535,8 @@ extern "C" int egspr_debug_read_ts(long long *host_dst) {
 #endif
 
 int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, bool fast, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(egcl_edge_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(egcl_edge_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM_BYTES) != cudaSuccess)
-            return EGSPR_E_LAUNCH;
-        configured = true;
-    }
+    if (!(fast ? opt_in_smem(egcl_edge_ts_kernel<true>, V_SMEM_BYTES) : opt_in_smem(egcl_edge_ts_kernel<false>, V_SMEM_BYTES)))
+        return EGSPR_E_LAUNCH;
     // one persistent CTA per SM; small graphs: at least ~2 tiles of edges per group
     int64_t grid = sm_count();
     const int64_t need = (a.num_nodes + 63) / 64;

@@ -150,16 +150,14 @@ __global__ void __launch_bounds__(128) node_embed_kernel(const float *__restrict
 
 template <int NB>
 static int launch_layer(const LayerArgs &a, cudaStream_t st) {
-    static bool configured = false;
-    static int ctas_per_sm = 1;
+    static int ctas_per_sm = 0;        // occupancy of this kernel (the same on every B200 of the box)
     constexpr size_t smem = layer_smem_bytes<NB>();
-    if (!configured) {
-        if (cudaFuncSetAttribute(egcl_layer_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return EGSPR_E_LAUNCH;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, egcl_layer_kernel<NB>, L_THREADS, smem) != cudaSuccess ||
-            ctas_per_sm < 1)
-            ctas_per_sm = 1;
-        configured = true;
+    if (!opt_in_smem(egcl_layer_kernel<NB>, smem)) return EGSPR_E_LAUNCH;
+    if (ctas_per_sm == 0) {
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egcl_layer_kernel<NB>, L_THREADS, smem) != cudaSuccess || occ < 1)
+            occ = 1;
+        ctas_per_sm = occ;
     }
     const int64_t items = (a.num_nodes + NB - 1) / NB;
     int64_t grid = (int64_t)sm_count() * ctas_per_sm;
@@ -180,13 +178,7 @@ extern "C" int egspr_node_embed(const float *feat, const float *x3, int64_t num_
     using namespace egspr;
     if (!feat || !layer0_pack || !h || !P || !Q || num_nodes <= 0) return EGSPR_E_INVALID;
     if (x4 && !x3) return EGSPR_E_INVALID;
-    static const bool simt = getenv("EGSPR_EMBED_SIMT") != nullptr;     // developer switch: CUDA-core embed kernel
-    if (!simt) return launch_node_embed_ts(feat, x3, num_nodes, embed_pack, layer0_pack, h, x4, P, Q, (cudaStream_t)stream);
-    int64_t grid = (num_nodes + 127) / 128;
-    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
-    node_embed_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(feat, x3, num_nodes, embed_pack, layer0_pack, h, x4, P, Q);
-    EGSPR_CHECK_LAUNCH();
-    return EGSPR_OK;
+    return launch_node_embed_ts(feat, x3, num_nodes, embed_pack, layer0_pack, h, x4, P, Q, (cudaStream_t)stream);
 }
 
 extern "C" int egspr_egcl_forward(const float *h, const float *x4, const float *P, const float *Q,

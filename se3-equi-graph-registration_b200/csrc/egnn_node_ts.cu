@@ -277,12 +277,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) egnn_node_ts_kernel(const NodeT
 }
 
 static int launch_node_ts(const NodeTsArgs &a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(egnn_node_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM_BYTES) != cudaSuccess)
-            return EGSPR_E_LAUNCH;
-        configured = true;
-    }
+    if (!opt_in_smem(egnn_node_ts_kernel, NT_SMEM_BYTES)) return EGSPR_E_LAUNCH;
     const int64_t tiles = (a.G + 127) / 128;
     int64_t grid = (tiles + NT_GROUPS - 1) / NT_GROUPS;
     if (grid > sm_count()) grid = sm_count();

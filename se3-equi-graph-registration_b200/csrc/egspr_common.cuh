@@ -127,15 +127,27 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
 inline int sm_count() {
-    static int n = 0;
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev];
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev] = n;
     }
     return n;
+}
+
+// opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (kernel, device) pair, so
+// it is set on every launch path for the current device (a host-side call of ~1 us; launches replayed from a CUDA
+// graph do not pay it) instead of being latched in a process-wide flag.
+template <class K>
+inline bool opt_in_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
 }
 
 }  // namespace egspr

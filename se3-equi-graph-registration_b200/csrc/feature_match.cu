@@ -145,12 +145,7 @@ extern "C" int egspr_feature_nn(const float *a, int na, const float *b, int nb, 
     if (!a || !b || !workspace || !idx || !dist || na <= 0 || nb <= 0) return EGSPR_E_INVALID;
     if (workspace_bytes < sizeof(unsigned long long) * (size_t)na) return EGSPR_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(feature_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM_BYTES) != cudaSuccess)
-            return EGSPR_E_LAUNCH;
-        configured = true;
-    }
+    if (!opt_in_smem(feature_nn_kernel, FM_SMEM_BYTES)) return EGSPR_E_LAUNCH;
     unsigned long long *packed = (unsigned long long *)workspace;
     if (cudaMemsetAsync(packed, 0xff, sizeof(unsigned long long) * (size_t)na, st) != cudaSuccess) return EGSPR_E_LAUNCH;
     const int mt = (na + 127) / 128, nt = (nb + FM_BN - 1) / FM_BN;

@@ -205,220 +205,6 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
 
 constexpr int GQ_WARPS = 8;
 
-__global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_kernel(
-    const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
-    int n, int k, int32_t *__restrict__ nbr, int maxc) {
-    const int cloud = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qs = blockIdx.x * GQ_WARPS + warp;          // query = qs-th point in cell-sorted order
-    if (qs >= n) return;
-    const float4 *so = sorted + (size_t)cloud * n;
-    const int *cs = cell_start + (size_t)cloud * (maxc + 1);
-    const GridParams gp = params[cloud];
-    const float4 q = __ldg(so + qs);
-    const int qi = __float_as_int(q.w);
-    const int nx = gp.dims[0], ny = gp.dims[1], nz = gp.dims[2];
-    const int cx = min(nx - 1, max(0, (int)((q.x - gp.mn[0]) * gp.inv[0])));
-    const int cy = min(ny - 1, max(0, (int)((q.y - gp.mn[1]) * gp.inv[1])));
-    const int cz = min(nz - 1, max(0, (int)((q.z - gp.mn[2]) * gp.inv[2])));
-    float bd = 1e10f;
-    int bi = -1;
-    float thr_d = 1e10f;
-    int thr_i = -1;
-    const int Lmax = max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz));
-    for (int L = 0; L <= Lmax; ++L) {
-        // rows (dz, dy) of the shell at Chebyshev radius L
-        for (int dz = -L; dz <= L; ++dz) {
-            const int z = cz + dz;
-            if (z < 0 || z >= nz) continue;
-            for (int dy = -L; dy <= L; ++dy) {
-                const int y = cy + dy;
-                if (y < 0 || y >= ny) continue;
-                const bool outer = (dz == -L || dz == L || dy == -L || dy == L);
-                // outer rows: the full x-run [cx-L, cx+L]; inner rows: only the two end cells
-                const int nruns = (outer || L == 0) ? 1 : 2;
-                for (int run = 0; run < nruns; ++run) {
-                    int x0, x1;
-                    if (nruns == 1) { x0 = max(cx - L, 0); x1 = min(cx + L, nx - 1); }
-                    else { x0 = x1 = (run == 0) ? cx - L : cx + L; if (x0 < 0 || x0 >= nx) continue; }
-                    const int rowbase = (z * ny + y) * nx;
-                    const int s = __ldg(cs + rowbase + x0), e = __ldg(cs + rowbase + x1 + 1);
-                    for (int j0 = s; j0 < e; j0 += 32) {
-                        const int j = j0 + lane;
-                        float d = 3e38f;
-                        int idx = 0x7fffffff;
-                        if (j < e) {
-                            const float4 c = __ldg(so + j);
-                            const float dx = c.x - q.x, dy2 = c.y - q.y, dz2 = c.z - q.z;
-                            d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
-                            idx = __float_as_int(c.w);
-                        }
-                        unsigned m = __ballot_sync(0xffffffffu, d < thr_d || (d == thr_d && idx < thr_i));
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const float dd = __shfl_sync(0xffffffffu, d, src);
-                            const int jj = __shfl_sync(0xffffffffu, idx, src);
-                            if (dd < thr_d || (dd == thr_d && jj < thr_i)) {
-                                const bool before = lane < k && (bd < dd || (bd == dd && bi < jj) );
-                                // empty slots are (1e10, -1): never "before" a real candidate (dd < 1e10)
-                                const int pos = __popc(__ballot_sync(0xffffffffu, before && bi >= 0));
-                                const float ubd = __shfl_up_sync(0xffffffffu, bd, 1);
-                                const int ubi = __shfl_up_sync(0xffffffffu, bi, 1);
-                                if (lane > pos) { bd = ubd; bi = ubi; }
-                                if (lane == pos) { bd = dd; bi = jj; }
-                                thr_d = __shfl_sync(0xffffffffu, bd, k - 1);
-                                thr_i = __shfl_sync(0xffffffffu, bi, k - 1);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        // done when the k-th best is strictly inside the scanned block (sides on the domain boundary
-        // have nothing beyond them)
-        float margin = 3e38f;
-        if (cx - L > 0) margin = fminf(margin, q.x - (gp.mn[0] + (float)(cx - L) * gp.cs[0]));
-        if (cx + L < nx - 1) margin = fminf(margin, (gp.mn[0] + (float)(cx + L + 1) * gp.cs[0]) - q.x);
-        if (cy - L > 0) margin = fminf(margin, q.y - (gp.mn[1] + (float)(cy - L) * gp.cs[1]));
-        if (cy + L < ny - 1) margin = fminf(margin, (gp.mn[1] + (float)(cy + L + 1) * gp.cs[1]) - q.y);
-        if (cz - L > 0) margin = fminf(margin, q.z - (gp.mn[2] + (float)(cz - L) * gp.cs[2]));
-        if (cz + L < nz - 1) margin = fminf(margin, (gp.mn[2] + (float)(cz + L + 1) * gp.cs[2]) - q.z);
-        if (margin > 1e37f) break;                              // block covers the whole grid
-        if (margin > 0.f) {
-            const float ms = margin * 0.9999f - gp.slack;
-            if (thr_i >= 0 && ms > 0.f && thr_d < ms * ms) break;
-        }
-    }
-    if (lane < k) nbr[((size_t)cloud * n + qi) * k + lane] = bi;
-}
-
-// ---- flattened variant of the query kernel -------------------------------------------------------
-// Same search (shells of cells at Chebyshev radius L around the query's cell, same (d2, index) total
-// order, same stopping rule), but the cells of a shell are not walked by nested loops: every lane
-// describes ONE contiguous run of cells (a "segment": start, length in the cell-sorted point array),
-// a warp scan turns the lengths into offsets, and the lanes then sweep the concatenated candidate list
-// 32 at a time (segment found by a 5-step shuffle binary search).  Removes the loop / branch overhead
-// that dominated the nested version (ncu: 27 % ISETP+BRA, 10 % BSSY/BSYNC) and keeps lanes busy on
-// short runs.
-__device__ __forceinline__ void knn_insert_batch(float d, int idx, int k, int lane, float &bd, int &bi, float &thr_d, int &thr_i) {
-    unsigned m = __ballot_sync(0xffffffffu, d < thr_d || (d == thr_d && idx < thr_i));
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float dd = __shfl_sync(0xffffffffu, d, src);
-        const int jj = __shfl_sync(0xffffffffu, idx, src);
-        if (dd < thr_d || (dd == thr_d && jj < thr_i)) {
-            const bool before = lane < k && (bd < dd || (bd == dd && bi < jj));
-            // empty slots are (1e10, -1): never "before" a real candidate (dd < 1e10)
-            const int pos = __popc(__ballot_sync(0xffffffffu, before && bi >= 0));
-            const float ubd = __shfl_up_sync(0xffffffffu, bd, 1);
-            const int ubi = __shfl_up_sync(0xffffffffu, bi, 1);
-            if (lane > pos) { bd = ubd; bi = ubi; }
-            if (lane == pos) { bd = dd; bi = jj; }
-            thr_d = __shfl_sync(0xffffffffu, bd, k - 1);
-            thr_i = __shfl_sync(0xffffffffu, bi, k - 1);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_flat_kernel(
-    const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
-    int n, int k, int32_t *__restrict__ nbr, int maxc) {
-    const int cloud = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qs = blockIdx.x * GQ_WARPS + warp;          // query = qs-th point in cell-sorted order
-    if (qs >= n) return;
-    const float4 *so = sorted + (size_t)cloud * n;
-    const int *cs = cell_start + (size_t)cloud * (maxc + 1);
-    const GridParams gp = params[cloud];
-    const float4 q = __ldg(so + qs);
-    const int qi = __float_as_int(q.w);
-    const int nx = gp.dims[0], ny = gp.dims[1], nz = gp.dims[2];
-    const int cx = min(nx - 1, max(0, (int)((q.x - gp.mn[0]) * gp.inv[0])));
-    const int cy = min(ny - 1, max(0, (int)((q.y - gp.mn[1]) * gp.inv[1])));
-    const int cz = min(nz - 1, max(0, (int)((q.z - gp.mn[2]) * gp.inv[2])));
-    float bd = 1e10f;
-    int bi = -1;
-    float thr_d = 1e10f;
-    int thr_i = -1;
-    const int Lmax = max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz));
-    for (int L = 1; L <= max(Lmax, 1); ++L) {
-        // segments of this step: L == 1: the 9 rows of the 3x3x3 block (shells 0 and 1 together);
-        // L >= 2: 8L outer rows (full x-run) + (2L-1)^2 inner rows x 2 end cells
-        const int w = 2 * L - 1;
-        const int nseg = (L == 1) ? 9 : 8 * L + 2 * w * w;
-        for (int s0 = 0; s0 < nseg; s0 += 32) {
-            const int s = s0 + lane;
-            int start = 0, len = 0;
-            if (s < nseg) {
-                int dz, dy, x0, x1;
-                if (L == 1) {
-                    dz = s / 3 - 1; dy = s % 3 - 1; x0 = cx - 1; x1 = cx + 1;
-                } else if (s < 8 * L) {
-                    x0 = cx - L; x1 = cx + L;
-                    if (s < 2 * L + 1) { dz = -L; dy = s - L; }
-                    else if (s < 2 * (2 * L + 1)) { dz = L; dy = s - (2 * L + 1) - L; }
-                    else { const int t = s - 2 * (2 * L + 1); dy = (t >= w) ? L : -L; dz = (t >= w ? t - w : t) - (L - 1); }
-                } else {
-                    const int t = s - 8 * L, rr = t >> 1;
-                    dz = rr / w - (L - 1); dy = rr % w - (L - 1);
-                    x0 = x1 = (t & 1) ? cx + L : cx - L;
-                }
-                const int z = cz + dz, y = cy + dy;
-                x0 = max(x0, 0); x1 = min(x1, nx - 1);
-                if (z >= 0 && z < nz && y >= 0 && y < ny && x0 <= x1) {
-                    const int rowbase = (z * ny + y) * nx;
-                    start = __ldg(cs + rowbase + x0);
-                    len = __ldg(cs + rowbase + x1 + 1) - start;
-                }
-            }
-            // exclusive scan of the segment lengths
-            int incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const int excl = incl - len;
-            const int T = __shfl_sync(0xffffffffu, incl, 31);
-            for (int t0 = 0; t0 < T; t0 += 32) {
-                const int t = t0 + lane;
-                // segment of candidate t: the last lane whose exclusive offset is <= t (empty segments share
-                // an offset with their successor, so "last" lands on the non-empty one)
-                int lo = 0;
-#pragma unroll
-                for (int h = 16; h > 0; h >>= 1) {
-                    const int v = __shfl_sync(0xffffffffu, excl, lo + h);
-                    if (v <= t) lo += h;
-                }
-                const int sstart = __shfl_sync(0xffffffffu, start, lo), sbase = __shfl_sync(0xffffffffu, excl, lo);
-                float d = 3e38f;
-                int idx = 0x7fffffff;
-                if (t < T) {
-                    const float4 c = __ldg(so + sstart + (t - sbase));
-                    const float dx = c.x - q.x, dy2 = c.y - q.y, dz2 = c.z - q.z;
-                    d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
-                    idx = __float_as_int(c.w);
-                }
-                knn_insert_batch(d, idx, k, lane, bd, bi, thr_d, thr_i);
-            }
-        }
-        // done when the k-th best is strictly inside the scanned block (sides on the domain boundary
-        // have nothing beyond them)
-        float margin = 3e38f;
-        if (cx - L > 0) margin = fminf(margin, q.x - (gp.mn[0] + (float)(cx - L) * gp.cs[0]));
-        if (cx + L < nx - 1) margin = fminf(margin, (gp.mn[0] + (float)(cx + L + 1) * gp.cs[0]) - q.x);
-        if (cy - L > 0) margin = fminf(margin, q.y - (gp.mn[1] + (float)(cy - L) * gp.cs[1]));
-        if (cy + L < ny - 1) margin = fminf(margin, (gp.mn[1] + (float)(cy + L + 1) * gp.cs[1]) - q.y);
-        if (cz - L > 0) margin = fminf(margin, q.z - (gp.mn[2] + (float)(cz - L) * gp.cs[2]));
-        if (cz + L < nz - 1) margin = fminf(margin, (gp.mn[2] + (float)(cz + L + 1) * gp.cs[2]) - q.z);
-        if (margin > 1e37f) break;                              // block covers the whole grid
-        if (margin > 0.f) {
-            const float ms = margin * 0.9999f - gp.slack;
-            if (thr_i >= 0 && ms > 0.f && thr_d < ms * ms) break;
-        }
-    }
-    if (lane < k) nbr[((size_t)cloud * n + qi) * k + lane] = bi;
-}
-
 // ---- sub-warp variant (k <= 16): 32/W queries per warp, W lanes each ---------------------------------
 // The per-iteration instruction cost of the flat kernel (segment search, candidate scoring, the
 // serial insertion loop) is paid once per warp, so sharing a warp between 32/W neighbouring queries
@@ -605,9 +391,9 @@ static void launch_knn_sub(const float4 *sorted, const int *cell_start, const Gr
                            int32_t *nbr, int maxc, cudaStream_t st) {
     constexpr int QPB = GQ_WARPS * (32 / W);
     dim3 grid((n + QPB - 1) / QPB, clouds);
-    static const int merge_min = getenv("EGSPR_KNN_MERGE_MIN") ? atoi(getenv("EGSPR_KNN_MERGE_MIN")) : 5;
-    static const int l0 = getenv("EGSPR_KNN_L0") ? atoi(getenv("EGSPR_KNN_L0")) : 1;       // radius of the first block
-    knn_grid_query_sub_kernel<W, E><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min, maxc, l0 < 1 ? 1 : l0);
+    constexpr int merge_min = 5;     // batches with >= 5 passing candidates are bitonic-merged (measured optimum)
+    constexpr int l0 = 1;            // radius of the first block of cells
+    knn_grid_query_sub_kernel<W, E><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min, maxc, l0);
 }
 
 __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int k,
@@ -651,18 +437,10 @@ extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t
     if (build_smem > 48 * 1024 &&
         cudaFuncSetAttribute(knn_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem) != cudaSuccess)
         return EGSPR_E_LAUNCH;
-    static const float ppc = getenv("EGSPR_KNN_PPC") ? (float)atof(getenv("EGSPR_KNN_PPC")) : 2.0f;   // target points per cell (measured optimum at 2048-point clouds, k = 16)
+    constexpr float ppc = 2.0f;      // target points per cell (measured optimum at 2048-point clouds, k = 16)
     knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, build_smem, st>>>(x, n, sorted, cell_start, params, maxc, ppc);
-    dim3 grid((n + GQ_WARPS - 1) / GQ_WARPS, clouds);
-    static const bool nested = getenv("EGSPR_KNN_NESTED") != nullptr;    // developer switch: the nested-loop query kernel
-    static const bool flat32 = getenv("EGSPR_KNN_FLAT32") != nullptr;    // developer switch: one query per warp even for k <= 16
-    if (nested) knn_grid_query_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, maxc);
-    else if (k <= 16 && !flat32) {
-        static const int wsel = getenv("EGSPR_KNN_W") ? atoi(getenv("EGSPR_KNN_W")) : 16;   // lanes per query
-        if (wsel == 8) launch_knn_sub<8, 2>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);
-        else launch_knn_sub<16, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);
-    } else if (!flat32) launch_knn_sub<32, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);   // 16 < k <= 32
-    else knn_grid_query_flat_kernel<<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, maxc);
+    if (k <= 16) launch_knn_sub<16, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);       // 16 lanes per query
+    else launch_knn_sub<32, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);               // 16 < k <= 32
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }

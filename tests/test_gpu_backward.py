@@ -35,14 +35,11 @@ def _model(golden_dir, temper=None):
     return m
 
 
-@pytest.mark.parametrize("per_edge_attr,full_thread", [(False, False), (True, False), (True, True)])
-def test_egcl_layer_backward_matches_autograd(golden_dir, monkeypatch, per_edge_attr, full_thread):
+@pytest.mark.parametrize("per_edge_attr", [False, True])
+def test_egcl_layer_backward_matches_autograd(golden_dir, per_edge_attr):
     """One E_GCL layer through the module API (E_GCL.forward 3dm:280-289) on an arbitrary user graph with duplicate
-    points: gradients w.r.t. h, coord and every parameter vs autograd of the oracle (fp64).  Both edge-backward
-    kernels: two threads per edge (default) and one thread per edge (EGSPR_EDGE_BWD_FULL, the kernel that calls the
-    CPU-checked edge_backward() of egnn_backward_math.cuh directly)."""
-    if full_thread:
-        monkeypatch.setenv("EGSPR_EDGE_BWD_FULL", "1")
+    points: gradients w.r.t. h, coord and every parameter vs autograd of the oracle (fp64).  The edge part is the
+    tcgen05 kernel (egnn_edge_bwd_tc.cu); its formulas are the CPU-checked ones of egnn_backward_math.cuh."""
     model = _model(golden_dir)
     gcl = model.egnn.gcl_1
     g = torch.Generator().manual_seed(3)
