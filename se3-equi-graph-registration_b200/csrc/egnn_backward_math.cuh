@@ -56,6 +56,26 @@ EGSPR_HD float sigmoidf_(float v) {
 #endif
 }
 
+// sqrt / reciprocal: MUFU approximations on the device (~2 ulp, far inside the gradient tolerance), IEEE on the host
+EGSPR_HD float sqrt_(float v) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    return sqrtf(v);
+#endif
+}
+EGSPR_HD float rcp_(float v) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    return 1.0f / v;
+#endif
+}
+
 // cross product
 EGSPR_HD void cross3(const float *a, const float *b, float *o) {
     o[0] = a[1] * b[2] - a[2] * b[1];
@@ -73,12 +93,12 @@ struct EdgeGeo {
 EGSPR_HD void edge_geometry(const float *xr, const float *xc, EdgeGeo &g, float *geo) {
     for (int i = 0; i < 3; ++i) g.d[i] = xr[i] - xc[i];                        // :273
     const float radial = g.d[0] * g.d[0] + g.d[1] * g.d[1] + g.d[2] * g.d[2];  // :274
-    g.dist = sqrtf(radial);                                                    // :179
-    const float ia = 1.0f / (g.dist + 1e-8f);                                  // :140
+    g.dist = sqrt_(radial);                                                    // :179
+    const float ia = rcp_(g.dist + 1e-8f);                                     // :140
     for (int i = 0; i < 3; ++i) g.a[i] = g.d[i] * ia;
     cross3(xr, xc, g.cr);                                                      // :143
-    g.nb = sqrtf(g.cr[0] * g.cr[0] + g.cr[1] * g.cr[1] + g.cr[2] * g.cr[2]);
-    const float ib = 1.0f / (g.nb + 1e-8f);                                    // :144
+    g.nb = sqrt_(g.cr[0] * g.cr[0] + g.cr[1] * g.cr[1] + g.cr[2] * g.cr[2]);
+    const float ib = rcp_(g.nb + 1e-8f);                                       // :144
     for (int i = 0; i < 3; ++i) g.b[i] = g.cr[i] * ib;
     float c[3];
     cross3(g.a, g.b, c);                                                       // :149
@@ -112,17 +132,17 @@ EGSPR_HD void edge_geometry_backward(const float *xr, const float *xc, const Edg
         cross3(gc, g.a, t);
         for (int i = 0; i < 3; ++i) gb[i] += t[i];
         // a = d / (|d| + eps)
-        const float sa = 1.0f / (g.dist + 1e-8f);
+        const float sa = rcp_(g.dist + 1e-8f);
         const float gad = ga[0] * g.d[0] + ga[1] * g.d[1] + ga[2] * g.d[2];
-        const float ka = g.dist > 0.f ? gad * sa * sa / g.dist : 0.f;
+        const float ka = g.dist > 0.f ? gad * sa * sa * rcp_(g.dist) : 0.f;
         for (int i = 0; i < 3; ++i) gd[i] += sa * ga[i] - ka * g.d[i];
         // b = cr / (|cr| + eps)
-        const float sb = 1.0f / (g.nb + 1e-8f);
+        const float sb = rcp_(g.nb + 1e-8f);
         const float gbc = gb[0] * g.cr[0] + gb[1] * g.cr[1] + gb[2] * g.cr[2];
-        const float kb = g.nb > 0.f ? gbc * sb * sb / g.nb : 0.f;
+        const float kb = g.nb > 0.f ? gbc * sb * sb * rcp_(g.nb) : 0.f;
         for (int i = 0; i < 3; ++i) gcr[i] = sb * gb[i] - kb * g.cr[i];
     }
-    const float kd = (g.dist > 0.f ? gg[1] / g.dist : 0.f) + 2.0f * gg[0];   // dist = |d|, radial = |d|^2
+    const float kd = (g.dist > 0.f ? gg[1] * rcp_(g.dist) : 0.f) + 2.0f * gg[0];   // dist = |d|, radial = |d|^2
     for (int i = 0; i < 3; ++i) gd[i] += kd * g.d[i];
     float t[3];
     cross3(xc, gcr, t);                                      // cr = xr x xc: dxr = xc x gcr, dxc = gcr x xr

@@ -41,7 +41,7 @@ constexpr int XS_GRP = ((XS_PAR + 5 * 128 + 4096 + 1023) / 1024) * 1024;
 constexpr int XG_TILE = 16384;                // one 128 x 128-byte tile
 constexpr int XG_SIZE = 4 * XG_TILE;          // geo | a1 | m -> du | dc1 -> dpre
 constexpr int XS_MISC = XS_GRP + XG * XG_SIZE;
-constexpr size_t X_SMEM_BYTES = XS_MISC + 64 + 1024;
+constexpr size_t X_SMEM_BYTES = XS_MISC + 16 + 32 * XG + 1024;
 
 // TMEM columns
 constexpr uint32_t XT_D = 0;                  // + 32 g
@@ -55,6 +55,45 @@ constexpr uint32_t ID_KM_N16 = idesc_bf16(128, 16, 0, 1);
 constexpr uint32_t ID_MM_N32 = idesc_bf16(64, 32, 1, 1);
 constexpr uint32_t ID_MM_N16 = idesc_bf16(64, 16, 1, 1);
 constexpr uint32_t ID_MK_N8 = idesc_bf16(64, 8, 1, 0);
+
+#ifdef EGSPR_XB_TIMING       // developer build: per-phase clock64() timeline of one group (tools/xb_timing.py)
+__device__ long long g_xb_dbg[4 * 64 * 32];
+#define XB_MARK(slot)                                                                                              \
+    do {                                                                                                           \
+        if (blockIdx.x == 7 && grp == 1 && lane == 0 && tile_no < 64) g_xb_dbg[(hw * 64 + tile_no) * 32 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define XB_MARK(slot)
+#endif
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// loads that must be ISSUED where they are written (look-ahead loads: a plain __ldg is "invariant" and gets sunk to its
+// first use, which turns the prefetch into a stall)
+__device__ __forceinline__ int ldg_now(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_now(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg4_now(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldcg4_now(const float *p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
 // low half = bf16(a), high half = bf16(b), both truncated
 __device__ __forceinline__ uint32_t pack_hi16(float a, float b) {
@@ -177,7 +216,10 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
         spar[128 + tid] = __ldg(a.pack + OFF_WC2 + tid);
     }
     if (tid < 32) tmem_alloc(smem_u32(tmem_holder), 512);
-    if (ht == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (ht == 0) {
+        mbar_init(mbar, 1); mbar_init(mbar + 8 * XG, 1); mbar_init(mbar + 16 * XG, 1); mbar_init(mbar + 24 * XG, 1);
+        fence_mbar_init();
+    }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -212,41 +254,100 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
     auto opaque = [](uint32_t x) { asm volatile("" : "+r"(x)); return x; };
     auto dsc64 = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
     const uint32_t mbar_u = __shfl_sync(0xffffffffu, mbar, 0);
-    uint32_t phase = 0;
-    float *stash = a.stash + ((size_t)blockIdx.x * X_THREADS + tid) * 32;
+    // mbarriers of the group: [0] per-edge products (six phases per tile), [1..3] the weight-gradient batches of stages
+    // 4 / 5 / 6 (one phase per tile each), waited only where their operand tiles are about to be overwritten
+    const uint32_t mbarA = mbar + 8 * XG, mbarB = mbar + 16 * XG, mbarC = mbar + 24 * XG;
+    const uint32_t mbarA_u = mbar_u + 8 * XG, mbarB_u = mbar_u + 16 * XG, mbarC_u = mbar_u + 24 * XG;
+    uint32_t phase = 0, phase_w = 0;
+    // per-thread scratch in L2 (dSiLU/dpre: chunks 0..7, LayerNorm uh: chunks 8..15), CHUNK-major: chunk i of thread t at
+    // (i * X_THREADS + t) * 16 bytes, so one warp-wide 128-bit access covers 512 contiguous bytes (4 L1 wavefronts; with a
+    // row per thread every access touched 32 lines and the stash alone was a third of the kernel's L1 wavefronts)
+    float *stash = a.stash + (size_t)blockIdx.x * X_THREADS * 64 + (size_t)tid * 4;
+    constexpr int SCH = X_THREADS * 4;          // floats between consecutive chunks of a thread
+    // row of this thread / rows this lane fills in the coalesced gather, inside a 128 x 128-byte tile
+    const uint32_t own_row = (uint32_t)(ht * 128), own_sw = (uint32_t)(ht & 7);
+    const uint32_t bufB_s = smem_u32(bufB), bufC_s = smem_u32(bufC);
 
     const int64_t E = __ldg(a.csr_ptr + a.num_nodes);
     const int64_t T = (E + 127) / 128;
     const int64_t NG = (int64_t)gridDim.x * XG, gi = (int64_t)blockIdx.x * XG + grp;
+#ifdef EGSPR_XB_SOLO      // developer experiment: only group 1 of every CTA works (uncontended per-stage latencies)
+    const int64_t tile0 = T * gi / NG, tile1 = grp == 1 ? T * (gi + 1) / NG : tile0;
+#else
     const int64_t tile0 = T * gi / NG, tile1 = T * (gi + 1) / NG;
-    for (int64_t tile = tile0; tile < tile1; ++tile) {
+#endif
+
+    // per-tile edge state, fetched ONE TILE AHEAD (indices at the top of the previous tile, coordinates in its middle)
+    struct EdgeIn { int r, c; int64_t ge; float ea; bool valid; float xr[3], xc[3], dxo[3]; };
+    auto load_indices = [&](int64_t tile, int &r_, int &c_, int &eid_, bool &valid_) {
         const int64_t p0 = tile * 128 + ht;
-        const bool valid = p0 < E;
-        const int64_t p = valid ? p0 : E - 1;          // idle slots redo the last edge with zero upstream gradient
-        const int r = __ldg(a.csr_row + p), c = __ldg(a.csr_col + p);
-        const int64_t ge = (int64_t)(r / a.n_per_cloud) * a.edges_per_cloud + __ldg(a.csr_eid + p);
-        const float ea = a.edge_attr ? __ldg(a.edge_attr + ge) : a.edge_attr_const;
-        float xr[3], xc[3], dxo[3] = {0.f, 0.f, 0.f};
-        {
-            const float4 t0 = ldg4(a.x4 + (int64_t)r * 4), t1 = ldg4(a.x4 + (int64_t)c * 4);
-            xr[0] = t0.x; xr[1] = t0.y; xr[2] = t0.z; xc[0] = t1.x; xc[1] = t1.y; xc[2] = t1.z;
+        valid_ = p0 < E;
+        const int64_t p = valid_ ? p0 : E - 1;          // idle slots redo the last edge with zero upstream gradient
+        r_ = ldg_now(a.csr_row + p); c_ = ldg_now(a.csr_col + p); eid_ = ldg_now(a.csr_eid + p);
+    };
+    auto load_coords = [&](EdgeIn &e, int eid_) {
+        e.ge = (int64_t)(e.r / a.n_per_cloud) * a.edges_per_cloud + eid_;
+        e.ea = a.edge_attr ? ldg_now(a.edge_attr + e.ge) : a.edge_attr_const;
+        const float4 t0 = ldg4_now(a.x4 + (int64_t)e.r * 4), t1 = ldg4_now(a.x4 + (int64_t)e.c * 4);
+        e.xr[0] = t0.x; e.xr[1] = t0.y; e.xr[2] = t0.z; e.xc[0] = t1.x; e.xc[1] = t1.y; e.xc[2] = t1.z;
+        e.dxo[0] = e.dxo[1] = e.dxo[2] = 0.f;
+        if (e.valid) {
+            e.dxo[0] = ldg_now(a.dx_out + (int64_t)e.r * 3); e.dxo[1] = ldg_now(a.dx_out + (int64_t)e.r * 3 + 1);
+            e.dxo[2] = ldg_now(a.dx_out + (int64_t)e.r * 3 + 2);
         }
-        if (valid) {
-            dxo[0] = __ldg(a.dx_out + (int64_t)r * 3); dxo[1] = __ldg(a.dx_out + (int64_t)r * 3 + 1); dxo[2] = __ldg(a.dx_out + (int64_t)r * 3 + 2);
+    };
+    EdgeIn nx;
+    nx.r = nx.c = 0; nx.valid = false;
+    if (tile0 < tile1) {
+        int eid0;
+        load_indices(tile0, nx.r, nx.c, eid0, nx.valid);
+        load_coords(nx, eid0);
+    }
+#ifdef EGSPR_XB_TIMING
+    int tile_no = -1;
+#endif
+    for (int64_t tile = tile0; tile < tile1; ++tile) {
+#ifdef EGSPR_XB_TIMING
+        ++tile_no;
+#endif
+        const EdgeIn cur = nx;
+        XB_MARK(0);
+        const int r = cur.r, c = cur.c;
+        const bool valid = cur.valid;
+        const int64_t ge = cur.ge;
+        // ---- this tile's P[row] / Q[col] rows -> shared memory with cp.async (no registers, a tile's worth of latency
+        // hidden behind the geometry): Q rows gathered COALESCED (8 lanes per 128-byte row) into tile C, P rows (few distinct
+        // rows per warp) copied by their own thread into tile B.  Both tiles were last read by the previous tile's
+        // stage-5 weight-gradient MMAs.
+        if (tile > tile0) { mbar_wait(mbarB, phase_w ^ 1); fence_after_sync(); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c_src = __shfl_sync(0xffffffffu, c, 4 * i + (lane >> 3));
+            const uint32_t row = (uint32_t)(hw * 32 + 4 * i + (lane >> 3));
+            cp_async16_cg(bufC_s + row * 128 + ((((uint32_t)lane & 7u) ^ (row & 7u)) << 4), a.Q + (int64_t)c_src * H + 4 * (lane & 7));
+            cp_async16_cg(bufB_s + own_row + (((uint32_t)i ^ own_sw) << 4), a.P + (int64_t)r * H + 4 * i);
         }
+        cp_async_commit();
+        int rn = 0, cn = 0, eidn = 0;
+        const bool more = tile + 1 < tile1;
+        if (more) load_indices(tile + 1, rn, cn, eidn, nx.valid);
         float dsc;                                      // d loss / d s  (trans = coord_diff * s, 3dm:264)
         // ---------------- stage 1: pre = P[row] + Q[col] + [geo | edge_attr] Wg^T ----------------
         {
             EdgeGeo g;
             float geo[16];
-            edge_geometry(xr, xc, g, geo);
-            geo[12] = ea; geo[13] = 0.f; geo[14] = 0.f; geo[15] = 0.f;
-            dsc = g.d[0] * dxo[0] + g.d[1] * dxo[1] + g.d[2] * dxo[2];
+            edge_geometry(cur.xr, cur.xc, g, geo);
+            geo[12] = cur.ea; geo[13] = 0.f; geo[14] = 0.f; geo[15] = 0.f;
+            dsc = g.d[0] * cur.dxo[0] + g.d[1] * cur.dxo[1] + g.d[2] * cur.dxo[2];
+            XB_MARK(1);
+            if (tile > tile0) { mbar_wait(mbarC, phase_w ^ 1); fence_after_sync(); }    // stage-6 batch of the previous tile read tile A
             write_row_split3(bufA, ht, geo);
         }
         fence_proxy_async();
         fence_before_sync();
+        XB_MARK(2);
         bar_sync(bar_id, 128);
+        XB_MARK(3);
         if (hw_u == 0 && elect_one()) {
             fence_after_sync();
             // geo terms (K-steps 0..2) x weight terms (offsets 0 / 32 / 64 B): all products down to 2^-24
@@ -260,51 +361,58 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             umma_commit(mbar_u);
         }
         float v[32];
-        {
-        float ds1[32];
-        {   // P[row] + Q[col] (bias folded in Q) while the tensor core works
-            const float *Pr = a.P + (int64_t)r * H, *Qc = a.Q + (int64_t)c * H;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 pv = ldg4(Pr + 4 * i), qv = ldg4(Qc + 4 * i);
-                ds1[4 * i] = pv.x + qv.x; ds1[4 * i + 1] = pv.y + qv.y; ds1[4 * i + 2] = pv.z + qv.z; ds1[4 * i + 3] = pv.w + qv.w;
-            }
-        }
+        cp_async_wait_all();
+        __syncwarp();                                   // the Q rows of this warp's edges were written by its other lanes
+        XB_MARK(4);
         mbar_wait(mbar, phase); phase ^= 1;
+        XB_MARK(5);
         fence_after_sync();
         tmem_ld32(tDw, v);
+        {
+            float ds1[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {               // a1 = SiLU(pre);  ds1 = d SiLU / d pre
-            fadd2(v[i], v[i + 1], ds1[i], ds1[i + 1]);
-            float s0, s1;
-            sigmoid2(v[i], v[i + 1], s0, s1);
-            ds1[i] = s0 * (1.0f + v[i] * (1.0f - s0)); ds1[i + 1] = s1 * (1.0f + v[i + 1] * (1.0f - s1));
-            fmul2(v[i], v[i + 1], s0, s1);
-        }
-        // dSiLU/dpre is needed again only in stage 5: parked in this thread's 128-byte slot of an L2-resident scratch
-        // (8 vector stores + 8 vector loads; keeping it in registers next to uh and the working row spilled ~180 words)
+            for (int i = 0; i < 8; ++i) {               // a1 = SiLU(pre);  ds1 = d SiLU / d pre
+                const float4 pv = *reinterpret_cast<const float4 *>(bufB + own_row + (((uint32_t)i ^ own_sw) << 4));
+                const float4 qv = *reinterpret_cast<const float4 *>(bufC + own_row + (((uint32_t)i ^ own_sw) << 4));
+                fadd2(v[4 * i], v[4 * i + 1], pv.x, pv.y); fadd2(v[4 * i + 2], v[4 * i + 3], pv.z, pv.w);
+                fadd2(v[4 * i], v[4 * i + 1], qv.x, qv.y); fadd2(v[4 * i + 2], v[4 * i + 3], qv.z, qv.w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            __stcg(reinterpret_cast<float4 *>(stash) + i, make_float4(ds1[4 * i], ds1[4 * i + 1], ds1[4 * i + 2], ds1[4 * i + 3]));
+                for (int j = 4 * i; j < 4 * i + 4; j += 2) {
+                    float s0, s1;
+                    sigmoid2(v[j], v[j + 1], s0, s1);
+                    ds1[j] = s0 * (1.0f + v[j] * (1.0f - s0)); ds1[j + 1] = s1 * (1.0f + v[j + 1] * (1.0f - s1));
+                    fmul2(v[j], v[j + 1], s0, s1);
+                }
+            }
+            // dSiLU/dpre is needed again only in stage 5: parked in this thread's 128-byte slot of an L2-resident scratch
+            // (8 vector stores + 8 vector loads; keeping it in registers next to uh and the working row spilled ~180 words)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                __stcg(reinterpret_cast<float4 *>(stash + i * SCH), make_float4(ds1[4 * i], ds1[4 * i + 1], ds1[4 * i + 2], ds1[4 * i + 3]));
         }
         // ---------------- stage 2: u = a1 W2^T + b2 (block diagonal), m = LayerNorm(u) ----------------
+        XB_MARK(6);
         write_row_split2(bufB, ht, v);
         fence_proxy_async();
         fence_before_sync();
+        XB_MARK(7);
         bar_sync(bar_id, 128);
+        XB_MARK(8);
         if (hw_u == 1 && elect_one()) {
             fence_after_sync();
             const uint32_t gB = opaque(g_lo) + O_B, w2 = opaque(w_lo) + O_W2;
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) umma_bf16_ss(tD, dsc64(gB + 2 * j), dsc64(w2 + 4 * q + 2 * (j & 1)), ID_KK_N32, (q | j) > 0);
+                for (int j = 0; j < 4 - 2 * q; ++j) umma_bf16_ss(tD, dsc64(gB + 2 * j), dsc64(w2 + 4 * q + 2 * (j & 1)), ID_KK_N32, (q | j) > 0);
             umma_commit(mbar_u);
         }
+        if (more) { nx.r = rn; nx.c = cn; load_coords(nx, eidn); }      // the next tile's coordinates (its indices have arrived)
         mbar_wait(mbar, phase); phase ^= 1;
+        XB_MARK(9);
         fence_after_sync();
         tmem_ld32(tDw, v);
-        float uh[32], rstd;
+        float rstd;
         {
             float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -325,27 +433,31 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             for (int j = 0; j < 32; j += 4) {
                 const float4 gm = *reinterpret_cast<const float4 *>(slng + j), bt = *reinterpret_cast<const float4 *>(spar + 64 + j);
                 fmul2(v[j], v[j + 1], rstd, rstd); fmul2(v[j + 2], v[j + 3], rstd, rstd);
-                uh[j] = v[j]; uh[j + 1] = v[j + 1]; uh[j + 2] = v[j + 2]; uh[j + 3] = v[j + 3];
+                __stcg(reinterpret_cast<float4 *>(stash + (8 + j / 4) * SCH), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));   // uh: needed again in stage 4
                 float o0 = bt.x, o1 = bt.y, o2 = bt.z, o3 = bt.w;
                 ffma2(o0, o1, v[j], v[j + 1], gm.x, gm.y); ffma2(o2, o3, v[j + 2], v[j + 3], gm.z, gm.w);
                 v[j] = o0; v[j + 1] = o1; v[j + 2] = o2; v[j + 3] = o3;
             }
         }
         // ---------------- stage 3: c = m Wc1^T + bc1, s = wc2 . SiLU(c) ----------------
+        XB_MARK(10);
         write_row_split2(bufC, ht, v);
         fence_proxy_async();
         fence_before_sync();
+        XB_MARK(11);
         bar_sync(bar_id, 128);
+        XB_MARK(12);
         if (hw_u == 2 && elect_one()) {
             fence_after_sync();
             const uint32_t gC = opaque(g_lo) + O_C, wc = opaque(w_lo) + O_WC1;
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) umma_bf16_ss(tD, dsc64(gC + 2 * j), dsc64(wc + 4 * q + 2 * (j & 1)), ID_KK_N32, (q | j) > 0);
+                for (int j = 0; j < 4 - 2 * q; ++j) umma_bf16_ss(tD, dsc64(gC + 2 * j), dsc64(wc + 4 * q + 2 * (j & 1)), ID_KK_N32, (q | j) > 0);
             umma_commit(mbar_u);
         }
         mbar_wait(mbar, phase); phase ^= 1;
+        XB_MARK(13);
         fence_after_sync();
         tmem_ld32(tDw, v);
         float s = 0.f;
@@ -355,11 +467,12 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
                 const int o = hb + i;
-                fadd2(v[o], v[o + 1], sbc1[o], sbc1[o + 1]);
+                const float2 bc = *reinterpret_cast<const float2 *>(sbc1 + o), wc2v = *reinterpret_cast<const float2 *>(swc2 + o);
+                fadd2(v[o], v[o + 1], bc.x, bc.y);
                 float s0, s1;
                 sigmoid2(v[o], v[o + 1], s0, s1);
                 const float a20 = v[o] * s0, a21 = v[o + 1] * s1;
-                const float w0 = swc2[o], w1 = swc2[o + 1];
+                const float w0 = wc2v.x, w1 = wc2v.y;
                 s = fmaf(w0, a20, s); s = fmaf(w1, a21, s);
                 t[i] = a20 * dsc; t[i + 1] = a21 * dsc;
                 v[o] = w0 * dsc * (s0 * (1.0f + v[o] * (1.0f - s0)));
@@ -368,11 +481,14 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             tmem_add16(tPriv + 32 + hb, t);
         }
         // ---------------- stage 4: dm = dagg[row] + dc1 Wc1;  dWc1 += dc1^T m, dbc1 += dc1^T 1 ----------------
+        XB_MARK(14);
         write_row_split2(bufD, ht, v);
         tmem_wait_st();
         fence_proxy_async();
         fence_before_sync();
+        XB_MARK(15);
         bar_sync(bar_id, 128);
+        XB_MARK(16);
         if (hw_u == 3 && elect_one()) {
             fence_after_sync();
             const uint32_t gD = opaque(g_lo) + O_D, gC = opaque(g_lo) + O_C, wc = opaque(w_lo) + O_WC1;
@@ -380,24 +496,34 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) umma_bf16_ss(tD, dsc64(gD + 2 * j), dsc64(wc + 4 * q + 128 * (j & 1)), ID_KM_N32, (q | j) > 0);
+                for (int j = 0; j < 4 - 2 * q; ++j) umma_bf16_ss(tD, dsc64(gD + 2 * j), dsc64(wc + 4 * q + 128 * (j & 1)), ID_KM_N32, (q | j) > 0);
+            umma_commit(mbar_u);
+#ifndef EGSPR_XB_NO_WG
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 umma_bf16_ss(tWG + XW_WC1, dsc64(gD + 128 * j), dsc64(gC + 128 * j), ID_MM_N32, 1);
                 umma_bf16_ss(tWG + XW_WC1, dsc64(gD + 128 * j), dsc64(gC + 4 + 128 * j), ID_MM_N32, 1);
                 umma_bf16_ss(tWG + XW_BC1, dsc64(gD + 128 * j), ones, ID_MK_N8, 1);
             }
-            umma_commit(mbar_u);
+#endif
+            umma_commit(mbarA_u);
         }
         {   // upstream message gradient while the tensor core works (zero for idle slots)
             const float *dg = a.dagg + (int64_t)r * H;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 t = valid ? ldg4(dg + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 t = valid ? ldg4_now(dg + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
             }
         }
+        float uh[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t = ldcg4_now(stash + (8 + i) * SCH);
+            uh[4 * i] = t.x; uh[4 * i + 1] = t.y; uh[4 * i + 2] = t.z; uh[4 * i + 3] = t.w;
+        }
         mbar_wait(mbar, phase); phase ^= 1;
+        XB_MARK(17);
         fence_after_sync();
 #pragma unroll
         for (int hb = 0; hb < 32; hb += 16) {
@@ -417,7 +543,8 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             float s1a[2] = {0.f, 0.f}, s2a[2] = {0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-                fmul2(v[i], v[i + 1], slng[i], slng[i + 1]);
+                const float2 gmv = *reinterpret_cast<const float2 *>(slng + i);
+                fmul2(v[i], v[i + 1], gmv.x, gmv.y);
                 fadd2(s1a[0], s1a[1], v[i], v[i + 1]);
                 ffma2(s2a[0], s2a[1], v[i], v[i + 1], uh[i], uh[i + 1]);
             }
@@ -426,11 +553,16 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             for (int i = 0; i < 32; ++i) v[i] = rstd * (v[i] - s1 - uh[i] * s2);
         }
         // ---------------- stage 5: da1 = du W2;  dW2 += du^T a1, db2 += du^T 1 ----------------
+        XB_MARK(18);
+        mbar_wait(mbarA, phase_w); fence_after_sync();          // the stage-4 batch read m in tile C
+        XB_MARK(19);
         write_row_split2(bufC, ht, v);
         tmem_wait_st();
         fence_proxy_async();
         fence_before_sync();
+        XB_MARK(20);
         bar_sync(bar_id, 128);
+        XB_MARK(21);
         if (hw_u == 0 && elect_one()) {
             fence_after_sync();
             const uint32_t gC = opaque(g_lo) + O_C, gB = opaque(g_lo) + O_B, w2 = opaque(w_lo) + O_W2;
@@ -438,19 +570,23 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) umma_bf16_ss(tD, dsc64(gC + 2 * j), dsc64(w2 + 4 * q + 128 * (j & 1)), ID_KM_N32, (q | j) > 0);
+                for (int j = 0; j < 4 - 2 * q; ++j) umma_bf16_ss(tD, dsc64(gC + 2 * j), dsc64(w2 + 4 * q + 128 * (j & 1)), ID_KM_N32, (q | j) > 0);
+            umma_commit(mbar_u);
+#ifndef EGSPR_XB_NO_WG
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 umma_bf16_ss(tWG + XW_W2, dsc64(gC + 128 * j), dsc64(gB + 128 * j), ID_MM_N32, 1);
                 umma_bf16_ss(tWG + XW_W2, dsc64(gC + 128 * j), dsc64(gB + 4 + 128 * j), ID_MM_N32, 1);
                 umma_bf16_ss(tWG + XW_B2, dsc64(gC + 128 * j), ones, ID_MK_N8, 1);
             }
-            umma_commit(mbar_u);
+#endif
+            umma_commit(mbarB_u);
         }
         float4 dsv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dsv[i] = __ldcg(reinterpret_cast<const float4 *>(stash) + i);
+        for (int i = 0; i < 8; ++i) dsv[i] = ldcg4_now(stash + i * SCH);
         mbar_wait(mbar, phase); phase ^= 1;
+        XB_MARK(22);
         fence_after_sync();
         tmem_ld32(tDw, v);
 #pragma unroll
@@ -458,119 +594,166 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             fmul2(v[4 * i], v[4 * i + 1], dsv[i].x, dsv[i].y); fmul2(v[4 * i + 2], v[4 * i + 3], dsv[i].z, dsv[i].w);
         }
         // ---------------- stage 6: d geo = dpre Wg;  dWg += dpre^T [geo | edge_attr] ----------------
+        // (tile D: its stage-4 readers finished before the stage-5 products that were just waited for)
+        XB_MARK(23);
         write_row_split2(bufD, ht, v);
         fence_proxy_async();
         fence_before_sync();
+        XB_MARK(24);
         bar_sync(bar_id, 128);
+        XB_MARK(25);
         if (hw_u == 1 && elect_one()) {
             fence_after_sync();
             const uint32_t gD = opaque(g_lo) + O_D, ga = opaque(g_lo) + O_A, wg = opaque(w_lo) + O_WG;
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) umma_bf16_ss(tD, dsc64(gD + 2 * j), dsc64(wg + 2 * q + 128 * (j & 1)), ID_KM_N16, (q | j) > 0);
+                for (int j = 0; j < 4 - 2 * q; ++j) umma_bf16_ss(tD, dsc64(gD + 2 * j), dsc64(wg + 2 * q + 128 * (j & 1)), ID_KM_N16, (q | j) > 0);
+            umma_commit(mbar_u);
+#ifndef EGSPR_XB_NO_WG
 #pragma unroll
             for (int j = 0; j < 8; ++j)
 #pragma unroll
                 for (int q = 0; q < 3; ++q) umma_bf16_ss(tWG + XW_WGEO, dsc64(gD + 128 * j), dsc64(ga + 2 * q + 128 * j), ID_MM_N16, 1);
-            umma_commit(mbar_u);
+#endif
+            umma_commit(mbarC_u);
         }
-        if (valid) {    // dpre = the gradient of P[row] and of Q[col], by ORIGINAL edge id
-            float *dp = a.dpre + ge * H;
+        {   // dpre = the gradient of P[row] and of Q[col], by ORIGINAL edge id.  Written COALESCED: 8 lanes per 128-byte
+            // row (4 full rows per warp-wide store) out of the b0 + b1 terms this warp just wrote to tile D (16 mantissa
+            // bits) -- a row per thread touched 32 lines per store instruction.
+            const int64_t ge_w = valid ? ge : (int64_t)-1;
+            const int j = lane & 7;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4 *>(dp + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int it = 0; it < 8; ++it) {
+                // rows of one instruction: two with (row & 4) == 0 and two with (row & 4) != 0, so that their swizzled 64-byte
+                // halves cover all 32 banks (rows 4 it .. 4 it + 3 all landed on the same 16 banks: 4-way conflicts)
+                const int rl = 8 * (it >> 1) + 2 * (it & 1) + ((lane >> 3) & 1) + 4 * (lane >> 4);
+                const long long ge_s = __shfl_sync(0xffffffffu, ge_w, rl);
+                const int row = hw * 32 + rl;
+                const uint8_t *rp = bufD + row * 128 + (j & 1) * 8;
+                const uint2 t0 = *reinterpret_cast<const uint2 *>(rp + (((j >> 1) ^ (row & 7)) << 4));
+                const uint2 t1 = *reinterpret_cast<const uint2 *>(rp + ((((j >> 1) + 4) ^ (row & 7)) << 4));
+                float4 o;
+                o.x = __uint_as_float(t0.x << 16) + __uint_as_float(t1.x << 16);
+                o.y = __uint_as_float(t0.x & 0xffff0000u) + __uint_as_float(t1.x & 0xffff0000u);
+                o.z = __uint_as_float(t0.y << 16) + __uint_as_float(t1.y << 16);
+                o.w = __uint_as_float(t0.y & 0xffff0000u) + __uint_as_float(t1.y & 0xffff0000u);
+                if (ge_s >= 0) *reinterpret_cast<float4 *>(a.dpre + ge_s * H + 4 * j) = o;
+            }
         }
         mbar_wait(mbar, phase); phase ^= 1;
+        XB_MARK(26);
         fence_after_sync();
         {
             float gg[16];
             tmem_ld16(tDw, gg);
             EdgeGeo g;
             float geo[12];
-            edge_geometry(xr, xc, g, geo);
-            const float gde[3] = {s * dxo[0], s * dxo[1], s * dxo[2]};
+            edge_geometry(cur.xr, cur.xc, g, geo);
+            const float gde[3] = {s * cur.dxo[0], s * cur.dxo[1], s * cur.dxo[2]};
             float dxr[3], dxc[3];
-            edge_geometry_backward(xr, xc, g, gg, gde, dxr, dxc);
+            edge_geometry_backward(cur.xr, cur.xc, g, gg, gde, dxr, dxc);
             if (valid) {
                 *reinterpret_cast<float4 *>(a.dxe + ge * 8) = make_float4(dxr[0], dxr[1], dxr[2], 0.f);
                 *reinterpret_cast<float4 *>(a.dxe + ge * 8 + 4) = make_float4(dxc[0], dxc[1], dxc[2], 0.f);
             }
         }
+        XB_MARK(27);
+        phase_w ^= 1;
         fence_before_sync();        // the tcgen05.ld above is ordered before the next tile's first MMA by its barrier
+    }
+    if (tile0 < tile1) {            // the last tile's weight-gradient batches
+        mbar_wait(mbarB, phase_w ^ 1);
+        mbar_wait(mbarC, phase_w ^ 1);
+        fence_after_sync();
     }
 
     // ---- epilogue: private sums and the weight-gradient accumulators -> gradient pack ----
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    float *red = reinterpret_cast<float *>(base + XS_GRP);        // tiles are free: 2592 floats of CTA partial sums
-    constexpr int R_WC1 = 0, R_W2 = 1024, R_WG = 2048, R_BC1 = 2560, R_B2 = 2592, R_LNG = 2624, R_WC2 = 2656, R_N = 2688;
-    for (int i = tid; i < R_N; i += X_THREADS) red[i] = 0.f;
-    __syncthreads();
+    // every (group, b0 / b1 term) writes its accumulator rows to its own slot, the slots are summed on the way out
+    float *red = reinterpret_cast<float *>(base + XS_GRP);        // tiles are free now
+    constexpr int R_WC1 = 0, R_W2 = 1024, R_WG = 2048, R_BC1 = 2560, R_B2 = 2592, R_N = 2624, R_SLOTS = 2 * XG;
+    float *colp = red + R_SLOTS * R_N;                            // [warps][64]: d ln gamma | d wc2 column sums per warp
     {
         float t[32];
         tmem_ld32(tPriv, t);
         const float cs0 = warp_colsum32(t);
         tmem_ld32(tPriv + 32, t);
         const float cs1 = warp_colsum32(t);
-        atomicAdd(red + R_LNG + lane, cs0);
-        atomicAdd(red + R_WC2 + lane, cs1);
+        colp[(tid >> 5) * 64 + lane] = cs0;
+        colp[(tid >> 5) * 64 + 32 + lane] = cs1;
     }
     {
         // M = 64 accumulator layout: row m = 16 * warp + (lane & 15), at lanes 0..15 of every warp quarter (group 1: 16..31);
-        // rows 0..31 = b0 term of feature m, rows 32..63 = b1 term of feature m - 32: both add into the same entry
+        // rows 0..31 = b0 term of feature m, rows 32..63 = b1 term of feature m - 32
         const bool mine = ((lane >> 4) == (grp == 1 ? 1 : 0));
-        const int feat = (16 * hw + (lane & 15)) & 31;
+        const int m = 16 * hw + (lane & 15), feat = m & 31;
+        float *slot = red + (2 * grp + (m >> 5)) * R_N;
         const uint32_t tw = tmem0 + XT_WG + (grp == 2 ? 96u : 0u) + lane_base;
         float t[32];
         tmem_ld32(tw + XW_WC1, t);
         if (mine) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(red + R_WC1 + 32 * feat + i, t[i]);                 // dWc1[o = feat][i]
+            for (int i = 0; i < 32; i += 4)                                                   // dWc1[o = feat][i]
+                *reinterpret_cast<float4 *>(slot + R_WC1 + 32 * feat + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
         }
         tmem_ld32(tw + XW_W2, t);
         if (mine) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if ((i >> 3) == (feat >> 3)) atomicAdd(red + R_W2 + 64 * (feat >> 3) + 8 * (i & 7) + (feat & 7), t[i]);   // [head][in][out]
+            for (int i = 0; i < 32; ++i) slot[R_W2 + 32 * feat + i] = t[i];                  // full 32 x 32, block diagonal picked below
         }
         tmem_ld32(tw + XW_WGEO, t);          // 16 geo columns | dbc1 (8 equal columns) | db2 (8 equal columns)
         if (mine) {
 #pragma unroll
-            for (int k = 0; k < 13; ++k) atomicAdd(red + R_WG + 32 * k + feat, t[k]);                  // rows of Wg, row 12 = edge_attr
-            atomicAdd(red + R_BC1 + feat, t[16]);
-            atomicAdd(red + R_B2 + feat, t[24]);
+            for (int k = 0; k < 16; ++k) slot[R_WG + 32 * k + feat] = t[k];                  // rows of Wg, row 12 = edge_attr
+            slot[R_BC1 + feat] = t[16];
+            slot[R_B2 + feat] = t[24];
         }
     }
     fence_before_sync();
     __syncthreads();
     for (int i = tid; i < R_N; i += X_THREADS) {
-        const float val = red[i];
-        int dst;
+        float val = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < R_SLOTS; ++sl) val += red[sl * R_N + i];
+        int dst = -1;
         if (i < R_W2) dst = OFF_WC1 + i;
-        else if (i < R_WG) dst = OFF_W2P + (i - R_W2);
-        else if (i < R_WG + 384) dst = OFF_WG + (i - R_WG);
+        else if (i < R_WG) {                                   // dW2[o][i2] -> pack [head][in][out], same-head entries only
+            const int o = (i - R_W2) >> 5, i2 = (i - R_W2) & 31;
+            if ((o >> 3) == (i2 >> 3)) dst = OFF_W2P + 64 * (o >> 3) + 8 * (i2 & 7) + (o & 7);
+        } else if (i < R_WG + 384) dst = OFF_WG + (i - R_WG);
         else if (i < R_WG + 416) dst = OFF_WEA + (i - R_WG - 384);
-        else if (i < R_BC1) continue;                        // geo rows 13..15 are padding
-        else if (i < R_B2) dst = OFF_BC1 + (i - R_BC1);
-        else if (i < R_LNG) dst = OFF_B2 + (i - R_B2);
-        else if (i < R_WC2) dst = OFF_LNG + (i - R_LNG);
-        else dst = OFF_WC2 + (i - R_WC2);
-        if (i >= R_W2 && i < R_WG && (i - R_W2) >= 256) continue;     // dW2P has 4 x 8 x 8 = 256 entries
-        atomicAdd(a.gpack + dst, val);
+        else if (i < R_BC1) dst = -1;                          // geo rows 13..15 are padding
+        else if (i < R_B2) { dst = OFF_BC1 + (i - R_BC1); red[i] = val; }      // kept for the d ln beta product below
+        else dst = OFF_B2 + (i - R_B2);
+        if (dst >= 0) atomicAdd(a.gpack + dst, val);
     }
+    if (tid < 64) {
+        float val = 0.f;
+#pragma unroll
+        for (int w = 0; w < X_THREADS / 32; ++w) val += colp[w * 64 + tid];
+        atomicAdd(a.gpack + (tid < 32 ? OFF_LNG + tid : OFF_WC2 + tid - 32), val);
+    }
+    __syncthreads();
     if (tid < 32) {      // d ln beta, coord-MLP part: (sum_e dc1_e) Wc1  (the dagg part comes from node_mlp_backward_kernel)
         float acc = 0.f;
 #pragma unroll 8
-        for (int o = 0; o < 32; ++o) acc = fmaf(red[R_BC1 + o], swc1f[32 * o + tid], acc);
+        for (int o = 0; o < 32; ++o) acc = fmaf(red[R_BC1 + o], swc1f[32 * o + tid], acc);     // slot 0 now holds the CTA total
         atomicAdd(a.gpack + OFF_LNB + tid, acc);
     }
     __syncthreads();
     if (tid < 32) tmem_dealloc(tmem0, 512);
 }
 
-size_t edge_backward_tc_stash_bytes() { return (size_t)sm_count() * X_THREADS * 32 * sizeof(float); }
+size_t edge_backward_tc_stash_bytes() { return (size_t)sm_count() * X_THREADS * 64 * sizeof(float); }
+
+#ifdef EGSPR_XB_TIMING
+extern "C" int egspr_debug_read_xb(long long *host_dst) {
+    return cudaMemcpyFromSymbol(host_dst, g_xb_dbg, sizeof(long long) * 4 * 64 * 32) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 int launch_edge_backward_tc(const EdgeBwdArgs &a, cudaStream_t st) {
     if (!opt_in_smem(edge_backward_tc_kernel, X_SMEM_BYTES)) return EGSPR_E_LAUNCH;
