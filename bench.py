@@ -348,11 +348,22 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
     barrier()
     ms = max(max_over_ranks(e0.elapsed_time(e1), dev), max_over_ranks((time.perf_counter() - t0) * 1e3, dev)) / steps
     finite = bool(torch.isfinite(loss).item())
+    # the replicas must hold bit-identical parameters after the all-reduced updates (checked on every run with N > 1)
+    replicas_identical = None
+    if world > 1:
+        import torch.distributed as dist
+        chk = torch.cat([p.detach().flatten() for p in model.parameters()]).double().sum().reshape(1)
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_identical = all(c.item() == allc[0].item() for c in allc)
+        if not replicas_identical:
+            raise RuntimeError(f"data-parallel replicas diverged: parameter checksums {[c.item() for c in allc]}")
     cpu = cpu_train_baseline() if rank == 0 else None
     return {"workload": "BASELINE configs[3]: 3DMatch training step, fwd + bwd + Adam, 16 pairs/GPU x 2 clouds x 2048 pts, "
                         "k-NN graph build included; gradient all-reduce (one flat fp32 bucket, NCCL) when n_gpus > 1",
             "pairs_per_gpu": B, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": "pairs/s (training)",
-            "steps": steps, "loss_finite": finite, "embedding_out_scale": TRAIN_TEMPER, "launch_mode": mode, "cpu_baseline": cpu}
+            "steps": steps, "loss_finite": finite, "replicas_identical": replicas_identical, "embedding_out_scale": TRAIN_TEMPER,
+            "launch_mode": mode, "cpu_baseline": cpu}
 
 
 def cpu_train_baseline(pairs=2, reps=2):

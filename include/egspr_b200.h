@@ -203,6 +203,35 @@ int egspr_head_train_backward(const float *h_out_src, const float *h_out_tgt, co
                               const float *dsim, int pairs, int n, float *dh_src, float *dh_tgt,
                               float *dx_src, float *dx_tgt, void *stream);
 
+/* ---- 8(f).2: the training losses of one batch on the device.  After egspr_head_train (which leaves sim [pairs][n]):
+ * egspr_train_loss_forward, one CTA per pair (src/3dmatch_train_egnn_with_batch.py:681-694, 760-773):
+ *   top_idx [pairs][top_k]  members of torch.topk(sim, top_k) (the k largest, ties -> lower index; UNORDERED -- every
+ *                           consumer is a mean over the set; -1 past min(top_k, n)),
+ *   scores  [pairs][top_k]  mlp([h_out_src | h_out_tgt][top_idx]) logits (3dm:760-768),
+ *   bce     [pairs]         sum over the pair's rows of BCEWithLogits(score, labels[top_idx]) (3dm:772),
+ *   raw     [pairs][n]      <feat_src, feat_tgt> (3dm:773),
+ *   stats   [pairs][4]      fp64 sums of sim, sim^2, raw, raw^2 (the z-scores of 3dm:776-777 use batch-wide statistics).
+ * egspr_train_loss_finalize, one CTA: loss[0..4] = corr_loss (mean BCE), sim_loss = MSE(zscore(sim), zscore(raw))
+ * (unbiased std, +1e-6), mean rot_loss, mean trans_loss (pose_loss 3dm:896-962; 0 when R is null), and their sum =
+ * the loop's total (3dm:1118); loss[7] = scale.  Optional seeds of the backward pass, all multiplied by `scale` (the
+ * upstream gradient, e.g. 1 / world size): dsim [pairs][n] = d sim_loss / d sim, dR [pairs][9] / dt [pairs][3] =
+ * d (mean rot + mean trans) / d (R, t).
+ * egspr_head_train_loss_backward = egspr_head_train_backward plus the backward of the mean BCE through mlp: adds
+ * d corr_loss / d h_out rows into dh_src / dh_tgt at top_idx and accumulates d corr_loss / d mlp into
+ * head_grad_pack [EGSPR_HEAD_PACK_FLOATS] (atomics; zero it first).  `loss` = the finalize kernel's output (scale). */
+int egspr_train_loss_forward(const float *h_out_src, const float *h_out_tgt, const float *feat_src,
+                             const float *feat_tgt, const float *sim, const float *labels, const float *head_pack,
+                             int pairs, int n, int top_k, int32_t *top_idx, float *scores, float *raw,
+                             double *stats, float *bce, void *stream);
+int egspr_train_loss_finalize(const float *sim, const float *raw, const double *stats, const float *bce, int pairs,
+                              int n, int top_k, const float *R, const float *t, const float *gt_pose, float scale,
+                              float *loss, float *dsim, float *dR, float *dt, void *stream);
+int egspr_head_train_loss_backward(const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                                   const float *x_out_tgt, const float *labels, const float *dR, const float *dt,
+                                   const float *dsim, const int32_t *top_idx, const float *head_pack,
+                                   const float *loss, int pairs, int n, int top_k, float *dh_src, float *dh_tgt,
+                                   float *dx_src, float *dx_tgt, float *head_grad_pack, void *stream);
+
 /* ---- a16: pose_loss(pred_rot, pred_translation, gt_pose) 3dm:896-962 (the two returned losses): per pair
  * rot_loss = acos(clamp((trace(R^T R_gt) - 1) / 2, -1, 1)), trans_loss = acos(clamp(cos(t, t_gt), -1, 1)), and
  * (optional) their gradients grad_R [pairs][9] = d rot_loss / d R, grad_t [pairs][3] = d trans_loss / d t, so that

@@ -14,9 +14,10 @@ from .engine import RegistrationEngine  # noqa: F401
 from . import train  # noqa: F401
 
 
-def build_model(checkpoint=None, device="cuda:0", n_layers=3, variant=None):
+def build_model(checkpoint=None, device="cuda:0", n_layers=3, variant="eval"):
     """EGNN(32,32,32,in_edge_nf=1,n_layers=3) + CrossAttentionPoseRegression(hidden_nf=32), the
-    configuration of the reference scripts (src/eval_egnn_metrics.py:1371-1375)."""
+    configuration of the reference scripts (src/eval_egnn_metrics.py:1371-1375).  variant: 'eval' = the class of the
+    evaluation script (default here: the inference engine), 'train' = the class of the training scripts."""
     egnn = EGNN(32, 32, 32, in_edge_nf=1, device=device, n_layers=n_layers)
     model = CrossAttentionPoseRegression(egnn, num_nodes=2048, hidden_nf=32, device=device, variant=variant).to(device)
     if checkpoint is not None:

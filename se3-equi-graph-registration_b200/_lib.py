@@ -47,6 +47,9 @@ SIGNATURES = {
     "egspr_linear32_backward": (_i, [_p, _p, _l, _p, _p, _p, _p]),
     "egspr_head_train_backward": (_i, [_p] * 8 + [_i, _i] + [_p] * 5),
     "egspr_pose_loss": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "egspr_train_loss_forward": (_i, [_p] * 7 + [_i, _i, _i] + [_p] * 6),
+    "egspr_train_loss_finalize": (_i, [_p] * 4 + [_i, _i, _i] + [_p] * 3 + [_f] + [_p] * 5),
+    "egspr_head_train_loss_backward": (_i, [_p] * 11 + [_i, _i, _i] + [_p] * 6),
 }
 
 

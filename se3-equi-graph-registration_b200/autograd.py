@@ -128,3 +128,36 @@ class EquiLossFunction(torch.autograd.Function):
             loss = ctx.loss_fn(leaves[0], leaves[1], leaves[2], leaves[3], R_gt, t_gt, labels_f)
             grads = torch.autograd.grad(loss, leaves, g)
         return (None, *grads, None, None, None, None)
+
+
+class CorrSimLossFunction(torch.autograd.Function):
+    """corr_loss + sim_loss (slot 2 of the train-variant forward, 3dm:681-694, 760-781) as two kernels
+    (egspr_train_loss_forward / _finalize); backward = the mean-BCE backward through mlp (egspr_head_train_loss_backward
+    with zero pose seeds) and the closed-form gradient of the z-scored similarity MSE.
+    (hs, ht, feat_src, feat_tgt, sim, labels_f, *mlp parameters) -> scalar; gradients flow to hs, ht, sim and mlp."""
+
+    @staticmethod
+    def forward(ctx, spec, hs, ht, fs, ft, sim, labels_f, *mlp_params):
+        head_pack, top_k, mlp = spec
+        top_idx, scores, raw, stats, bce = ops.train_loss_forward(hs, ht, fs, ft, sim, labels_f, head_pack, top_k)
+        loss, dsim, _, _ = ops.train_loss_finalize(sim, raw, stats, bce, top_k, scale=1.0, need_grad=True)
+        ctx.save_for_backward(hs, ht, labels_f, top_idx, dsim, loss)
+        ctx.spec = spec
+        ctx.aux = {"top_idx": top_idx, "scores": scores, "loss": loss}
+        return loss[0] + loss[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        hs, ht, labels_f, top_idx, dsim, loss = ctx.saved_tensors
+        head_pack, top_k, mlp = ctx.spec
+        B, n, _ = hs.shape
+        lvec = loss.clone()
+        lvec[7] = g                                           # upstream gradient, read by the kernel from device memory
+        zR = torch.zeros((B, 3, 3), dtype=torch.float32, device=hs.device)
+        zt = torch.zeros((B, 3), dtype=torch.float32, device=hs.device)
+        zx = torch.zeros((B, n, 3), dtype=torch.float32, device=hs.device)
+        gp = torch.zeros(packing.HEAD_PACK, dtype=torch.float32, device=hs.device)
+        # zero pose seeds: the Kabsch part of the kernel contributes nothing, only the BCE-through-mlp part remains
+        dhs, dht, _, _ = ops.head_train_loss_backward(hs, ht, zx, zx, labels_f, zR, zt, None, top_idx, head_pack, lvec, gp, top_k)
+        grads = _unpacker(mlp, packing.unpack_head_grad, packing.HEAD_PACK)(gp)
+        return (None, dhs, dht, None, None, dsim * g, None, *grads)

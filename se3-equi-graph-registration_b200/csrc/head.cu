@@ -6,8 +6,6 @@
 //   train variant src/3dmatch_train_egnn_with_batch.py:696-758 (softmax of output-feature similarity
 //                 over the GT inliers, Kabsch on the EGNN coords)
 // and the cuSOLVER launch + `if det<0` host sync per pair (:741-751) with an in-kernel fp64 Jacobi SVD.
-#include <cstdlib>
-
 #include "egspr_common.cuh"
 
 namespace egspr {
@@ -498,7 +496,35 @@ struct HeadTrainBwdArgs {
     const float *h_out_src, *h_out_tgt, *x_out_src, *x_out_tgt, *labels, *dR, *dt, *dsim;
     int n;
     float *dh_src, *dh_tgt, *dx_src, *dx_tgt;
+    // optional: backward of the correspondence BCE (3dm:760-772) through mlp into the top-k rows and the head pack
+    const int32_t *top_idx;     // [pairs][k] or null
+    const float *head_pack;
+    float *head_gpack;
+    int k, pairs;
+    const float *corr_scale;    // device scalar: upstream gradient of the mean BCE (loss[7] of egspr_train_loss_finalize)
 };
+
+// mlp 64 -> 32 -> 16 -> 1 (3dm:594-600) on one row [zs | zt], one warp: lane = output unit.  w = head pack (shared memory).
+struct MlpRow { float h0, h1, score; };      // post-ReLU activations of this lane's unit (h1: lanes < 16)
+__device__ __forceinline__ MlpRow mlp_row(const float *__restrict__ w, float zs, float zt, int lane) {
+    MlpRow r;
+    float h0 = w[HOFF_B0 + lane];
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) h0 = fmaf(w[HOFF_W0T + 32 * i + lane], __shfl_sync(0xffffffffu, zs, i), h0);
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) h0 = fmaf(w[HOFF_W0T + 32 * (32 + i) + lane], __shfl_sync(0xffffffffu, zt, i), h0);
+    r.h0 = fmaxf(h0, 0.f);
+    float h1 = lane < 16 ? w[HOFF_B1 + lane] : 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+        const float v = __shfl_sync(0xffffffffu, r.h0, i);
+        if (lane < 16) h1 = fmaf(w[HOFF_W1T + 16 * i + lane], v, h1);
+    }
+    r.h1 = fmaxf(h1, 0.f);
+    float pr = lane < 16 ? r.h1 * w[HOFF_W2 + lane] : 0.f;
+    r.score = warp_sum(pr) + w[HOFF_B2];
+    return r;
+}
 
 __global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(const HeadTrainBwdArgs a) {
     extern __shared__ __align__(16) float dyn[];
@@ -655,6 +681,273 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(con
         *reinterpret_cast<float4 *>(a.dh_src + (nb + i) * H + 4 * lane8) = make_float4(ds * ht.x, ds * ht.y, ds * ht.z, ds * ht.w);
         *reinterpret_cast<float4 *>(a.dh_tgt + (nb + i) * H + 4 * lane8) = make_float4(ds * hs.x, ds * hs.y, ds * hs.z, ds * hs.w);
     }
+    if (!a.top_idx) return;
+    // ---- correspondence loss backward (3dm:760-772): BCEWithLogits(mlp([h_s | h_t][top-k]), labels[top-k]), mean over
+    // pairs * k.  One warp per selected row: recompute the mlp, push d score back through it into the row of dh_src /
+    // dh_tgt (rows of this pair: written above by this CTA) and into the head-pack gradient (shared-memory partial sums,
+    // one atomicAdd per entry and CTA). ----
+    __threadfence_block();
+    __syncthreads();
+    float *swp = dyn;                       // head pack [HEAD_PACK] | its gradient [HEAD_PACK]  (2 n >= 2 * HEAD_PACK is checked on the host)
+    float *sgp = dyn + HEAD_PACK;
+    for (int i = tid; i < HEAD_PACK; i += blockDim.x) { swp[i] = __ldg(a.head_pack + i); sgp[i] = 0.f; }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float gscale = __ldg(a.corr_scale) / (float)(a.pairs * (a.k < n ? a.k : n));
+    for (int r = warp; r < a.k; r += nwarps) {
+        const int i = __ldg(a.top_idx + (size_t)b * a.k + r);
+        if (i < 0) continue;                                       // fewer than k points
+        const float zs = __ldg(a.h_out_src + (nb + i) * H + lane), zt = __ldg(a.h_out_tgt + (nb + i) * H + lane);
+        const MlpRow m = mlp_row(swp, zs, zt, lane);
+        const float y = __ldg(a.labels + nb + i);
+        const float dsc = gscale * (1.0f / (1.0f + expf(-m.score)) - y);          // d BCEWithLogits / d score
+        // last Linear (16 -> 1)
+        float dh1 = 0.f;
+        if (lane < 16) {
+            atomicAdd(sgp + HOFF_W2 + lane, dsc * m.h1);
+            dh1 = m.h1 > 0.f ? dsc * swp[HOFF_W2 + lane] : 0.f;
+            atomicAdd(sgp + HOFF_B1 + lane, dh1);
+        }
+        if (lane == 0) atomicAdd(sgp + HOFF_B2, dsc);
+        // middle Linear (32 -> 16): dW1T[i][j] += h0[i] dh1[j];  dh0[i] = sum_j W1T[i][j] dh1[j]
+        float dh0 = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+            const float dj = __shfl_sync(0xffffffffu, dh1, j);
+            atomicAdd(sgp + HOFF_W1T + 16 * lane + j, m.h0 * dj);
+            dh0 = fmaf(swp[HOFF_W1T + 16 * lane + j], dj, dh0);
+        }
+        dh0 = m.h0 > 0.f ? dh0 : 0.f;
+        atomicAdd(sgp + HOFF_B0 + lane, dh0);
+        // first Linear (64 -> 32): dW0T[in][out] += z[in] dh0[out];  dz[in] = sum_out W0T[in][out] dh0[out]
+        float dzs = 0.f, dzt = 0.f;
+#pragma unroll 4
+        for (int o = 0; o < 32; ++o) {
+            const float d = __shfl_sync(0xffffffffu, dh0, o);
+            dzs = fmaf(swp[HOFF_W0T + 32 * lane + o], d, dzs);
+            dzt = fmaf(swp[HOFF_W0T + 32 * (32 + lane) + o], d, dzt);
+        }
+#pragma unroll 4
+        for (int in = 0; in < 32; ++in) {
+            atomicAdd(sgp + HOFF_W0T + 32 * in + lane, __shfl_sync(0xffffffffu, zs, in) * dh0);
+            atomicAdd(sgp + HOFF_W0T + 32 * (32 + in) + lane, __shfl_sync(0xffffffffu, zt, in) * dh0);
+        }
+        a.dh_src[(nb + i) * H + lane] += dzs;
+        a.dh_tgt[(nb + i) * H + lane] += dzt;
+    }
+    __syncthreads();
+    for (int i = tid; i < HEAD_PACK; i += blockDim.x) {
+        const float g = sgp[i];
+        if (g != 0.f) atomicAdd(a.head_gpack + i, g);
+    }
+}
+
+// ---- training losses on the device: 3dm:681-694 (top-k of the output-feature similarity), 3dm:760-781
+// (BCE of mlp([h_s | h_t][top-k]) against the labels; MSE between the z-scored similarity and the z-scored input-feature
+// similarity, mean / unbiased std over the whole batch), plus pose_loss 3dm:896-962 and the loop's total 3dm:1118. ----
+struct TrainLossArgs {
+    const float *h_out_src, *h_out_tgt, *feat_src, *feat_tgt, *sim, *labels, *head_pack;
+    int n, k;
+    int32_t *top_idx;       // [pairs][k]: members of the top-k set (unordered; -1 past min(k, n))
+    float *scores;          // [pairs][k]: mlp logits of those rows
+    float *raw;             // [pairs][n]: input-feature similarity
+    double *stats;          // [pairs][4]: sum sim, sum sim^2, sum raw, sum raw^2
+    float *bce;             // [pairs]: sum over the pair's rows of BCEWithLogits
+};
+
+__global__ void __launch_bounds__(HD_THREADS_BIG) train_loss_forward_kernel(const TrainLossArgs a) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ BlockScratch sc;
+    __shared__ double dred[HD_WARPS][4];
+    __shared__ int s_count;
+    const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const size_t nb = (size_t)b * n;
+    float *ssim = dyn;                       // [n]
+    int *slist = reinterpret_cast<int *>(dyn + n);      // [k]
+    float *swp = dyn + n + a.k;              // [HEAD_PACK]
+    for (int i = tid; i < HEAD_PACK; i += blockDim.x) swp[i] = __ldg(a.head_pack + i);
+    if (tid == 0) s_count = 0;
+    double acc[4] = {0, 0, 0, 0};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float s = __ldg(a.sim + nb + i);
+        ssim[i] = s;
+        const float r = dot32(a.feat_src + (nb + i) * H, a.feat_tgt + (nb + i) * H);     // 3dm:773
+        a.raw[nb + i] = r;
+        acc[0] += (double)s; acc[1] += (double)s * (double)s; acc[2] += (double)r; acc[3] += (double)r * (double)r;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) dred[warp][q] = acc[q];
+    }
+    __syncthreads();
+    if (tid < 4) {
+        double t = 0;
+        for (int w = 0; w < nwarps; ++w) t += dred[w][tid];
+        a.stats[(size_t)b * 4 + tid] = t;
+    }
+    // k-th largest similarity by 4-pass radix select (torch.topk; ties -> lower index), as in head_eval_kernel
+    const int kk = a.k < n ? a.k : n;
+    unsigned prefix = 0, pmask = 0;
+    int want = kk;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        __syncthreads();
+        if (tid < 256) sc.hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) {
+            const unsigned key = order_key(ssim[i]);
+            if ((key & pmask) == prefix) atomicAdd(&sc.hist[(key >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, bin = 255;
+            for (; bin > 0; --bin) {
+                if (cum + (int)sc.hist[bin] >= want) break;
+                cum += (int)sc.hist[bin];
+            }
+            sc.u[1] = (unsigned)bin; sc.u[2] = (unsigned)(want - cum);
+        }
+        __syncthreads();
+        prefix |= sc.u[1] << shift; pmask |= 0xffu << shift; want = (int)sc.u[2];
+    }
+    const unsigned kth_key = prefix;
+    unsigned eq_carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        unsigned key = 0;
+        if (i < n) key = order_key(ssim[i]);
+        const bool is_eq = (i < n) && key == kth_key;
+        const unsigned bal = __ballot_sync(0xffffffffu, is_eq);
+        __syncthreads();
+        if (lane == 0) sc.hist[warp] = __popc(bal);
+        __syncthreads();
+        unsigned before = eq_carry, total = 0;
+        for (int w = 0; w < nwarps; ++w) { const unsigned c = sc.hist[w]; if (w < warp) before += c; total += c; }
+        before += __popc(bal & ((1u << lane) - 1u));
+        eq_carry += total;
+        if ((i < n) && (key > kth_key || (is_eq && (int)before < want))) slist[atomicAdd(&s_count, 1)] = i;
+    }
+    __syncthreads();
+    float bsum[1] = {0.f};
+    for (int r = warp; r < a.k; r += nwarps) {
+        if (r >= kk) {
+            if (lane == 0) { a.top_idx[(size_t)b * a.k + r] = -1; a.scores[(size_t)b * a.k + r] = 0.f; }
+            continue;
+        }
+        const int i = slist[r];
+        const float zs = __ldg(a.h_out_src + (nb + i) * H + lane), zt = __ldg(a.h_out_tgt + (nb + i) * H + lane);
+        const MlpRow m = mlp_row(swp, zs, zt, lane);
+        if (lane == 0) {
+            const float x = m.score, y = __ldg(a.labels + nb + i);
+            bsum[0] += fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));              // BCEWithLogits
+            a.top_idx[(size_t)b * a.k + r] = i;
+            a.scores[(size_t)b * a.k + r] = x;
+        }
+    }
+    block_sum<1>(bsum, sc);
+    if (tid == 0) a.bce[b] = bsum[0];
+}
+
+// one CTA: batch statistics, losses, and the seeds of the backward pass
+//   loss[0..7] = corr, sim, mean rot, mean trans, total (3dm:1118), 0, 0, upstream scale of the mean BCE (= scale)
+__global__ void __launch_bounds__(1024) train_loss_finalize_kernel(const float *__restrict__ sim, const float *__restrict__ raw,
+                                                                   const double *__restrict__ stats, const float *__restrict__ bce,
+                                                                   int pairs, int n, int k, const float *__restrict__ R,
+                                                                   const float *__restrict__ t, const float *__restrict__ gt_pose,
+                                                                   float scale, float *__restrict__ loss, float *__restrict__ dsim,
+                                                                   float *__restrict__ dR, float *__restrict__ dt) {
+    __shared__ double dred[32][4];
+    __shared__ double bc[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long M = (long long)pairs * n;
+    auto block_sum_d = [&](double (&v)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        }
+        __syncthreads();
+        if (lane == 0) { dred[warp][0] = v[0]; dred[warp][1] = v[1]; dred[warp][2] = v[2]; dred[warp][3] = v[3]; }
+        __syncthreads();
+        if (tid < 4) {
+            double s = 0;
+            for (int w = 0; w < 32; ++w) s += dred[w][tid];
+            bc[tid] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = bc[q];
+    };
+    double st[4] = {0, 0, 0, 0};
+    for (int b = tid; b < pairs; b += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st[q] += stats[(size_t)b * 4 + q];
+    }
+    block_sum_d(st);
+    const double mu_s = st[0] / (double)M, mu_r = st[2] / (double)M;
+    const double var_s = fmax((st[1] - (double)M * mu_s * mu_s) / (double)(M - 1), 0.0);        // torch.std: unbiased
+    const double var_r = fmax((st[3] - (double)M * mu_r * mu_r) / (double)(M - 1), 0.0);
+    const double sd_s = sqrt(var_s), sd_r = sqrt(var_r);
+    const double is = 1.0 / (sd_s + 1e-6), ir = 1.0 / (sd_r + 1e-6);                             // 3dm:776-777
+    // pass 1: sim loss and the two sums its gradient needs
+    double a1[4] = {0, 0, 0, 0};       // sum d^2, sum g, sum g (sim - mu)
+    for (long long i = tid; i < M; i += blockDim.x) {
+        const double s = (double)sim[i] - mu_s;
+        const double d = s * is - ((double)raw[i] - mu_r) * ir;
+        const double g = 2.0 * d / (double)M;
+        a1[0] += d * d; a1[1] += g; a1[2] += g * s;
+    }
+    block_sum_d(a1);
+    const double sim_loss = a1[0] / (double)M;                                                   // F.mse_loss 3dm:779
+    const double gmean = a1[1] / (double)M;
+    const double kcoef = sd_s > 0.0 ? a1[2] * is * is / ((double)(M - 1) * sd_s) : 0.0;
+    if (dsim) {
+        for (long long i = tid; i < M; i += blockDim.x) {
+            const double s = (double)sim[i] - mu_s;
+            const double d = s * is - ((double)raw[i] - mu_r) * ir;
+            const double g = 2.0 * d / (double)M;
+            dsim[i] = (float)((double)scale * ((g - gmean) * is - s * kcoef));
+        }
+    }
+    // pose_loss (3dm:896-962) per pair + means; correspondence BCE mean
+    double pl[4] = {0, 0, 0, 0};       // sum rot, sum trans, sum bce
+    for (int b = tid; b < pairs; b += blockDim.x) {
+        pl[2] += (double)bce[b];
+        if (!R) continue;
+        const float *Rb = R + b * 9, *G = gt_pose + b * 16;
+        float tr = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) tr = fmaf(Rb[i * 3 + j], G[i * 4 + j], tr);
+        const float c = (tr - 1.0f) * 0.5f, cc = fminf(fmaxf(c, -1.0f), 1.0f);
+        pl[0] += (double)acosf(cc);
+        const float kr = (c < -1.0f || c > 1.0f) ? 0.f : -0.5f / sqrtf(1.0f - cc * cc);
+        const float t0 = t[b * 3], t1 = t[b * 3 + 1], t2 = t[b * 3 + 2], g0 = G[3], g1 = G[7], g2 = G[11];
+        const float dot = t0 * g0 + t1 * g1 + t2 * g2;
+        const float nt = sqrtf(t0 * t0 + t1 * t1 + t2 * t2), ng = sqrtf(g0 * g0 + g1 * g1 + g2 * g2);
+        const float cs = dot / (nt * ng), cl = fminf(fmaxf(cs, -1.0f), 1.0f);
+        pl[1] += (double)acosf(cl);
+        const float kt = (cs < -1.0f || cs > 1.0f) ? 0.f : -1.0f / sqrtf(1.0f - cl * cl);
+        const float ia = 1.0f / (nt * ng), bb = cs / (nt * nt), sc = scale / (float)pairs;       // .mean() over the pairs 3dm:1118
+        if (dR) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dR[b * 9 + i * 3 + j] = sc * kr * G[i * 4 + j];
+            dt[b * 3] = sc * kt * (g0 * ia - bb * t0); dt[b * 3 + 1] = sc * kt * (g1 * ia - bb * t1); dt[b * 3 + 2] = sc * kt * (g2 * ia - bb * t2);
+        }
+    }
+    block_sum_d(pl);
+    if (tid == 0) {
+        const int kk = k < n ? k : n;
+        const double corr = pl[2] / ((double)pairs * kk);
+        const double rot = R ? pl[0] / pairs : 0.0, tra = R ? pl[1] / pairs : 0.0;
+        loss[0] = (float)corr; loss[1] = (float)sim_loss; loss[2] = (float)rot; loss[3] = (float)tra;
+        loss[4] = (float)(corr + sim_loss + rot + tra);
+        loss[5] = 0.f; loss[6] = 0.f; loss[7] = scale;
+    }
 }
 
 // ---- pose_loss (3dm:896-962): rotation loss = acos(clamp((trace(R^T R_gt) - 1) / 2, -1, 1)), translation loss =
@@ -695,11 +988,7 @@ __global__ void pose_loss_kernel(const float *__restrict__ R, const float *__res
     }
 }
 
-static int head_threads(int n) {
-    static const int forced = getenv("EGSPR_HEAD_THREADS") ? atoi(getenv("EGSPR_HEAD_THREADS")) : 0;   // developer switch
-    if (forced == 256 || forced == 512 || forced == 1024) return forced;
-    return n > HD_BIG_N ? HD_THREADS_BIG : HD_THREADS;
-}
+static int head_threads(int n) { return n > HD_BIG_N ? HD_THREADS_BIG : HD_THREADS; }
 
 template <class K>
 static int ensure_smem(K kernel, size_t bytes) {
@@ -761,19 +1050,67 @@ extern "C" int egspr_head_train(const float *h_out_src, const float *h_out_tgt, 
     return EGSPR_OK;
 }
 
+static int head_train_backward_impl(const egspr::HeadTrainBwdArgs &a, int pairs, int n, void *stream) {
+    using namespace egspr;
+    if (!a.h_out_src || !a.h_out_tgt || !a.x_out_src || !a.x_out_tgt || !a.labels || !a.dR || !a.dt || !a.dh_src || !a.dh_tgt ||
+        !a.dx_src || !a.dx_tgt || pairs <= 0 || n <= 0)
+        return EGSPR_E_INVALID;
+    if (2 * n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
+    size_t floats = 2 * (size_t)n;
+    if (a.top_idx && floats < 2 * (size_t)HEAD_PACK) floats = 2 * (size_t)HEAD_PACK;      // the pack + its gradient reuse the rows
+    const size_t smem = sizeof(float) * floats;
+    if (int e = ensure_smem(head_train_backward_kernel, smem)) return e;
+    head_train_backward_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
 extern "C" int egspr_head_train_backward(const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
                                          const float *x_out_tgt, const float *labels, const float *dR, const float *dt,
                                          const float *dsim, int pairs, int n, float *dh_src, float *dh_tgt,
                                          float *dx_src, float *dx_tgt, void *stream) {
+    egspr::HeadTrainBwdArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, dR, dt, dsim, n, dh_src, dh_tgt, dx_src, dx_tgt,
+                              nullptr, nullptr, nullptr, 0, pairs, nullptr};
+    return head_train_backward_impl(a, pairs, n, stream);
+}
+
+extern "C" int egspr_head_train_loss_backward(const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                                              const float *x_out_tgt, const float *labels, const float *dR, const float *dt,
+                                              const float *dsim, const int32_t *top_idx, const float *head_pack,
+                                              const float *loss, int pairs, int n, int top_k, float *dh_src, float *dh_tgt,
+                                              float *dx_src, float *dx_tgt, float *head_grad_pack, void *stream) {
+    if (!top_idx || !head_pack || !loss || !head_grad_pack || top_k <= 0) return EGSPR_E_INVALID;
+    egspr::HeadTrainBwdArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, dR, dt, dsim, n, dh_src, dh_tgt, dx_src, dx_tgt,
+                              top_idx, head_pack, head_grad_pack, top_k, pairs, loss + 7};
+    return head_train_backward_impl(a, pairs, n, stream);
+}
+
+extern "C" int egspr_train_loss_forward(const float *h_out_src, const float *h_out_tgt, const float *feat_src,
+                                        const float *feat_tgt, const float *sim, const float *labels, const float *head_pack,
+                                        int pairs, int n, int top_k, int32_t *top_idx, float *scores, float *raw,
+                                        double *stats, float *bce, void *stream) {
     using namespace egspr;
-    if (!h_out_src || !h_out_tgt || !x_out_src || !x_out_tgt || !labels || !dR || !dt || !dh_src || !dh_tgt || !dx_src ||
-        !dx_tgt || pairs <= 0 || n <= 0)
+    if (!h_out_src || !h_out_tgt || !feat_src || !feat_tgt || !sim || !labels || !head_pack || !top_idx || !scores || !raw ||
+        !stats || !bce || pairs <= 0 || n <= 0 || top_k <= 0)
         return EGSPR_E_INVALID;
-    if (2 * n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
-    const size_t smem = sizeof(float) * 2 * (size_t)n;
-    if (int e = ensure_smem(head_train_backward_kernel, smem)) return e;
-    HeadTrainBwdArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, dR, dt, dsim, n, dh_src, dh_tgt, dx_src, dx_tgt};
-    head_train_backward_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    const size_t smem = sizeof(float) * ((size_t)n + top_k + HEAD_PACK);
+    if (smem > 200 * 1024) return EGSPR_E_UNSUPPORTED;
+    if (int e = ensure_smem(train_loss_forward_kernel, smem)) return e;
+    TrainLossArgs a{h_out_src, h_out_tgt, feat_src, feat_tgt, sim, labels, head_pack, n, top_k, top_idx, scores, raw, stats, bce};
+    train_loss_forward_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
+extern "C" int egspr_train_loss_finalize(const float *sim, const float *raw, const double *stats, const float *bce, int pairs,
+                                         int n, int top_k, const float *R, const float *t, const float *gt_pose, float scale,
+                                         float *loss, float *dsim, float *dR, float *dt, void *stream) {
+    using namespace egspr;
+    if (!sim || !raw || !stats || !bce || !loss || pairs <= 0 || n <= 0 || top_k <= 0) return EGSPR_E_INVALID;
+    if (R && (!t || !gt_pose)) return EGSPR_E_INVALID;
+    if (dR && (!dt || !R)) return EGSPR_E_INVALID;
+    train_loss_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sim, raw, stats, bce, pairs, n, top_k, R, t, gt_pose, scale, loss,
+                                                                     dsim, dR, dt);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }

@@ -252,20 +252,24 @@ def compute_losses(rot, translation, h_src_norm, x_src, h_tgt_norm, x_tgt, gt_la
 class CrossAttentionPoseRegression(nn.Module):
     """EGNN on both clouds + correspondence-weight head + weighted Kabsch pose.
 
-    `variant`: 'train' = 3dm:634-796 (weights = softmax of output-feature similarity over the GT
-    inliers, Kabsch on EGNN coords), 'eval' = evl:643-827 (weights from the input-feature
-    similarity / top-128 / mlp chain, Kabsch on the original coords, all points; the reference
-    body only works for B=1 -- here every pair of the batch is treated as its own B=1 call),
-    None (default) = 'train' while self.training else 'eval'.
+    `variant`: 'train' (default) = the class of the training scripts, 3dm:634-796 (weights = softmax of
+    output-feature similarity over the GT inliers, Kabsch on EGNN coords; used unchanged under
+    model.eval() by the reference's validate(), 3dm:1141, 1272-1290), 'eval' = the class of
+    src/eval_egnn_metrics.py, evl:643-827 (weights from the input-feature similarity / top-128 /
+    mlp chain, Kabsch on the original coords, all points; the reference body only works for B=1 --
+    here every pair of the batch is treated as its own B=1 call).  The variant never follows
+    self.training: the two reference files define two different classes, not two modes.
     All parameters of the reference exist (incl. the dead shared_mlp_decoder / shallow_mlp_pose /
     bn1 / bn2) so strict checkpoint loading works."""
 
-    def __init__(self, egnn, num_nodes=2048, hidden_nf=33, device='cuda:0', variant=None):
+    def __init__(self, egnn, num_nodes=2048, hidden_nf=33, device='cuda:0', variant='train'):
         super().__init__()
         self.egnn = egnn
         self.hidden_nf = hidden_nf
         self.num_nodes = num_nodes
         self.device = device
+        if variant not in ("train", "eval"):
+            raise ValueError("variant must be 'train' (3dm / kit class) or 'eval' (evl class)")
         self.variant = variant
         self.mlp = nn.Sequential(nn.Linear(2 * hidden_nf, hidden_nf), nn.ReLU(),
                                  nn.Linear(hidden_nf, hidden_nf // 2), nn.ReLU(),
@@ -287,7 +291,7 @@ class CrossAttentionPoseRegression(nn.Module):
                 nn.init.zeros_(layer.bias)
 
     def _variant(self):
-        return self.variant if self.variant is not None else ("train" if self.training else "eval")
+        return self.variant
 
     def _egnn_both(self, h_src, x_src, edges_src, edge_attr_src, h_tgt, x_tgt, edges_tgt, edge_attr_tgt):
         B, N, _ = h_src.shape
@@ -330,20 +334,17 @@ class CrossAttentionPoseRegression(nn.Module):
             R, t, w, sim, Hm, lp = ops.head_train(hs, ht, xs, xt, labels_f, gt_pose)
             total_loss = lp.sum(0).sum() / (B * N)                                           # 3dm:677
         self.last_aux = {"w": w, "H": Hm}
-        # correspondence BCE on the top-128 + similarity-consistency loss (3dm:681-694, 760-781)
-        k = min(self.top_k, N)
-        _, top_idx = torch.topk(sim, k=k, dim=-1)
-        Fd = hs.shape[-1]
-        chs = torch.gather(hs, 1, top_idx.unsqueeze(-1).expand(-1, -1, Fd))
-        cht = torch.gather(ht, 1, top_idx.unsqueeze(-1).expand(-1, -1, Fd))
-        cl = torch.gather(labels_f, 1, top_idx)
-        scores = self.mlp(torch.cat([chs, cht], dim=-1).view(-1, 2 * Fd)).view(B, k)
-        corr_loss = F.binary_cross_entropy_with_logits(scores, cl)
-        raw = (h_src.to(torch.float32) * h_tgt.to(torch.float32)).sum(-1)
-        simn = (sim - sim.mean()) / (sim.std() + 1e-6)
-        rawn = (raw - raw.mean()) / (raw.std() + 1e-6)
-        sim_loss = F.mse_loss(simn, rawn)
-        return R, t, corr_loss + sim_loss, total_loss, hs, xs, ht, xt, labels
+        # correspondence BCE on the top-128 + similarity-consistency loss (3dm:681-694, 760-781): two kernels
+        # (egspr_train_loss_forward / _finalize), differentiable w.r.t. the EGNN outputs, sim and mlp
+        fs, ft = h_src.to(torch.float32).contiguous(), h_tgt.to(torch.float32).contiguous()
+        spec = (self._pack_head.get(), int(self.top_k), self.mlp)
+        if grad:
+            corr_sim = _ag.CorrSimLossFunction.apply(spec, hs, ht, fs, ft, sim, labels_f, *self.mlp.parameters())
+        else:
+            top_idx, scores, raw, stats, bce = ops.train_loss_forward(hs, ht, fs, ft, sim, labels_f, spec[0], spec[1])
+            lv, _, _, _ = ops.train_loss_finalize(sim, raw, stats, bce, spec[1], need_grad=False)
+            corr_sim = lv[0] + lv[1]
+        return R, t, corr_sim, total_loss, hs, xs, ht, xt, labels
 
 
 # ---------------------------------------------------------------------------------------------

@@ -120,12 +120,27 @@ def csr_from_edges(edges, n):
     return g
 
 
+_IMPLICIT_CSC = {}
+
+
 def with_csc(graph, nbr=None):
     """Adds the col-grouped edge lists the backward pass needs (graph.cptr / graph.ceid): the CSR of the same edge
     tensor with its two rows swapped.  Graphs built from k-NN ids pass `nbr` (the edge tensor is rebuilt from it)."""
     if graph.cptr is not None:
         return graph
     nbr = nbr if nbr is not None else graph.nbr
+    if nbr is not None and graph.edges is None:
+        # k-NN graph: edge e = i * k + s has col = i, so the col-grouped lists are the original edge order --
+        # cptr[g] = g * k, ceid = 0 .. N k - 1 per cloud: constants of the shape, no second CSR build
+        C, N, k = nbr.shape
+        key = (C, N, k, str(nbr.device))
+        c = _IMPLICIT_CSC.get(key)
+        if c is None:
+            cptr = (torch.arange(C * N + 1, dtype=torch.int64, device=nbr.device) * k).to(torch.int32)
+            ceid = torch.arange(N * k, dtype=torch.int32, device=nbr.device).repeat(C)
+            c = _IMPLICIT_CSC[key] = (cptr, ceid)
+        graph.cptr, graph.ceid = c
+        return graph
     edges = graph.edges if graph.edges is not None else (nbr_to_edges(nbr) if nbr is not None else None)
     if edges is None:
         raise ValueError("with_csc needs the edge tensor (or the k-NN ids) the graph was built from")
@@ -309,12 +324,13 @@ def linear32_forward(x, pack):
     return y
 
 
-def linear32_backward(x, dy, pack, need_dx=True):
-    """-> (dx | None, grad_pack [EMBED_PACK])"""
+def linear32_backward(x, dy, pack, need_dx=True, gp=None):
+    """-> (dx | None, grad_pack [EMBED_PACK]); gp: an already-zeroed gradient pack to accumulate into (else a new one)"""
     x = _req(x, "x", torch.float32); dy = _req(dy, "dy", torch.float32)
     rows = x.numel() // H
     dx = torch.empty_like(x) if need_dx else None
-    gp = torch.zeros(pack.numel(), dtype=torch.float32, device=x.device)
+    if gp is None:
+        gp = torch.zeros(pack.numel(), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().egspr_linear32_backward(_ptr(x), _ptr(dy), rows, _ptr(pack), _ptr(dx), _ptr(gp), _stream()),
                    "egspr_linear32_backward")
@@ -365,8 +381,10 @@ def egnn_forward_saved(feat, x, graph, layer_packs, embed_in_pack, embed_out_pac
     return h_out.view(C, N, H), x_out, saved
 
 
-def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_out, dx_out, need_dfeat=True):
+def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_out, dx_out, need_dfeat=True, gpacks_out=None):
     """Backward of egnn_forward_saved.  dh_out [C,N,32], dx_out [C,N,3] (either may be None = zero).
+    gpacks_out: optional (layer grad packs, embed_in grad pack, embed_out grad pack), ALREADY ZEROED, to accumulate into
+    (views of one persistent gradient buffer in the training step); otherwise new zero-filled packs are allocated.
     Returns dfeat [C,N,32] | None, dx [C,N,3], layer grad packs (list), embed_in grad pack | None, embed_out grad pack | None."""
     if graph.cptr is None:
         raise ValueError("the backward pass needs graph.cptr / graph.ceid: call ops.with_csc(graph) first")
@@ -377,8 +395,9 @@ def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_o
     dh = torch.zeros((G, H), dtype=torch.float32, device=dev) if dh_out is None else _req(dh_out, "dh_out", torch.float32).reshape(G, H)
     dx = torch.zeros((G, 3), dtype=torch.float32, device=dev) if dx_out is None else _req(dx_out, "dx_out", torch.float32).reshape(G, 3)
     g_out = None
+    gl_out, gi_out, go_out = gpacks_out if gpacks_out is not None else (None, None, None)
     if embed_out_pack is not None:
-        dh, g_out = linear32_backward(saved["hs"][L], dh, embed_out_pack, need_dx=True)
+        dh, g_out = linear32_backward(saved["hs"][L], dh, embed_out_pack, need_dx=True, gp=go_out)
     E = C * graph.edges_per_cloud
     ws_bytes = lib.egspr_egcl_backward_workspace_bytes(G, E)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -386,7 +405,7 @@ def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_o
     with torch.cuda.device(dev):
         st = _stream()
         for i in range(L - 1, -1, -1):
-            gp = torch.zeros(layer_packs[i].numel(), dtype=torch.float32, device=dev)
+            gp = gl_out[i] if gl_out is not None else torch.zeros(layer_packs[i].numel(), dtype=torch.float32, device=dev)
             dh_in = torch.empty((G, H), dtype=torch.float32, device=dev)
             dx_in = torch.empty((G, 3), dtype=torch.float32, device=dev)
             _lib.check(lib.egspr_egcl_backward(
@@ -398,7 +417,7 @@ def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_o
             dh, dx = dh_in, dx_in
     g_in, dfeat = None, dh
     if embed_in_pack is not None:
-        dfeat, g_in = linear32_backward(saved["feat"].reshape(G, H), dh, embed_in_pack, need_dx=need_dfeat)
+        dfeat, g_in = linear32_backward(saved["feat"].reshape(G, H), dh, embed_in_pack, need_dx=need_dfeat, gp=gi_out)
     return (dfeat.view(C, N, H) if dfeat is not None else None), dx.view(C, N, 3), gpacks, g_in, g_out
 
 
@@ -433,3 +452,69 @@ def pose_loss(R, t, gt_pose, need_grad=True):
         _lib.check(_lib.lib().egspr_pose_loss(_ptr(R), _ptr(t), _ptr(gt_pose), B, _ptr(rl), _ptr(tl), _ptr(gR), _ptr(gt), _stream()),
                    "egspr_pose_loss")
     return rl, tl, gR, gt
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training losses on the device
+# ---------------------------------------------------------------------------------------------------------------
+def train_loss_forward(h_out_src, h_out_tgt, feat_src, feat_tgt, sim, labels, head_pack, top_k=128):
+    """3dm:681-694, 760-773 for a batch -> top_idx [B,k] i32 (unordered top-k set of sim), scores [B,k] (mlp logits),
+    raw [B,n] (input-feature similarity), stats [B,4] f64, bce [B] (per-pair BCE sums)."""
+    ts = [_req(v, nm, torch.float32, 3) for v, nm in ((h_out_src, "h_out_src"), (h_out_tgt, "h_out_tgt"),
+                                                      (feat_src, "feat_src"), (feat_tgt, "feat_tgt"))]
+    sim = _req(sim, "sim", torch.float32, 2)
+    labels = _req(labels.to(torch.float32), "labels", torch.float32, 2)
+    B, n, _ = ts[0].shape
+    dev = sim.device
+    top_idx = torch.empty((B, top_k), dtype=torch.int32, device=dev)
+    scores = torch.empty((B, top_k), dtype=torch.float32, device=dev)
+    raw = torch.empty((B, n), dtype=torch.float32, device=dev)
+    stats = torch.empty((B, 4), dtype=torch.float64, device=dev)
+    bce = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().egspr_train_loss_forward(*[_ptr(v) for v in ts], _ptr(sim), _ptr(labels), _ptr(head_pack), B, n,
+                                                       int(top_k), _ptr(top_idx), _ptr(scores), _ptr(raw), _ptr(stats), _ptr(bce),
+                                                       _stream()), "egspr_train_loss_forward")
+    return top_idx, scores, raw, stats, bce
+
+
+def train_loss_finalize(sim, raw, stats, bce, top_k, R=None, t=None, gt_pose=None, scale=1.0, need_grad=True):
+    """-> loss [8] = (corr, sim, mean rot, mean trans, total, 0, 0, scale), dsim [B,n] | None, dR [B,3,3] | None,
+    dt [B,3] | None (the seeds are multiplied by `scale`); the pose terms need R, t, gt_pose."""
+    sim = _req(sim, "sim", torch.float32, 2)
+    B, n = sim.shape
+    dev = sim.device
+    loss = torch.empty(8, dtype=torch.float32, device=dev)
+    dsim = torch.empty((B, n), dtype=torch.float32, device=dev) if need_grad else None
+    pose = R is not None
+    if pose:
+        R = _req(R, "R", torch.float32, 3); t = _req(t, "t", torch.float32, 2)
+        gt_pose = _req(gt_pose.to(torch.float32), "gt_pose", torch.float32, 3)
+    dR = torch.empty((B, 3, 3), dtype=torch.float32, device=dev) if (pose and need_grad) else None
+    dt = torch.empty((B, 3), dtype=torch.float32, device=dev) if (pose and need_grad) else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().egspr_train_loss_finalize(_ptr(sim), _ptr(raw), _ptr(stats), _ptr(bce), B, n, int(top_k), _ptr(R),
+                                                        _ptr(t), _ptr(gt_pose), float(scale), _ptr(loss), _ptr(dsim), _ptr(dR),
+                                                        _ptr(dt), _stream()), "egspr_train_loss_finalize")
+    return loss, dsim, dR, dt
+
+
+def head_train_loss_backward(h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, dR, dt, dsim, top_idx, head_pack, loss,
+                             head_gpack, top_k=128, outs=None):
+    """egspr_head_train_loss_backward: backward of head_train (dR, dt, dsim) plus the mean-BCE backward through mlp.
+    head_gpack [HEAD_PACK] is accumulated into (zero it first).  -> dh_src, dh_tgt, dx_src, dx_tgt."""
+    ts = [_req(v, nm, torch.float32, 3) for v, nm in
+          ((h_out_src, "h_out_src"), (h_out_tgt, "h_out_tgt"), (x_out_src, "x_out_src"), (x_out_tgt, "x_out_tgt"))]
+    B, n, _ = ts[0].shape
+    labels = _req(labels.to(torch.float32), "labels", torch.float32, 2)
+    dR = _req(dR, "dR", torch.float32, 3); dt = _req(dt, "dt", torch.float32, 2)
+    if dsim is not None:
+        dsim = _req(dsim, "dsim", torch.float32, 2)
+    if outs is None:
+        outs = [torch.empty_like(ts[0]), torch.empty_like(ts[1]), torch.empty_like(ts[2]), torch.empty_like(ts[3])]
+    with torch.cuda.device(ts[0].device):
+        _lib.check(_lib.lib().egspr_head_train_loss_backward(*[_ptr(v) for v in ts], _ptr(labels), _ptr(dR), _ptr(dt), _ptr(dsim),
+                                                             _ptr(top_idx), _ptr(head_pack), _ptr(loss), B, n, int(top_k),
+                                                             *[_ptr(o) for o in outs], _ptr(head_gpack), _stream()),
+                   "egspr_head_train_loss_backward")
+    return outs

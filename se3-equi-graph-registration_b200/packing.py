@@ -80,8 +80,18 @@ def pack_head(mlp):
     return buf
 
 
+_GENERATION = 0
+
+
+def invalidate_packs():
+    """Every PackCache rebuilds on its next use.  Called after parameter updates that bump no version counter: a
+    CUDA-graph replay of optimizer.step() rewrites the parameters' storage behind autograd's back."""
+    global _GENERATION
+    _GENERATION += 1
+
+
 class PackCache:
-    """Rebuilds a pack only when one of the source parameters changed (data_ptr or _version).
+    """Rebuilds a pack only when one of the source parameters changed (data_ptr, _version, or invalidate_packs()).
 
     The re-layout is a fixed permutation of the parameters' elements (plus zero padding), so after the first build
     its index map is known (the build function is run once more on a copy of the parameters holding their own
@@ -112,7 +122,7 @@ class PackCache:
 
     def get(self):
         params = list(self._params_fn())
-        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        key = (_GENERATION,) + tuple((p.data_ptr(), p._version, p.device) for p in params)
         if key != self._key:
             with torch.no_grad():
                 dev = params[0].device
@@ -170,6 +180,14 @@ def unpack_linear32_grad(gpack, lin):
     return [_g(gpack, 0, 32, 32).t().contiguous(), _g(gpack, 1024, 32).contiguous()]
 
 
+def unpack_head_grad(gpack, mlp):
+    """gpack [HEAD_PACK] -> gradients of mlp.parameters() (inverse of pack_head)."""
+    l0, l1, l2 = mlp[0], mlp[2], mlp[4]
+    by = {l0.weight: _g(gpack, 0, 64, 32).t(), l0.bias: _g(gpack, 2048, 32), l1.weight: _g(gpack, 2080, 32, 16).t(),
+          l1.bias: _g(gpack, 2592, 16), l2.weight: _g(gpack, 2608, 1, 16), l2.bias: _g(gpack, 2624, 1)}
+    return [by[p].contiguous() for p in mlp.parameters()]
+
+
 class GradUnpacker:
     """unpack_*_grad as ONE gather: the pack -> parameter re-layout is a permutation, so its index map is obtained
     once by unpacking an arange, and every later call is `flat = gpack[index]` + views (one kernel instead of ~40)."""
@@ -191,3 +209,80 @@ class GradUnpacker:
             out.append(flat[off:off + n].view(shp))
             off += n
         return out
+
+
+class FlatState:
+    """The training step's view of a CrossAttentionPoseRegression: ALL parameters are re-homed as views of one flat fp32
+    buffer (element 0 = a constant zero), the gradients of the live parameters (egnn.* and mlp.*, SURVEY F8: the other
+    12 tensors never get one and keep grad = None, like in the reference) as views of one flat gradient buffer.
+      * every kernel weight pack of the model = ONE gather  pack_buf = flat[pack_index]
+      * every parameter gradient            = ONE gather  flat_grad = gpack_buf[unpack_index]   (the packs are a
+        permutation of the parameters, so the second index is the inverse of the first)
+      * the data-parallel exchange            = ONE all-reduce of flat_grad (contiguous, persistent, no per-parameter copies)
+    nn.Parameter objects, state_dict keys and optimizer param groups are untouched (their .data now aliases the flat buffer)."""
+
+    def __init__(self, model):
+        egnn = model.egnn
+        self.layers = [egnn._modules["gcl_%d" % i] for i in range(egnn.n_layers)]
+        live = list(egnn.parameters()) + list(model.mlp.parameters())
+        live_ids = {id(p) for p in live}
+        dead = [p for p in model.parameters() if id(p) not in live_ids]
+        params = live + dead
+        dev = params[0].device
+        n_live = sum(p.numel() for p in live)
+        total = sum(p.numel() for p in params)
+        if total + 1 >= 1 << 24:
+            raise NotImplementedError("element numbers must stay exact in fp32")
+        self.flat = torch.zeros(1 + total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n_live, dtype=torch.float32, device=dev)
+        off = 1
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + n].view_as(p)
+                if id(p) in live_ids:
+                    p.grad = self.flat_grad[off - 1:off - 1 + n].view_as(p)
+                off += n
+            # index maps: the pack builders run once on parameters holding their own (1-based) element numbers
+            saved = [p.data for p in params]
+            off = 1
+            try:
+                for p in params:
+                    p.data = torch.arange(off, off + p.numel(), dtype=torch.float32, device=dev).view_as(p)
+                    off += p.numel()
+                packs = [pack_layer(g) for g in self.layers] + [pack_linear32(egnn.embedding_in), pack_linear32(egnn.embedding_out),
+                                                                 pack_head(model.mlp)]
+            finally:
+                for p, d in zip(params, saved):
+                    p.data = d
+        self.pack_index = torch.cat(packs).round().to(torch.int64)
+        sizes = [t.numel() for t in packs]
+        self.pack_buf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.gpack_buf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        unpack = torch.full((n_live + 1,), -1, dtype=torch.int64, device=dev)
+        pos = torch.arange(self.pack_index.numel(), dtype=torch.int64, device=dev)
+        sel = self.pack_index > 0
+        unpack[self.pack_index[sel]] = pos[sel]
+        self.unpack_index = unpack[1:]
+        if int((self.unpack_index < 0).sum()) != 0 or int(self.pack_index.max()) > n_live:
+            raise RuntimeError("weight packs do not cover the live parameters exactly once")
+        self.n_live = n_live
+        self._views(sizes)
+        invalidate_packs()
+
+    def _views(self, sizes):
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        L = len(self.layers)
+        cut = lambda buf: [buf[offs[i]:offs[i + 1]] for i in range(len(sizes))]
+        pv, gv = cut(self.pack_buf), cut(self.gpack_buf)
+        self.layer_packs, self.pack_in, self.pack_out, self.pack_head = pv[:L], pv[L], pv[L + 1], pv[L + 2]
+        self.layer_gpacks, self.gpack_in, self.gpack_out, self.gpack_head = gv[:L], gv[L], gv[L + 1], gv[L + 2]
+
+    def refresh_packs(self):
+        torch.index_select(self.flat, 0, self.pack_index, out=self.pack_buf)
+
+    def gather_gradients(self):
+        torch.index_select(self.gpack_buf, 0, self.unpack_index, out=self.flat_grad)

@@ -179,36 +179,95 @@ def test_train_step_runs_and_reduces_the_loss(golden_dir):
 
 
 def test_graphed_train_step_equals_eager(golden_dir):
-    """train.GraphedTrainStep (the whole step captured as one CUDA graph) follows the eager train_step: same losses
-    over several optimizer updates (the weight packs are rebuilt inside the graph from the live parameters)."""
+    """train.GraphedTrainStep (the fixed ~35-kernel launch sequence with the fused loss kernels, captured as one CUDA
+    graph) follows the eager train_step (nn.Module API + torch.autograd): same losses and the same parameters after
+    several optimizer updates.  Building the step must not train the model (warm-up is undone), and an eager forward
+    after replays must see the updated weights (the replay changes the parameters behind the version counters)."""
     keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
     batches = [tuple(P.synthetic.make_batch(40 + i, 2, n=512)[k].to(DEV) for k in keys) for i in range(3)]
     ones = torch.ones(2, 512 * 16, 1, device=DEV)
-    losses = {}
+    losses, finals = {}, {}
     for mode in ("eager", "graph"):
         model = _model(golden_dir, 0.005)
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
         out = []
         if mode == "graph":
-            w0 = [p.detach().clone() for p in model.parameters()]
+            w0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
             step = P.train.GraphedTrainStep(model, opt, batches[0], k=16, warmup=2)
-            with torch.no_grad():                                    # undo the warm-up / capture updates
-                for p, w in zip(model.parameters(), w0):
-                    p.copy_(w)
-            for st in opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            assert all(torch.equal(v, w0[k]) for k, v in model.state_dict().items())           # construction did not train
             for i in range(6):
                 out.append(float(step(batches[i % 3])))
+            assert sum(p.grad is not None for p in model.parameters()) == 85                    # dead parameters stay None
+            # eager eval forward after the replays == a fresh model holding the same state_dict
+            sf, sp, tf, tp, corr, labels, gt = batches[0]
+            es, et = P.knn_graph_batch(sp, 16), P.knn_graph_batch(tp, 16)
+            fresh = _model(golden_dir)
+            fresh.load_state_dict(model.state_dict())
+            with torch.no_grad():
+                a_ = model(sf, sp, es, ones, tf, tp, et, ones, corr, labels, gt)
+                b_ = fresh(sf, sp, es, ones, tf, tp, et, ones, corr, labels, gt)
+            assert torch.equal(a_[4], b_[4]) and torch.equal(a_[2], b_[2])
         else:
             for i in range(6):
                 sf, sp, tf, tp, corr, labels, gt = batches[i % 3]
                 es, et = P.knn_graph_batch(sp, 16), P.knn_graph_batch(tp, 16)
                 out.append(float(P.train.train_step(model, opt, (sf, sp, es, ones, tf, tp, et, ones, corr, labels, gt))))
         losses[mode] = out
+        finals[mode] = {k: v.detach().clone() for k, v in model.named_parameters()}
     assert np.all(np.isfinite(losses["graph"]))
     assert np.allclose(losses["eager"], losses["graph"], rtol=2e-3), losses
+    moved = 0.0
+    for k in finals["eager"]:
+        d = float((finals["eager"][k] - finals["graph"][k]).abs().max())
+        assert d <= 2e-5, (k, d)                                    # 6 Adam steps of 1e-4 move a weight by <= 6e-4
+        moved = max(moved, d)
+
+
+def test_fused_train_losses_match_torch_formulas(golden_dir):
+    """egspr_train_loss_forward / _finalize / egspr_head_train_loss_backward against the reference's torch
+    formulas (3dm:681-694, 760-781) evaluated with autograd in fp64: loss values, the top-k SET, d loss / d (h_src_out,
+    h_tgt_out, sim) and the six mlp gradients; n < top_k and heavy ties in sim included."""
+    model = _model(golden_dir, 0.005)
+    g = torch.Generator().manual_seed(9)
+    for B, n, k in ((3, 700, 128), (2, 90, 128)):
+        hs = torch.randn(B, n, 32, generator=g) * 0.3
+        ht = hs + 0.2 * torch.randn(B, n, 32, generator=g)
+        ht[:, n // 2:n // 2 + 20] = ht[:, :20]; hs[:, n // 2:n // 2 + 20] = hs[:, :20]        # exact ties in sim
+        fs = torch.nn.functional.normalize(torch.randn(B, n, 32, generator=g), dim=-1)
+        ft = torch.nn.functional.normalize(fs + 0.3 * torch.randn(B, n, 32, generator=g), dim=-1)
+        labels = (torch.rand(B, n, generator=g) < 0.6).float()
+        # reference formulas, fp64
+        sd = {k_: v.detach().cpu().double().requires_grad_(True) for k_, v in model.mlp.state_dict().items()}
+        H, T = hs.double().requires_grad_(True), ht.double().requires_grad_(True)
+        sim = (H * T).sum(-1)
+        sim_leaf = sim.detach().requires_grad_(True)
+        kk = min(k, n)
+        top = torch.topk(sim_leaf, kk, dim=-1).indices
+        z = torch.cat([torch.gather(H, 1, top[..., None].expand(-1, -1, 32)), torch.gather(T, 1, top[..., None].expand(-1, -1, 32))], -1)
+        a1 = torch.relu(z @ sd["0.weight"].T + sd["0.bias"]); a2 = torch.relu(a1 @ sd["2.weight"].T + sd["2.bias"])
+        sc = (a2 @ sd["4.weight"].T + sd["4.bias"])[..., 0]
+        corr = torch.nn.functional.binary_cross_entropy_with_logits(sc, torch.gather(labels.double(), 1, top))
+        raw = (fs.double() * ft.double()).sum(-1)
+        zs = (sim_leaf - sim_leaf.mean()) / (sim_leaf.std() + 1e-6); zr = (raw - raw.mean()) / (raw.std() + 1e-6)
+        siml = torch.nn.functional.mse_loss(zs, zr)
+        (corr + siml).backward()
+        # kernels
+        d = lambda v: v.float().to(DEV).contiguous()
+        pack = model._pack_head.get()
+        top_idx, scores, raw_k, stats, bce = ops.train_loss_forward(d(hs), d(ht), d(fs), d(ft), d(sim.detach()), d(labels), pack, k)
+        loss, dsim, _, _ = ops.train_loss_finalize(d(sim.detach()), raw_k, stats, bce, k, scale=1.0)
+        assert abs(float(loss[0]) - float(corr)) <= 2e-5 * max(1.0, abs(float(corr))) and abs(float(loss[1]) - float(siml)) <= 2e-5 * max(1.0, float(siml))
+        for b in range(B):
+            got = sorted(int(i) for i in top_idx[b].cpu() if i >= 0)
+            assert got == sorted(int(i) for i in top[b]), b
+        assert rel(dsim, sim_leaf.grad) < 1e-4
+        gp = torch.zeros(packing.HEAD_PACK, device=DEV)
+        zx = torch.zeros(B, n, 3, device=DEV)
+        dhs, dht, _, _ = ops.head_train_loss_backward(d(hs), d(ht), zx, zx, d(labels), torch.zeros(B, 3, 3, device=DEV), torch.zeros(B, 3, device=DEV),
+                                                      None, top_idx, pack, loss, gp, k)
+        assert rel(dhs, H.grad) < 1e-4 and rel(dht, T.grad) < 1e-4, (rel(dhs, H.grad), rel(dht, T.grad))
+        for got_g, (name, prm) in zip(packing.unpack_head_grad(gp, model.mlp), model.mlp.named_parameters()):
+            assert rel(got_g, sd[name].grad) < 1e-4, (name, rel(got_g, sd[name].grad))
 
 
 def test_backward_on_irregular_graph_hub_rows_isolated_nodes(golden_dir):

@@ -31,21 +31,43 @@ b = batch(100 + rank)
 model.train(); opt.zero_grad(set_to_none=True)
 P.train.training_loss(model(*b), b[10]).backward()
 params = [p for p in model.parameters()]
-local, _ = P.train.flat_gradient(params)
+live = [p for p in params if p.grad is not None]
+assert len(live) == 85
+local = torch.cat([p.grad.flatten() for p in live])
 gathered = [torch.empty_like(local) for _ in range(world)]
 dist.all_gather(gathered, local)
 P.train.allreduce_gradients(params)
-after, _ = P.train.flat_gradient(params)
+after = torch.cat([p.grad.flatten() for p in live])
 want = torch.stack(gathered).mean(0)
 assert torch.allclose(after, want, rtol=1e-5, atol=1e-7 * float(want.abs().max())), float((after - want).abs().max())
 assert float((gathered[0] - gathered[1]).abs().max()) > 0          # the ranks really had different data
-# (2) replicas stay identical over several steps on different data
-for s in range(4):
+assert sum(p.grad is not None for p in params) == 85                # dead parameters stay None on every rank
+# (2) replicas stay identical over several eager steps on different data
+for s in range(3):
     loss = P.train.train_step(model, opt, batch(200 + 10 * s + rank))
     assert torch.isfinite(loss)
-chk = torch.cat([p.detach().flatten() for p in params]).double().sum().reshape(1)
-both = [torch.empty_like(chk) for _ in range(world)]
-dist.all_gather(both, chk)
+def checksum():
+    chk = torch.cat([p.detach().flatten() for p in params]).double().sum().reshape(1)
+    both = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    return both
+both = checksum()
+assert both[0].item() == both[1].item(), (both[0].item(), both[1].item())
+# (3) the graphed step (one all-reduce of the persistent flat gradient inside the CUDA graph): its 2-rank gradient is the
+# mean of the two ranks' 1-rank gradients, and the replicas stay bit-identical
+keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
+def raw_batch(seed):
+    d = P.synthetic.make_batch(seed, 2, n=512)
+    return tuple(d[k].to(dev) for k in keys)
+opt2 = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+step = P.train.GraphedTrainStep(model, opt2, raw_batch(300 + rank), k=16)
+for s in range(3):
+    loss = step(raw_batch(310 + 10 * s + rank))
+    assert torch.isfinite(loss)
+gl = [torch.empty_like(step.state.flat_grad) for _ in range(world)]
+dist.all_gather(gl, step.state.flat_grad)
+assert torch.equal(gl[0], gl[1])                                    # every rank holds the same (all-reduced) gradient
+both = checksum()
 assert both[0].item() == both[1].item(), (both[0].item(), both[1].item())
 if rank == 0:
     print("DDP_OK", float(loss))

@@ -173,7 +173,7 @@ def test_pair_sharding_two_ranks_gloo(tmp_path):
 
 
 def test_gradient_allreduce_two_ranks_gloo(tmp_path):
-    """train.allreduce_gradients: ONE flat fp32 bucket over all parameters (BASELINE config 4's only collective);
+    """train.allreduce_gradients / packing.FlatState: ONE flat fp32 bucket (BASELINE config 4's only collective);
     after it every rank holds the mean gradient, parameters without a gradient (dead modules) included
     as zeros, so identical optimizer steps keep the replicas identical."""
     script = tmp_path / "g.py"
@@ -189,12 +189,26 @@ def test_gradient_allreduce_two_ranks_gloo(tmp_path):
         "params = list(model.parameters())\n"
         "for i, p in enumerate(params):\n"
         "    if i % 7 != 3: p.grad = torch.full_like(p, float(r + 1) * (i + 1))\n"     # some parameters get no gradient
-        "flat, views = P.train.flat_gradient(params)\n"
-        "assert flat.numel() == sum(p.numel() for p in params) and views[0].data_ptr() == flat.data_ptr()\n"
         "P.train.allreduce_gradients(params)\n"
         "for i, p in enumerate(params):\n"
-        "    want = 0.0 if i % 7 == 3 else 1.5 * (i + 1)\n"
-        "    assert p.grad is not None and torch.all(p.grad == want), (i, p.grad.flatten()[0], want)\n"
+        "    if i % 7 == 3:\n"
+        "        assert p.grad is None, i\n"                      # no gradient on any rank: stays None (Adam skips it, as in 1-rank training)
+        "    else:\n"
+        "        assert torch.all(p.grad == 1.5 * (i + 1)), (i, p.grad.flatten()[0])\n"
+        "# FlatState: the parameters' gradients as views of ONE persistent buffer -> the collective is a single all_reduce of it\n"
+        "from se3_equi_graph_registration_b200 import packing\n"
+        "sd0 = {k: v.clone() for k, v in model.state_dict().items()}\n"
+        "fs = packing.FlatState(model)\n"
+        "assert all(torch.equal(v, sd0[k]) for k, v in model.state_dict().items())\n"
+        "assert fs.flat_grad.numel() == 25953\n"
+        "fs.flat_grad.copy_(torch.arange(fs.n_live, dtype=torch.float32) * (r + 1))\n"
+        "dist.all_reduce(fs.flat_grad)\n"
+        "live = list(model.egnn.parameters()) + list(model.mlp.parameters())\n"
+        "off = 0\n"
+        "for p in live:\n"
+        "    assert p.grad.data_ptr() == fs.flat_grad[off:].data_ptr() and torch.all(p.grad.flatten() == 3.0 * torch.arange(off, off + p.numel()))\n"
+        "    off += p.numel()\n"
+        "params = list(model.parameters())\n"
         "opt = torch.optim.Adam(params, lr=1e-3); opt.step()\n"
         "chk = torch.cat([p.detach().flatten() for p in params]).double().sum().reshape(1)\n"
         "both = [torch.zeros(1, dtype=torch.float64) for _ in range(w)]; dist.all_gather(both, chk)\n"
@@ -253,3 +267,33 @@ def test_pack_cache_and_grad_unpacker_gather_paths(golden_dir):
     assert torch.equal(g0.layer_pack(), packing.pack_layer(g0))
     got = packing.GradUnpacker(packing.unpack_layer_grad, packing.LAYER_PACK, g0)(torch.arange(packing.LAYER_PACK, dtype=torch.float32))
     assert [tuple(t.shape) for t in got] == [tuple(p.shape) for p in g0.parameters()]
+
+
+def test_flat_state_packs_and_gradient_maps(golden_dir):
+    """packing.FlatState (the training step's one-gather weight packs and one-gather gradient unpacking): the packs
+    equal the per-module builders, follow in-place parameter updates, the gradient map is the inverse permutation, the
+    dead parameters keep grad = None, state_dict is unchanged."""
+    model = P.build_model(os.path.join(golden_dir, "checkpoint-3dmatch.pth"), device="cpu", variant="train")
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    fs = packing.FlatState(model)
+    assert all(torch.equal(v, sd0[k]) for k, v in model.state_dict().items())
+    with torch.no_grad():
+        model.egnn.gcl_1.coord_mlp[0].weight.add_(0.25); model.mlp[2].bias.sub_(1.0)
+    fs.refresh_packs()
+    for i in range(3):
+        assert torch.equal(fs.layer_packs[i], packing.pack_layer(model.egnn._modules["gcl_%d" % i]))
+    assert torch.equal(fs.pack_in, packing.pack_linear32(model.egnn.embedding_in))
+    assert torch.equal(fs.pack_out, packing.pack_linear32(model.egnn.embedding_out))
+    assert torch.equal(fs.pack_head, packing.pack_head(model.mlp))
+    fs.gpack_buf.copy_(torch.randn(fs.gpack_buf.numel()))
+    fs.gather_gradients()
+    for i in range(3):
+        gcl = model.egnn._modules["gcl_%d" % i]
+        for a, prm in zip(packing.unpack_layer_grad(fs.layer_gpacks[i], gcl), gcl.parameters()):
+            assert torch.equal(a, prm.grad)
+    for a, prm in zip(packing.unpack_head_grad(fs.gpack_head, model.mlp), model.mlp.parameters()):
+        assert torch.equal(a, prm.grad)
+    for a, prm in zip(packing.unpack_linear32_grad(fs.gpack_out, model.egnn.embedding_out), model.egnn.embedding_out.parameters()):
+        assert torch.equal(a, prm.grad)
+    n_grad = sum(p.grad is not None for p in model.parameters())
+    assert n_grad == 85 and len(list(model.parameters())) == 97
