@@ -83,10 +83,11 @@ class GraphedTrainStep:
         dev = sp.device
         B = self.B
         self.state = packing.FlatState(model)
+        # static input buffers of the graph (own storage: .to() / .contiguous() alias the example batch when nothing changes)
         self.feat_all = torch.cat([sf, tf]).to(torch.float32).contiguous()
         self.x_all = torch.cat([sp, tp]).to(torch.float32).contiguous()
-        self.labels_f = labels.to(torch.float32).reshape(B, self.N).contiguous()
-        self.gt_pose = gt.to(torch.float32).contiguous()
+        self.labels_f = labels.to(torch.float32).reshape(B, self.N).clone()
+        self.gt_pose = gt.to(torch.float32).clone()
         self.top_k = int(model.top_k)
         # optimizer state before the warm-up (None = not created yet)
         saved_state = {id(p): {n: (v.clone() if torch.is_tensor(v) else v) for n, v in st.items()} for p, st in self.opt.state.items()}

@@ -1,0 +1,33 @@
+"""Developer script for compute-sanitizer (memcheck / initcheck / racecheck): two eager training steps through the module
+API and two steps of the lean launch sequence (GraphedTrainStep._step without capture) on a small batch."""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import se3_equi_graph_registration_b200 as P
+from se3_equi_graph_registration_b200 import packing
+DEV = "cuda:0"
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+def mk():
+    m = P.build_model(os.path.join(ROOT, "tests", "golden", "checkpoint-3dmatch.pth"), device=DEV, variant="train")
+    with torch.no_grad():
+        m.egnn.embedding_out.weight.mul_(0.005); m.egnn.embedding_out.bias.mul_(0.005)
+    return m
+keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
+batches = [tuple(P.synthetic.make_batch(40 + i, 2, n=N)[k].to(DEV) for k in keys) for i in range(2)]
+ones = torch.ones(2, N * 16, 1, device=DEV)
+m1 = mk(); o1 = torch.optim.Adam(m1.parameters(), lr=1e-4)
+for i in range(2):
+    sf, sp, tf, tp, corr, labels, gt = batches[i]
+    es, et = P.knn_graph_batch(sp, 16), P.knn_graph_batch(tp, 16)
+    print("eager", float(P.train.train_step(m1, o1, (sf, sp, es, ones, tf, tp, et, ones, corr, labels, gt))))
+m2 = mk(); o2 = torch.optim.Adam(m2.parameters(), lr=1e-4)
+step = P.train.GraphedTrainStep.__new__(P.train.GraphedTrainStep)
+sf, sp, tf, tp, corr, labels, gt = batches[0]
+step.model, step.opt, step.k, step.group, step.world, step.B, step.N, step.top_k = m2, o2, 16, None, 1, 2, N, 128
+step.state = packing.FlatState(m2)
+step.feat_all = torch.cat([sf, tf]).contiguous(); step.x_all = torch.cat([sp, tp]).contiguous()
+step.labels_f = labels.float().reshape(2, N).contiguous(); step.gt_pose = gt.float().contiguous()
+for i in range(2):
+    step.load(batches[i])
+    print("lean", step._step().tolist()[:5])
+torch.cuda.synchronize()
