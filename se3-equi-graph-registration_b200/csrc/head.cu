@@ -681,20 +681,30 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(con
         *reinterpret_cast<float4 *>(a.dh_src + (nb + i) * H + 4 * lane8) = make_float4(ds * ht.x, ds * ht.y, ds * ht.z, ds * ht.w);
         *reinterpret_cast<float4 *>(a.dh_tgt + (nb + i) * H + 4 * lane8) = make_float4(ds * hs.x, ds * hs.y, ds * hs.z, ds * hs.w);
     }
-    if (!a.top_idx) return;
-    // ---- correspondence loss backward (3dm:760-772): BCEWithLogits(mlp([h_s | h_t][top-k]), labels[top-k]), mean over
-    // pairs * k.  One warp per selected row: recompute the mlp, push d score back through it into the row of dh_src /
-    // dh_tgt (rows of this pair: written above by this CTA) and into the head-pack gradient (shared-memory partial sums,
-    // one atomicAdd per entry and CTA). ----
-    __threadfence_block();
-    __syncthreads();
-    float *swp = dyn;                       // head pack [HEAD_PACK] | its gradient [HEAD_PACK]  (2 n >= 2 * HEAD_PACK is checked on the host)
-    float *sgp = dyn + HEAD_PACK;
+}
+
+// ---- correspondence loss backward (3dm:760-772): BCEWithLogits(mlp([h_s | h_t][top-k]), labels[top-k]), mean over
+// pairs * k.  grid (pairs, CB_SPLIT), one warp per selected row: recompute the mlp, push d score back through it into the
+// row of dh_src / dh_tgt (already written by head_train_backward_kernel; the rows of a pair's top-k set are distinct) and
+// into the head-pack gradient (registers per warp -> shared memory per CTA -> one global atomicAdd per entry and CTA). ----
+constexpr int CB_SPLIT = 4, CB_THREADS = 256;
+__global__ void __launch_bounds__(CB_THREADS) corr_loss_backward_kernel(const HeadTrainBwdArgs a) {
+    __shared__ __align__(16) float swp[HEAD_PACK];
+    __shared__ float sgp[HEAD_PACK];
+    const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
+    const size_t nb = (size_t)b * n;
     for (int i = tid; i < HEAD_PACK; i += blockDim.x) { swp[i] = __ldg(a.head_pack + i); sgp[i] = 0.f; }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const float gscale = __ldg(a.corr_scale) / (float)(a.pairs * (a.k < n ? a.k : n));
-    for (int r = warp; r < a.k; r += nwarps) {
+    // weight gradients: every lane owns the entries of ITS unit in registers across the warp's rows (lane = output unit of
+    // the first / second Linear, lane < 16: of the last two), one shared-memory atomicAdd per entry and WARP at the end
+    float gW0[64], gW1[32], gb0 = 0.f, gb1 = 0.f, gw2 = 0.f, gb2 = 0.f;      // dW0T[in][lane], dW1T[in][lane < 16]
+#pragma unroll
+    for (int i = 0; i < 64; ++i) gW0[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) gW1[i] = 0.f;
+    for (int r = blockIdx.y * nwarps + warp; r < a.k; r += gridDim.y * nwarps) {
         const int i = __ldg(a.top_idx + (size_t)b * a.k + r);
         if (i < 0) continue;                                       // fewer than k points
         const float zs = __ldg(a.h_out_src + (nb + i) * H + lane), zt = __ldg(a.h_out_tgt + (nb + i) * H + lane);
@@ -704,37 +714,45 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(con
         // last Linear (16 -> 1)
         float dh1 = 0.f;
         if (lane < 16) {
-            atomicAdd(sgp + HOFF_W2 + lane, dsc * m.h1);
+            gw2 = fmaf(dsc, m.h1, gw2);
             dh1 = m.h1 > 0.f ? dsc * swp[HOFF_W2 + lane] : 0.f;
-            atomicAdd(sgp + HOFF_B1 + lane, dh1);
+            gb1 += dh1;
         }
-        if (lane == 0) atomicAdd(sgp + HOFF_B2, dsc);
-        // middle Linear (32 -> 16): dW1T[i][j] += h0[i] dh1[j];  dh0[i] = sum_j W1T[i][j] dh1[j]
+        gb2 += dsc;
+        // middle Linear (32 -> 16): dW1T[i][j] += h0[i] dh1[j] (lane j < 16 owns column j);  dh0[i] = sum_j W1T[i][j] dh1[j]
         float dh0 = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
-            const float dj = __shfl_sync(0xffffffffu, dh1, j);
-            atomicAdd(sgp + HOFF_W1T + 16 * lane + j, m.h0 * dj);
-            dh0 = fmaf(swp[HOFF_W1T + 16 * lane + j], dj, dh0);
-        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dh0 = fmaf(swp[HOFF_W1T + 16 * lane + j], __shfl_sync(0xffffffffu, dh1, j), dh0);
+#pragma unroll
+        for (int in = 0; in < 32; ++in) gW1[in] = fmaf(__shfl_sync(0xffffffffu, m.h0, in), dh1, gW1[in]);
         dh0 = m.h0 > 0.f ? dh0 : 0.f;
-        atomicAdd(sgp + HOFF_B0 + lane, dh0);
-        // first Linear (64 -> 32): dW0T[in][out] += z[in] dh0[out];  dz[in] = sum_out W0T[in][out] dh0[out]
+        gb0 += dh0;
+        // first Linear (64 -> 32): dW0T[in][out] += z[in] dh0[out] (lane owns column out = lane);  dz[in] = sum_out W0T[in][out] dh0[out]
         float dzs = 0.f, dzt = 0.f;
-#pragma unroll 4
+#pragma unroll 8
         for (int o = 0; o < 32; ++o) {
             const float d = __shfl_sync(0xffffffffu, dh0, o);
             dzs = fmaf(swp[HOFF_W0T + 32 * lane + o], d, dzs);
             dzt = fmaf(swp[HOFF_W0T + 32 * (32 + lane) + o], d, dzt);
         }
-#pragma unroll 4
+#pragma unroll
         for (int in = 0; in < 32; ++in) {
-            atomicAdd(sgp + HOFF_W0T + 32 * in + lane, __shfl_sync(0xffffffffu, zs, in) * dh0);
-            atomicAdd(sgp + HOFF_W0T + 32 * (32 + in) + lane, __shfl_sync(0xffffffffu, zt, in) * dh0);
+            gW0[in] = fmaf(__shfl_sync(0xffffffffu, zs, in), dh0, gW0[in]);
+            gW0[32 + in] = fmaf(__shfl_sync(0xffffffffu, zt, in), dh0, gW0[32 + in]);
         }
         a.dh_src[(nb + i) * H + lane] += dzs;
         a.dh_tgt[(nb + i) * H + lane] += dzt;
     }
+#pragma unroll
+    for (int in = 0; in < 64; ++in) atomicAdd(sgp + HOFF_W0T + 32 * in + lane, gW0[in]);
+    atomicAdd(sgp + HOFF_B0 + lane, gb0);
+    if (lane < 16) {
+#pragma unroll
+        for (int in = 0; in < 32; ++in) atomicAdd(sgp + HOFF_W1T + 16 * in + lane, gW1[in]);
+        atomicAdd(sgp + HOFF_B1 + lane, gb1);
+        atomicAdd(sgp + HOFF_W2 + lane, gw2);
+    }
+    if (lane == 0) atomicAdd(sgp + HOFF_B2, gb2);
     __syncthreads();
     for (int i = tid; i < HEAD_PACK; i += blockDim.x) {
         const float g = sgp[i];
@@ -1056,12 +1074,14 @@ static int head_train_backward_impl(const egspr::HeadTrainBwdArgs &a, int pairs,
         !a.dx_src || !a.dx_tgt || pairs <= 0 || n <= 0)
         return EGSPR_E_INVALID;
     if (2 * n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
-    size_t floats = 2 * (size_t)n;
-    if (a.top_idx && floats < 2 * (size_t)HEAD_PACK) floats = 2 * (size_t)HEAD_PACK;      // the pack + its gradient reuse the rows
-    const size_t smem = sizeof(float) * floats;
+    const size_t smem = sizeof(float) * 2 * (size_t)n;
     if (int e = ensure_smem(head_train_backward_kernel, smem)) return e;
     head_train_backward_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
+    if (a.top_idx) {
+        corr_loss_backward_kernel<<<dim3((unsigned)pairs, CB_SPLIT), CB_THREADS, 0, (cudaStream_t)stream>>>(a);
+        EGSPR_CHECK_LAUNCH();
+    }
     return EGSPR_OK;
 }
 
