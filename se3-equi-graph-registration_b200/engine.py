@@ -65,6 +65,7 @@ class RegistrationEngine:
         self._graph_key = [None, None]
         self.impl = 0
         self.launches_per_step = 0
+        self.stage_events = None     # set to [] before an un-graphed run(): receives (stage name, CUDA event after the stage)
 
     def _bind_inputs(self, s):
         self._set = s
@@ -93,17 +94,28 @@ class RegistrationEngine:
         head = self.model._pack_head.get()
         st = ops._stream()
         n_launch = 0
+
+        def mark(name):
+            if self.stage_events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                self.stage_events.append((name, ev))
+
+        mark("start")
         if self.knn_brute_force:
             _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), None, 0, st), "egspr_knn_build"); n_launch += 1
         else:
             _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), p(self.knn_ws), self.knn_ws_bytes, st),
                        "egspr_knn_build"); n_launch += 2
+        mark("knn")
         _lib.check(lib.egspr_csr_from_nbr(p(self.nbr), C, N, k, p(self.csr_ptr), p(self.csr_row), p(self.csr_col),
                                           p(self.csr_eid), p(self.ws), self.ws_bytes, p(self.err), st), "egspr_csr_from_nbr")
-        # csr: one fused launch for small clouds (csr.cu: shared-memory build), else count/scan/fill/emit
+        # csr: one fused launch for small clouds (csr.cu: shared-memory build), else memset + count/scan/fill/emit
         n_launch += 1 if (4 * (2 * N + 1 + N * k) <= 200 * 1024 and C >= 16) else 4
+        mark("csr")
         _lib.check(lib.egspr_node_embed(p(self.feat), p(self.x), G, p(pin), p(layers[0]), p(self.h[0]), p(self.x4[0]),
                                         p(self.P[0]), p(self.Q[0]), st), "egspr_node_embed"); n_launch += 1
+        mark("embed")
         cur = 0
         L = len(layers)
         for i in range(L):
@@ -117,6 +129,7 @@ class RegistrationEngine:
                 None if last else p(self.P[nxt]), None if last else p(self.Q[nxt]), p(self.agg_ws), int(self.impl), st),
                 "egspr_egcl_forward")
             n_launch += 2 if self.impl in (0, 3, 4) else 1
+            mark("layer%d" % i)
             cur = nxt
         self.h_out = self.h[cur].view(C, N, H)
         ho, xo = self.h_out, self.x_out
@@ -124,6 +137,7 @@ class RegistrationEngine:
                                        p(ho[:B]), p(ho[B:]), p(xo[:B]), p(xo[B:]), p(self.labels), p(self.gt_pose),
                                        p(head), B, N, int(self.model.top_k), p(self.w), p(self.R), p(self.t), p(self.Hm),
                                        p(self.loss_parts), st), "egspr_head_eval"); n_launch += 1
+        mark("head")
         self.launches_per_step = n_launch
 
     def run(self):

@@ -87,3 +87,18 @@ def make_cloud(seed, n, density=75.85):
     rng = np.random.default_rng(seed)
     side = (n / density) ** (1.0 / 3.0)
     return (rng.random((n, 3)) * side).astype(np.float32)
+
+
+def make_sweep_batch(seed, batch, n, feat_dim=32, pin=False):
+    """Scaling-sweep batch (BASELINE config 5): constant-density uniform cubes of n points (make_cloud), targets = the
+    rigidly moved sources + 1 cm noise, all points inliers, unit-norm features."""
+    base = make_batch(seed, batch, n=16, feat_dim=feat_dim)                 # poses only
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.stack([torch.from_numpy(make_cloud(seed * 977 + i, n)) for i in range(batch)])
+    R, t = base["gt_pose"][:, :3, :3], base["gt_pose"][:, :3, 3]
+    f = torch.nn.functional.normalize(torch.randn(batch, n, feat_dim, generator=g), dim=-1)
+    out = {"src_pts": pts, "tgt_pts": pts @ R.transpose(1, 2) + t[:, None, :] + 0.01 * torch.randn(batch, n, 3, generator=g),
+           "src_feat": f, "tgt_feat": torch.nn.functional.normalize(f + 0.2 * torch.randn(batch, n, feat_dim, generator=g), dim=-1),
+           "labels": torch.ones(batch, n), "gt_pose": base["gt_pose"],
+           "corr": torch.arange(n, dtype=torch.float32)[None, :, None].expand(batch, n, 2).contiguous()}
+    return {k: (v.pin_memory() if pin else v) for k, v in out.items()}
