@@ -36,9 +36,20 @@ def knn_graph(x, k, batch=None, loop=False, flow="source_to_target", cosine=Fals
         raise NotImplementedError("egspr_b200.knn_graph: use knn_graph_batch for batches; cosine is unsupported")
     if x.dim() != 2 or x.shape[1] != 3:
         raise ValueError("x must be [N,3]")
-    if not loop:
-        raise NotImplementedError("the reference builds its graphs with loop=True (3dm:1005); loop=False is not built")
-    nbr = ops.knn_build(x.unsqueeze(0).to(torch.float32), k)
+    if loop:                                     # the reference's call sites (3dm:1005): self included
+        nbr = ops.knn_build(x.unsqueeze(0).to(torch.float32), k)
+    else:
+        # torch_cluster's default: the query point itself (by INDEX) is not a neighbour.  k + 1 candidates, drop the
+        # entry equal to the centre id if it is among them, else the farthest one (> k exact duplicates of a point)
+        n = x.shape[0]
+        if k + 1 > 32:
+            raise NotImplementedError("loop=False supports k <= 31")
+        cand = ops.knn_build(x.unsqueeze(0).to(torch.float32), k + 1)[0].long()          # [N, k+1]
+        centre = torch.arange(n, device=x.device)[:, None]
+        is_self = cand == centre
+        drop = torch.where(is_self.any(1), is_self.float().argmax(1), torch.full((n,), k, device=x.device))
+        keep = torch.arange(k + 1, device=x.device)[None, :] != drop[:, None]
+        nbr = cand[keep].view(1, n, k).to(torch.int32).contiguous()
     edges = ops.nbr_to_edges(nbr)[0]
     if flow == "target_to_source":
         edges = edges.flip(0)
@@ -74,15 +85,31 @@ def unsorted_segment_mean(data, segment_ids, num_segments):
     return s / cnt[:, None]
 
 
+# user-supplied edge indices are range-checked on the device while the CSR is built (bad ids are clamped and flagged);
+# the module entry points read the flag back -- one host sync per call, skipped during CUDA-graph capture -- and raise
+# like the reference's index_select / scatter_add_ would.  The engine / training step build their graphs from k-NN ids.
+CHECK_EDGE_INDICES = True
+
+
+def _checked(graph):
+    if CHECK_EDGE_INDICES and not torch.cuda.is_current_stream_capturing():
+        graph.check()
+    return graph
+
+
 def unsorted_segment_sum(data, segment_ids, num_segments):
-    """3dm:343-348, deterministic (ascending edge order) instead of atomics."""
-    import ctypes
+    """3dm:343-348, deterministic (ascending edge order) instead of atomics.  Forward only: the model's own segment sums
+    are fused into the layer kernels (and differentiated there); a tensor that requires grad is refused instead of
+    silently dropping its gradient."""
     from . import _lib
+    if torch.is_grad_enabled() and data.requires_grad:
+        raise NotImplementedError("unsorted_segment_sum is not differentiable here: use E_GCL / EGNN (their backward kernels "
+                                  "differentiate the fused segment sums) or detach the input")
     data = ops._req(data, "data", torch.float32, 2)
     ids = ops._req(segment_ids, "segment_ids", torch.int64, 1)
     E, C = data.shape
     edges = torch.stack([ids, torch.zeros_like(ids)]).unsqueeze(0)
-    g = ops.csr_from_edges(edges, num_segments)
+    g = _checked(ops.csr_from_edges(edges, num_segments))
     out = torch.empty((num_segments, C), dtype=torch.float32, device=data.device)
     with torch.cuda.device(data.device):
         _lib.check(_lib.lib().egspr_segment_sum(ops._ptr(data), C, ops._ptr(g.ptr), ops._ptr(g.eid), num_segments,
@@ -153,7 +180,7 @@ class E_GCL(nn.Module):
 
     def forward(self, h, edge_index, coord, edge_attr=None):
         """(h [N,32], [row,col], coord [N,3], edge_attr [E,1]|None) -> (h', coord', edge_attr)  3dm:280-289"""
-        graph = ops.csr_from_edges(_edges_to_tensor(edge_index), h.shape[0])
+        graph = _checked(ops.csr_from_edges(_edges_to_tensor(edge_index), h.shape[0]))
         ea = None if edge_attr is None else edge_attr.to(torch.float32)
         if _needs_grad(self, h, coord):
             self._check_supported()
@@ -212,7 +239,7 @@ class EGNN(nn.Module):
 
     def forward(self, h, x, edges, edge_attr):
         """(h [N,32], x [N,3], [row,col], edge_attr [E,1]) -> (h [N,32], x [N,3])  3dm:328-340"""
-        graph = ops.csr_from_edges(_edges_to_tensor(edges), h.shape[0])
+        graph = _checked(ops.csr_from_edges(_edges_to_tensor(edges), h.shape[0]))
         ea = None if edge_attr is None else edge_attr.to(torch.float32)
         ho, xo = self.forward_batch(h.unsqueeze(0).to(torch.float32), x.unsqueeze(0).to(torch.float32), graph,
                                     edge_attr=ea, edge_attr_const=0.0)
@@ -298,13 +325,13 @@ class CrossAttentionPoseRegression(nn.Module):
         tensors = torch.is_tensor(edges_src) and torch.is_tensor(edges_tgt) and edges_src.shape == edges_tgt.shape
         if tensors and (edge_attr_src is None) == (edge_attr_tgt is None):
             # both cloud sets as ONE graph of 2B clouds: one launch sequence (sources = clouds 0..B-1, targets B..2B-1)
-            g = ops.csr_from_edges(torch.cat([edges_src, edges_tgt]).to(torch.int64), N)
+            g = _checked(ops.csr_from_edges(torch.cat([edges_src, edges_tgt]).to(torch.int64), N))
             ea = None if edge_attr_src is None else torch.cat([edge_attr_src, edge_attr_tgt])
             h, x = self.egnn.forward_batch(torch.cat([h_src, h_tgt]).to(torch.float32), torch.cat([x_src, x_tgt]).to(torch.float32),
                                            g, edge_attr=ea, edge_attr_const=0.0 if ea is not None else 1.0)
             return h[:B], x[:B], h[B:], x[B:]
-        g_src = edges_src if isinstance(edges_src, ops.BatchGraph) else ops.csr_from_edges(edges_src.to(torch.int64), N)
-        g_tgt = edges_tgt if isinstance(edges_tgt, ops.BatchGraph) else ops.csr_from_edges(edges_tgt.to(torch.int64), N)
+        g_src = edges_src if isinstance(edges_src, ops.BatchGraph) else _checked(ops.csr_from_edges(edges_src.to(torch.int64), N))
+        g_tgt = edges_tgt if isinstance(edges_tgt, ops.BatchGraph) else _checked(ops.csr_from_edges(edges_tgt.to(torch.int64), N))
         hs, xs = self.egnn.forward_batch(h_src.to(torch.float32), x_src.to(torch.float32), g_src,
                                          edge_attr=edge_attr_src, edge_attr_const=0.0 if edge_attr_src is not None else 1.0)
         ht, xt = self.egnn.forward_batch(h_tgt.to(torch.float32), x_tgt.to(torch.float32), g_tgt,

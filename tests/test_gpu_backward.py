@@ -331,3 +331,37 @@ def test_pose_loss_kernel_matches_reference_function():
     assert torch.allclose(rl.detach().cpu().double(), rl_ref.detach(), atol=2e-6) and torch.allclose(tl.detach().cpu().double(), tl_ref.detach(), atol=2e-6)
     assert rel(Rg.grad, Rr.grad) < 1e-5 and rel(tg.grad, tr.grad) < 1e-5
     assert float(Rg.grad[0].abs().max()) == 0.0
+
+
+def test_full_size_gradients_against_fp64_autograd(golden_dir):
+    """BASELINE config 4's real cloud size: ONE pair of 2048 points (k = 16, 65,536 edges) through the module API, every
+    one of the 85 gradients against fp64 autograd of the oracle on the same inputs (tempered weights: well-conditioned
+    Kabsch), same 1e-3 * max|g| bar as the small fixtures."""
+    model = _model(golden_dir, 0.005)
+    model.train()
+    data = P.synthetic.make_batch(77, 1, n=2048)
+    nbr_s = ops.knn_build(data["src_pts"].to(DEV), 16).cpu(); nbr_t = ops.knn_build(data["tgt_pts"].to(DEV), 16).cpu()
+    es, et = edges_of(nbr_s.long()), edges_of(nbr_t.long())
+    sd = {k: (v.detach().cpu().double().requires_grad_(True) if v.is_floating_point() else v.cpu()) for k, v in model.state_dict().items()}
+    d64 = {k: v.double() for k, v in data.items()}
+    out = O.forward_train(sd, d64["src_feat"], d64["src_pts"], es, d64["tgt_feat"], d64["tgt_pts"], et, data["labels"], d64["gt_pose"])
+    rot, trans = O.pose_loss(out[0], out[1], d64["gt_pose"])
+    ref_loss = out[2] + rot.mean() + trans.mean()
+    ref_loss.backward()
+    dv = {k: v.to(DEV) for k, v in data.items()}
+    o = model(dv["src_feat"], dv["src_pts"], es.to(DEV), None, dv["tgt_feat"], dv["tgt_pts"], et.to(DEV), None, dv["corr"], dv["labels"], dv["gt_pose"])
+    loss = P.train.training_loss(o, dv["gt_pose"])
+    assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+    loss.backward()
+    worst, n = 0.0, 0
+    for k, p in model.named_parameters():
+        gref = sd[k].grad
+        if gref is None:
+            assert p.grad is None, k
+            continue
+        e = rel(p.grad, gref)
+        worst = max(worst, e)
+        assert e < G_TOL, (k, e)
+        n += 1
+    assert n == 85
+    print(f"full-size gradient check: worst relative-to-max error {worst:.2e}")

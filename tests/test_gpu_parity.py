@@ -473,9 +473,23 @@ def test_device_pose_metrics_match_reference_metrics(golden_dir, model):
     eng = P.RegistrationEngine(model, batch=B, n=N, k=16, use_graph=False)
     R, t = eng.register(*[data[k] for k in keys])
     got = eng.metrics().cpu().numpy()
-    ref = P.metrics.evaluate_batch(R.cpu().numpy(), t.cpu().numpy(), data["gt_pose"].numpy(), data["src_pts"].numpy(), data["tgt_pts"].numpy())
+    Rn, tn = R.cpu().numpy(), t.cpu().numpy()
+    ref = {k: [] for k in ("rot_err", "trans_err", "recall", "precision", "f1")}
+    for b in range(B):                                        # the oracle's numpy restatement, pair by pair like evl:1249-1281
+        T = np.eye(4); T[:3, :3] = Rn[b].astype(np.float64); T[:3, 3] = tn[b].astype(np.float64)
+        gtp = data["gt_pose"][b].numpy().astype(np.float64)
+        re, te = O.calculate_pose_error(gtp, T)
+        rec, prec = O.registration_recall(gtp, T, data["src_pts"][b].numpy().astype(np.float64), data["tgt_pts"][b].numpy().astype(np.float64))
+        for k, v in zip(ref, (re, te, rec, prec, 2 * prec * rec / (prec + rec + 1e-6))):
+            ref[k].append(v)
     for j, key in enumerate(("rot_err", "trans_err", "recall", "precision", "f1")):
         assert np.allclose(got[:, j], np.asarray(ref[key], dtype=np.float64), rtol=1e-9, atol=1e-9), key
+    # the module-level mirrors of the reference's two functions run the same kernel: known answers of the reference file
+    for c in torch.load(os.path.join(golden_dir, "metrics_kat.pt"), weights_only=False):
+        re, te = P.metrics.calculate_pose_error(c["gt"], c["pred"])
+        rec, prec = P.metrics.registration_recall(c["gt"], c["pred"], c["src"], c["tgt"])
+        assert np.isclose(re, c["re"], atol=2e-2) and np.isclose(te, c["te"], rtol=1e-5, atol=1e-4)       # fp32 pose in, fp64 math
+        assert np.isclose(rec, c["recall"], atol=1e-6) and np.isclose(prec, c["precision"], atol=1e-6)
     # a pose that is exactly the ground truth: zero errors, recall = sqrt(fraction of inliers within tau)
     gt = data["gt_pose"].to(DEV)
     m = ops.pose_metrics(gt[:, :3, :3].contiguous(), gt[:, :3, 3].contiguous(), gt, data["src_pts"].to(DEV), data["tgt_pts"].to(DEV)).cpu().numpy()
@@ -543,3 +557,41 @@ def test_feature_nn_matches_reference_correspondence_search(ns, nt):
     corr_m, _ = ops.feature_correspondences(torch.from_numpy(fs).to(DEV), torch.from_numpy(ft).to(DEV), use_mutual=True)
     got = set(map(tuple, corr_m.cpu().numpy().tolist())); want = set(map(tuple, corr_m_ref.tolist()))
     assert len(got ^ want) <= max(2, int(0.002 * len(want)))
+
+
+@pytest.mark.parametrize("n,k,extent", [(2048, 16, 3.0), (8192, 16, 100.0), (20000, 32, 3.0)])
+def test_knn_kernel_against_independent_kdtree(n, k, extent):
+    """The GPU k-NN (cell-grid search) against scipy cKDTree on tie-free clouds: identical ids in identical order on every
+    row whose top-(k+1) distances are separated beyond fp32 resolution -- an oracle-independent check of a1."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(77 + n)
+    x = (rng.random((n, 3)) * extent).astype(np.float32)
+    d, idx = cKDTree(x.astype(np.float64)).query(x.astype(np.float64), k=k + 1)
+    d2 = d ** 2
+    ok = (np.diff(d2, axis=1) > 1e-5 * np.maximum(d2[:, 1:], 1e-12)).all(axis=1)
+    assert ok.mean() > 0.9
+    got = ops.knn_build(torch.from_numpy(x)[None].to(DEV), k)[0].cpu().numpy()
+    assert np.array_equal(got[ok], idx[ok, :k].astype(np.int32))
+
+
+def test_module_api_rejects_bad_edge_indices_and_loop_false(model):
+    """Advice items: out-of-range edge ids raise (the reference's index ops would) instead of being clamped silently;
+    knn_graph(loop=False) = torch_cluster's default (the centre itself is not a neighbour); unsorted_segment_sum refuses
+    inputs that require grad."""
+    n = 300
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(n, 3, generator=g).to(DEV)
+    h = torch.randn(n, 32, generator=g).to(DEV)
+    e = P.knn_graph(x, 16, loop=True)
+    bad = e.clone(); bad[0, 5] = n + 7
+    with pytest.raises(IndexError):
+        model.egnn(h, x, [bad[0], bad[1]], torch.ones(bad.shape[1], 1, device=DEV))
+    with pytest.raises(IndexError):
+        P.unsorted_segment_sum(torch.ones(4, 2, device=DEV), torch.tensor([0, 1, 9, 2], device=DEV), 3)
+    e0 = P.knn_graph(x, 8, loop=False)
+    assert e0.shape == (2, n * 8) and int((e0[0] == e0[1]).sum()) == 0
+    ref = knn_oracle.knn(x.cpu().numpy(), 9)
+    want = np.stack([[j for j in ref[i] if j != i][:8] for i in range(n)])
+    assert np.array_equal(e0[0].view(n, 8).cpu().numpy(), want)
+    with pytest.raises(NotImplementedError):
+        P.unsorted_segment_sum(torch.ones(4, 2, device=DEV, requires_grad=True), torch.tensor([0, 1, 1, 2], device=DEV), 3)

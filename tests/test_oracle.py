@@ -90,14 +90,14 @@ def test_knn_golden_fixture_is_oracle_output(golden_dir):
 
 
 def test_metrics_known_answers(golden_dir):
+    """The oracle's numpy restatement of tools/evaluation_metrics.py against the known answers that file itself produced
+    (the product's metrics are the device kernel: checked against the same fixture in tests/test_gpu_parity.py)."""
     cases = torch.load(os.path.join(golden_dir, "metrics_kat.pt"), weights_only=False)
-    from se3_equi_graph_registration_b200 import metrics
     for c in cases:
-        for impl in (O, metrics):
-            re, te = impl.calculate_pose_error(c["gt"], c["pred"])
-            rec, prec = impl.registration_recall(c["gt"], c["pred"], c["src"], c["tgt"])
-            assert np.isclose(re, c["re"], atol=1e-9) and np.isclose(te, c["te"], atol=1e-9)
-            assert np.isclose(rec, c["recall"]) and np.isclose(prec, c["precision"])
+        re, te = O.calculate_pose_error(c["gt"], c["pred"])
+        rec, prec = O.registration_recall(c["gt"], c["pred"], c["src"], c["tgt"])
+        assert np.isclose(re, c["re"], atol=1e-9) and np.isclose(te, c["te"], atol=1e-9)
+        assert np.isclose(rec, c["recall"]) and np.isclose(prec, c["precision"])
 
 
 def test_kabsch_oracle_recovers_known_pose_and_reflection_fix():
@@ -199,3 +199,44 @@ def test_oracle_gradients_match_reference_golden(golden_dir, scenario, case, gfi
         r64 = gg[scenario + "_f64"]["grads"]
         worst = max(float((ref["grads"][k] - r64[k]).abs().max() / r64[k].abs().max()) for k in r64 if r64[k] is not None)
         assert worst < 1e-3
+
+
+def _tie_free_cloud(rng, n, extent):
+    """Points whose pairwise squared distances (fp32, the spec's fma order) are all distinct per query row."""
+    return (rng.random((n, 3)) * extent).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,k,extent", [(600, 16, 3.0), (2048, 16, 3.0), (1500, 32, 100.0)])
+def test_knn_oracle_against_independent_kdtree(n, k, extent):
+    """INDEPENDENT pin of oracle/knn_oracle.c (torch_cluster is absent): on clouds without distance ties
+    any correct k-NN returns the same ids in the same order, so scipy.spatial.cKDTree (different algorithm, different
+    author, fp64) must agree exactly.  Rows where cKDTree's own top-(k+1) distances are closer than fp32 resolution are
+    excluded (there the fp32 spec may legitimately order differently)."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(123 + n)
+    x = _tie_free_cloud(rng, n, extent)
+    d, idx = cKDTree(x.astype(np.float64)).query(x.astype(np.float64), k=k + 1)
+    d2 = d ** 2
+    gap = np.diff(d2, axis=1)
+    ok = (gap > 1e-5 * np.maximum(d2[:, 1:], 1e-12)).all(axis=1)           # well-separated ranks only
+    assert ok.mean() > 0.9
+    got = knn_oracle.knn(x, k)
+    assert np.array_equal(got[ok], idx[ok, :k].astype(np.int32))
+
+
+def test_knn_oracle_duplicate_heavy_properties():
+    """On duplicate-heavy clouds (many exact ties) the spec's order is (d2, index): ids sorted by that key, every
+    returned distance <= every omitted distance, ties broken towards the lower index."""
+    rng = np.random.default_rng(5)
+    n, k = 700, 16
+    x = (rng.random((n, 3)) * 3).astype(np.float32)
+    x[200:500] = x[rng.integers(0, 200, 300)]                               # > 40 % repeated points
+    got = knn_oracle.knn(x, k)
+    d2 = ((x[:, None, :].astype(np.float64) - x[None].astype(np.float64)) ** 2).sum(-1)
+    for i in range(0, n, 7):
+        row = got[i]
+        key = [(np.float32(d2[i, j]), j) for j in row]
+        assert key == sorted(key), i
+        kth = key[-1]
+        others = np.setdiff1d(np.arange(n), row)
+        assert all((np.float32(d2[i, j]), j) > kth for j in others), i
