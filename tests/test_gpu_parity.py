@@ -89,8 +89,6 @@ def test_knn_graph_matches_torch_cluster_layout():
     assert torch.equal(e[1].cpu(), torch.arange(300).repeat_interleave(16))
     eb = P.knn_graph_batch(torch.stack([x, x.flip(0)]), 16)
     assert torch.equal(eb[0], e) and tuple(eb.shape) == (2, 2, 4800)
-    with pytest.raises(NotImplementedError):
-        P.knn_graph(x, 16, loop=False)
     with pytest.raises(Exception):
         ops.knn_build(x[None], 64)           # k > EGSPR_MAX_K -> EGSPR_E_UNSUPPORTED
 
