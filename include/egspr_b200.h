@@ -105,6 +105,9 @@ int egspr_node_embed(const float *feat, const float *x3, int64_t num_nodes, cons
  *       4 = impl 3 with the edge kernel in reduced precision (BASELINE config 2's "looser bound" edge MLP):
  *           single-pass TF32 operands (10-bit mantissa, round to nearest) and SiLU through MUFU.TANH;
  *           segment sums, node kernel and everything else as in impl 3.
+ *       5 = impl 3 with the edge kernel's MLPs in bf16 (BASELINE config 2 "bf16 edge MLP"): tcgen05.mma.kind::f16 with
+ *           bf16 activations (A operand in tensor memory, two K elements per column) and bf16 weights, fp32
+ *           accumulation; the 13 geometric inputs as two bf16 terms; SiLU through MUFU.TANH.
  *       3 | EGSPR_IMPL_EDGE_ONLY = the edge kernel of impl 3 alone (writes agg_ws, x4_out, x3_out; no node
  *           update) -- for benchmarks and profiling of that kernel. */
 #define EGSPR_IMPL_EDGE_ONLY 0x100

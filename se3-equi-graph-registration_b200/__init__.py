@@ -10,7 +10,7 @@ from . import _lib, packing, ops  # noqa: F401
 from .modules import (E_GCL, EGNN, CrossAttentionPoseRegression, knn_graph, knn_graph_batch,  # noqa: F401
                       get_edges_batch, get_edges_from_idx, unsorted_segment_sum, unsorted_segment_mean, egnn_equi_loss, pose_loss, compute_losses,
                       save_checkpoint, load_checkpoint)
-from .engine import RegistrationEngine  # noqa: F401
+from .engine import RegistrationEngine, PipelinedEngine  # noqa: F401
 from . import train  # noqa: F401
 
 

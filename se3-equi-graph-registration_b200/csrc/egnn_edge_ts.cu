@@ -111,9 +111,9 @@ __device__ __forceinline__ void silu2_tanh(float &x0, float &x1) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(x1));
     ffma2(x0, x1, x0, x1, t0, t1);
 }
-template <bool FAST>
+template <int MODE>
 __device__ __forceinline__ void silu_pair(float &x0, float &x1) {
-    if constexpr (FAST) silu2_tanh(x0, x1);
+    if constexpr (MODE != 0) silu2_tanh(x0, x1);
     else silu2(x0, x1);
 }
 __device__ __forceinline__ void issue_1xtf32_ts(uint32_t d, uint32_t ahi, uint64_t whi) {
@@ -131,8 +131,39 @@ __device__ __forceinline__ void issue_3xtf32_ts(uint32_t d, uint32_t ahi, uint32
     for (int k = 0; k < 4; ++k) umma_tf32_ts(d, ahi + 8 * k, wlo + 2 * k, IDESC_TF32_M128_N32, 1);
 }
 
-template <bool FAST>
+// ---- bf16 mode (MODE 2, BASELINE config 2's "bf16 edge MLP"): tcgen05.mma.kind::f16 with bf16 A (tensor memory, two K
+// elements per 32-bit column: 16 columns per 32-vector, ONE tcgen05.st) and bf16 weight tiles, fp32 accumulation; the 13
+// geometric inputs travel as two bf16 terms (their magnitudes follow the coordinate scale).  K = 16 per instruction:
+// 2 MMAs per stage instead of 12 (fp32) / 4 (TF32). ----
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {       // low half = bf16(lo), high half = bf16(hi), RN
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void store_bf16_tmem(uint32_t taddr, const float (&v)[32]) {
+    float pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = __uint_as_float(pack_bf16x2(v[2 * i], v[2 * i + 1]));
+    tmem_st16(taddr, pk);
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t IDESC_BF16_M128_N32 = idesc_bf16(128, 32, 0, 0);
+__device__ __forceinline__ void issue_bf16_ts(uint32_t d, uint32_t a, uint64_t w) {       // K = 32: two K-steps of 8 columns / 32 bytes
+    umma_bf16_ts(d, a, w, IDESC_BF16_M128_N32, 0);
+    umma_bf16_ts(d, a + 8, w + 2, IDESC_BF16_M128_N32, 1);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerArgs a, float *__restrict__ agg_out) {
+    constexpr bool FAST = MODE != 0;
+    constexpr bool BF16 = MODE == 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, grp = tid >> 7, ht = tid & 127, lane = tid & 31, hw = ht >> 5;
@@ -153,6 +184,22 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     pdl_trigger();                  // the next kernel's prologue may overlap this kernel's tail
 
     // ---- one-time setup: swizzled hi/lo weight tiles (B operands: row = output o, K = input) ----
+    if constexpr (BF16) {
+        // bf16 tiles: row o = 128 bytes, the 32 K elements in its first 64 bytes (16-byte chunk c at c ^ (o & 7));
+        // stage 1: K 0..15 and K 16..31 both = [Wg(12) | w_edge_attr | 0 0 0] (the operand is [hi(geo) | lo(geo)])
+        for (int i = tid; i < 1024; i += V_THREADS) {
+            const int o = i >> 5, k = i & 31, kk = k & 15;
+            float w1 = 0.f;
+            if (kk < 12) w1 = __ldg(a.layer_pack + OFF_WG + 32 * kk + o);
+            else if (kk == 12) w1 = __ldg(a.layer_pack + OFF_WEA + o);
+            const float w2 = ((o >> 3) == (k >> 3)) ? __ldg(a.layer_pack + OFF_W2P + 64 * (o >> 3) + 8 * (k & 7) + (o & 7)) : 0.f;
+            const float w3 = __ldg(a.layer_pack + OFF_WC1 + i);
+            const int off = sw128_off_bf16(o, k);
+            *reinterpret_cast<uint16_t *>(base + VS_W + off) = (uint16_t)(pack_bf16x2(w1, 0.f) & 0xffffu);
+            *reinterpret_cast<uint16_t *>(base + VS_W + 4096 + off) = (uint16_t)(pack_bf16x2(w2, 0.f) & 0xffffu);
+            *reinterpret_cast<uint16_t *>(base + VS_W + 12288 + off) = (uint16_t)(pack_bf16x2(w3, 0.f) & 0xffffu);
+        }
+    } else
     for (int i = tid; i < 1024; i += V_THREADS) {
         const int o = i >> 5, k = i & 31;
         {   // stage 1: K 0..15 = hi of [Wg(12) | w_edge_attr | 0 0 0], K 16..31 = lo of the same
@@ -289,7 +336,15 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         geo[9] = az; geo[10] = bz; geo[11] = ez;
         geo[12] = ea; geo[13] = 0.f; geo[14] = 0.f; geo[15] = 0.f;
         float hi[16], lo[16];
-        if constexpr (FAST) {
+        if constexpr (BF16) {           // [hi(geo) (16 bf16 = 8 columns) | lo(geo) (8 columns)]
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t ph = pack_bf16x2(geo[2 * i], geo[2 * i + 1]);
+                hi[i] = __uint_as_float(ph);
+                hi[8 + i] = __uint_as_float(pack_bf16x2(geo[2 * i] - __uint_as_float(ph << 16), geo[2 * i + 1] - __uint_as_float(ph & 0xffff0000u)));
+            }
+            tmem_st16(tmem_w + 96, hi);
+        } else if constexpr (FAST) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) hi[i] = tf32_rna(geo[i]);
             tmem_st16(tmem_w + 96, hi);
@@ -358,8 +413,12 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(2);
         if (hw_u == 0 && elect_one()) {     // stage 1 is issued by warp 0, stage 2 by warp 1, stage 3 by warp 2
             fence_after_sync();
+            if constexpr (BF16) {
+                issue_bf16_ts(tD, tA1, dX1);
+            } else {
             umma_tf32_ts(tD, tA1 + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
             umma_tf32_ts(tD, tA1 + 8, dX1 + 2, IDESC_TF32_M128_N32, 1);
+            }
             if constexpr (!FAST) {
                 umma_tf32_ts(tD, tA1 + 16, dX1 + 0, IDESC_TF32_M128_N32, 1);     // lo x Whi
                 umma_tf32_ts(tD, tA1 + 24, dX1 + 2, IDESC_TF32_M128_N32, 1);
@@ -389,12 +448,13 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             const float4 qv = *reinterpret_cast<const float4 *>(qrow + 4 * i);
             fadd2(pv[i].x, pv[i].y, qv.x, qv.y); fadd2(pv[i].z, pv[i].w, qv.z, qv.w);
             fadd2(v[4 * i], v[4 * i + 1], pv[i].x, pv[i].y); fadd2(v[4 * i + 2], v[4 * i + 3], pv[i].z, pv[i].w);
-            silu_pair<FAST>(v[4 * i], v[4 * i + 1]); silu_pair<FAST>(v[4 * i + 2], v[4 * i + 3]);
+            silu_pair<MODE>(v[4 * i], v[4 * i + 1]); silu_pair<MODE>(v[4 * i + 2], v[4 * i + 3]);
         }
         __syncwarp();                   // every lane of the warp has read its Q row: refill the warp's rows for the next tile
         gather_q(cn);
         // ---------------- stage 2: per-head second Linear (block-diagonal) ----------------
-        if constexpr (FAST) store_tf32_tmem(tmem_w + 32, v);
+        if constexpr (BF16) store_bf16_tmem(tmem_w + 32, v);
+        else if constexpr (FAST) store_tf32_tmem(tmem_w + 32, v);
         else store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
         tmem_wait_st();
         fence_before_sync();
@@ -403,7 +463,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(6);
         if (hw_u == 1 && elect_one()) {
             fence_after_sync();
-            if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW2hi);
+            if constexpr (BF16) issue_bf16_ts(tD, tAhi, dW2hi);
+            else if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW2hi);
             else issue_3xtf32_ts(tD, tAhi, tAlo, dW2hi, dW2lo);
             umma_commit(mbar_u);
         }
@@ -439,7 +500,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             }
         }
         // ---------------- stage 3: coord_mlp.0; messages also to shared memory ----------------
-        if constexpr (FAST) store_tf32_tmem(tmem_w + 32, v);
+        if constexpr (BF16) store_bf16_tmem(tmem_w + 32, v);
+        else if constexpr (FAST) store_tf32_tmem(tmem_w + 32, v);
         else store_hilo_tmem(tmem_w + 32, tmem_w + 64, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -451,7 +513,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(9);
         if (hw_u == 2 && elect_one()) {
             fence_after_sync();
-            if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW3hi);
+            if constexpr (BF16) issue_bf16_ts(tD, tAhi, dW3hi);
+            else if constexpr (FAST) issue_1xtf32_ts(tD, tAhi, dW3hi);
             else issue_3xtf32_ts(tD, tAhi, tAlo, dW3hi, dW3lo);
             umma_commit(mbar_u);
         }
@@ -496,7 +559,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         for (int o = 0; o < 32; o += 4) {
             const float4 b = *reinterpret_cast<const float4 *>(sbc1 + o), wc = *reinterpret_cast<const float4 *>(swc2 + o);
             fadd2(v[o], v[o + 1], b.x, b.y); fadd2(v[o + 2], v[o + 3], b.z, b.w);
-            silu_pair<FAST>(v[o], v[o + 1]); silu_pair<FAST>(v[o + 2], v[o + 3]);
+            silu_pair<MODE>(v[o], v[o + 1]); silu_pair<MODE>(v[o + 2], v[o + 3]);
             ffma2(s4[0], s4[1], v[o], v[o + 1], wc.x, wc.y); ffma2(s4[2], s4[3], v[o + 2], v[o + 3], wc.z, wc.w);
         }
         const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
@@ -534,15 +597,14 @@ extern "C" int egspr_debug_read_ts(long long *host_dst) {
 }
 #endif
 
-int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, bool fast, cudaStream_t st) {
-    if (!(fast ? opt_in_smem(egcl_edge_ts_kernel<true>, V_SMEM_BYTES) : opt_in_smem(egcl_edge_ts_kernel<false>, V_SMEM_BYTES)))
-        return EGSPR_E_LAUNCH;
+int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, int mode, cudaStream_t st) {
+    auto kernel = mode == 2 ? egcl_edge_ts_kernel<2> : (mode == 1 ? egcl_edge_ts_kernel<1> : egcl_edge_ts_kernel<0>);
+    if (!opt_in_smem(kernel, V_SMEM_BYTES)) return EGSPR_E_LAUNCH;
     // one persistent CTA per SM; small graphs: at least ~2 tiles of edges per group
     int64_t grid = sm_count();
     const int64_t need = (a.num_nodes + 63) / 64;
     if (grid > need) grid = need;
-    const cudaError_t le = fast ? launch_pdl(egcl_edge_ts_kernel<true>, dim3((unsigned)grid), dim3(V_THREADS), V_SMEM_BYTES, st, a, agg_ws)
-                                : launch_pdl(egcl_edge_ts_kernel<false>, dim3((unsigned)grid), dim3(V_THREADS), V_SMEM_BYTES, st, a, agg_ws);
+    const cudaError_t le = launch_pdl(kernel, dim3((unsigned)grid), dim3(V_THREADS), V_SMEM_BYTES, st, a, agg_ws);
     if (le != cudaSuccess || cudaGetLastError() != cudaSuccess) return EGSPR_E_LAUNCH;
     if (edge_only) return EGSPR_OK;      // bench / profiling: the edge stage alone (agg_ws, x4_out written)
     return launch_node_update_ts(a, agg_ws, st);

@@ -167,7 +167,7 @@ static int launch_layer(const LayerArgs &a, cudaStream_t st) {
     return EGSPR_OK;
 }
 
-int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, bool fast, cudaStream_t st);   // egnn_edge_ts.cu
+int launch_layer_ts(const LayerArgs &a, float *agg_ws, bool edge_only, int mode, cudaStream_t st);   // egnn_edge_ts.cu
 int launch_node_embed_ts(const float *feat, const float *x3, int64_t G, const float *embed_pack, const float *layer0_pack,
                          float *h, float *x4, float *P, float *Q, cudaStream_t st);   // egnn_node_ts.cu
 
@@ -200,19 +200,22 @@ extern "C" int egspr_egcl_forward(const float *h, const float *x4, const float *
     // impl 0 (auto): tensor-core path when scratch is available, else the fused CUDA-core kernel
     const bool big = num_nodes >= (int64_t)256 * 2 * sm_count();
     const bool edge_only = (impl & EGSPR_IMPL_EDGE_ONLY) != 0;
-    if (edge_only && (impl & 0xff) != 3 && (impl & 0xff) != 4) return EGSPR_E_UNSUPPORTED;
+    if (edge_only && (impl & 0xff) != 3 && (impl & 0xff) != 4 && (impl & 0xff) != 5) return EGSPR_E_UNSUPPORTED;
     switch (impl & 0xff) {
         case 0:
-            if (agg_ws) return launch_layer_ts(a, agg_ws, false, false, (cudaStream_t)stream);
+            if (agg_ws) return launch_layer_ts(a, agg_ws, false, 0, (cudaStream_t)stream);
             return big ? launch_layer<256>(a, (cudaStream_t)stream) : launch_layer<64>(a, (cudaStream_t)stream);
         case 1: return launch_layer<64>(a, (cudaStream_t)stream);
         case 2: return launch_layer<256>(a, (cudaStream_t)stream);
         case 3:
             if (!agg_ws) return EGSPR_E_WORKSPACE;
-            return launch_layer_ts(a, agg_ws, edge_only, false, (cudaStream_t)stream);
+            return launch_layer_ts(a, agg_ws, edge_only, 0, (cudaStream_t)stream);
         case 4:
             if (!agg_ws) return EGSPR_E_WORKSPACE;
-            return launch_layer_ts(a, agg_ws, edge_only, true, (cudaStream_t)stream);
+            return launch_layer_ts(a, agg_ws, edge_only, 1, (cudaStream_t)stream);
+        case 5:
+            if (!agg_ws) return EGSPR_E_WORKSPACE;
+            return launch_layer_ts(a, agg_ws, edge_only, 2, (cudaStream_t)stream);
         default: return EGSPR_E_UNSUPPORTED;
     }
 }

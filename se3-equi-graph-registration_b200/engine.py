@@ -128,7 +128,7 @@ class RegistrationEngine:
                 p(self.h[nxt]), p(self.x4[nxt]), p(self.x_out) if last else None,
                 None if last else p(self.P[nxt]), None if last else p(self.Q[nxt]), p(self.agg_ws), int(self.impl), st),
                 "egspr_egcl_forward")
-            n_launch += 2 if self.impl in (0, 3, 4) else 1
+            n_launch += 2 if self.impl in (0, 3, 4, 5) else 1
             mark("layer%d" % i)
             cur = nxt
         self.h_out = self.h[cur].view(C, N, H)
@@ -216,3 +216,74 @@ class RegistrationEngine:
         return {"R": self.R, "t": self.t, "w": self.w, "H": self.Hm,
                 "h_src": self.h_out[:B], "h_tgt": self.h_out[B:], "x_src": self.x_out[:B], "x_tgt": self.x_out[B:],
                 "equi_loss": self.loss_parts.sum() / (B * self.N), "nbr": self.nbr}
+
+
+class PipelinedEngine:
+    """`lanes` RegistrationEngines, each with its own buffers, CUDA graph and stream: batch i runs on lane i % lanes.
+
+    One batch's launch sequence has wide kernels (k-NN query, the edge / node kernels: >= one CTA per SM) and narrow ones
+    (eval head: ONE CTA per pair = 64 of 148 SMs for 117 us; CSR build; k-NN grid build: one CTA per cloud).  With two
+    batches in flight the narrow kernels of one run beside the wide kernels of the other, and uploads overlap compute
+    as in RegistrationEngine.submit().  The reference's loop processes its batches strictly one after another
+    (src/eval_egnn_metrics.py:1122-1250).  Results are identical to a single engine's (same kernels, same order per batch)."""
+
+    def __init__(self, model, batch, n=2048, k=16, device=None, lanes=2, use_graph=True):
+        self.engines = [RegistrationEngine(model, batch, n=n, k=k, device=device, use_graph=use_graph) for _ in range(int(lanes))]
+        self.device = self.engines[0].device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
+        self._count = 0
+
+    @property
+    def impl(self):
+        return self.engines[0].impl
+
+    @impl.setter
+    def impl(self, v):
+        for e in self.engines:
+            e.impl = v
+
+    @property
+    def launches_per_step(self):
+        return self.engines[0].launches_per_step
+
+    def _next(self):
+        lane = self._count % len(self.engines)
+        self._count += 1
+        return lane
+
+    def register(self, src_feat, src_pts, tgt_feat, tgt_pts, labels=None, gt_pose=None):
+        """Enqueue one batch (device or pinned-host tensors) on the next lane -> ticket; result(ticket) waits for it."""
+        lane = self._next()
+        eng, st = self.engines[lane], self.streams[lane]
+        st.wait_stream(torch.cuda.current_stream(self.device))          # the inputs may have been produced there
+        with torch.cuda.stream(st):
+            eng.register(src_feat, src_pts, tgt_feat, tgt_pts, labels, gt_pose)
+            done = torch.cuda.Event()
+            done.record(st)
+        return (lane, done)
+
+    def result(self, ticket):
+        """(R [B,3,3], t [B,3]) device tensors of a registered batch (valid until the lane is used again)."""
+        lane, done = ticket
+        done.synchronize()
+        return self.engines[lane].R, self.engines[lane].t
+
+    def submit(self, src_feat, src_pts, tgt_feat, tgt_pts, labels=None, gt_pose=None):
+        """Host-to-host form (pinned host tensors in, pinned host poses out), see RegistrationEngine.submit()."""
+        lane = self._next()
+        with torch.cuda.stream(self.streams[lane]):
+            return (lane, self.engines[lane].submit(src_feat, src_pts, tgt_feat, tgt_pts, labels, gt_pose))
+
+    def collect(self, ticket):
+        lane, inner = ticket
+        return self.engines[lane].collect(inner)
+
+    def join(self):
+        """The current stream waits for every lane (use before recording an end-of-region event)."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def synchronize(self):
+        for st in self.streams:
+            st.synchronize()

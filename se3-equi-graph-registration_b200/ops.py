@@ -173,7 +173,7 @@ def egnn_forward(feat, x, graph, layer_packs, embed_in_pack, embed_out_pack, edg
     pbuf = [torch.empty((G, H), dtype=torch.float32, device=dev) for _ in range(2)]
     qbuf = [torch.empty((G, H), dtype=torch.float32, device=dev) for _ in range(2)]
     x_out = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
-    agg_ws = torch.empty((G, H), dtype=torch.float32, device=dev) if impl in (0, 3, 4) else None
+    agg_ws = torch.empty((G, H), dtype=torch.float32, device=dev) if impl in (0, 3, 4, 5) else None
     layers = []
     with torch.cuda.device(dev):
         st = _stream()

@@ -19,6 +19,9 @@ from oracle import egnn_oracle as O
 from oracle import knn_oracle
 
 pytestmark = pytest.mark.gpu
+# stated bounds of the reduced-precision edge modes (BASELINE config 2), set from tools/fast_mode_err.py on a B200
+BF16_H_TOL, BF16_X_TOL = 1e-2, 2e-2
+RED_ROT_DEG, RED_T_M, RED_H_REL = 1.0, 2e-2, 5e-2
 DEV = "cuda:0"
 H_TOL, X_TOL, ROT_TOL_DEG, T_TOL = 1e-4, 1e-4, 0.01, 1e-4
 CASES = ["small_b2_n256", "dup_b2_n512", "full_b1_n2048", "kitti_b1_n1024", "noenc_b1_n512"]
@@ -387,6 +390,48 @@ def test_reduced_precision_edge_mode_within_looser_bound(golden_dir, name):
     for b in range(inp["labels"].shape[0]):
         assert rot_angle_deg(out[0][b].cpu().numpy(), ref["R"][b].numpy()) <= ROT_TOL_DEG
         assert float((out[1][b].cpu() - ref["t"][b]).abs().max()) <= T_TOL * scale
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_bf16_edge_mode_within_stated_bound(golden_dir, name):
+    """impl 5 (BASELINE config 2's bf16 edge MLP: tcgen05.mma.kind::f16, bf16 activations and weights, fp32 accumulation,
+    geometric inputs as two bf16 terms, tanh SiLU).  Stated bound: features BF16_H_TOL of max|h|, coordinates
+    BF16_X_TOL * max(1, max|x|) m; the eval-variant pose keeps the fp32 bars (original coordinates, near-uniform weights).
+    On tempered weights (well-conditioned train-variant Kabsch) the TRAIN-variant pose and H of both reduced modes stay
+    within RED_ROT_DEG / RED_T_M / RED_H_REL of the fp32 path."""
+    g, ck = load_case(golden_dir, name)
+    model = P.build_model(ck, device=DEV, variant="eval")
+    model.egnn.impl = 5
+    inp = {k: v.to(DEV) for k, v in g["inputs"].items()}
+    es, et = P.knn_graph_batch(inp["src_pts"], 16), P.knn_graph_batch(inp["tgt_pts"], 16)
+    with torch.no_grad():
+        out = model(inp["src_feat"], inp["src_pts"], es, None, inp["tgt_feat"], inp["tgt_pts"], et, None,
+                    inp["corr"], inp["labels"], inp["gt_pose"])
+    ref = g["eval_f32"]
+    for i, key in ((4, "h_src"), (6, "h_tgt")):
+        err = float((out[i].cpu() - ref[key]).abs().max())
+        assert 1e-5 * float(ref[key].abs().max()) < err <= BF16_H_TOL * float(ref[key].abs().max()), (key, err / float(ref[key].abs().max()))
+    for i, key in ((5, "x_src"), (7, "x_tgt")):
+        assert float((out[i].cpu() - ref[key]).abs().max()) <= BF16_X_TOL * max(1.0, float(ref[key].abs().max())), key
+    scale = max(1.0, float(g["inputs"]["tgt_pts"].abs().max()))
+    for b in range(inp["labels"].shape[0]):
+        assert rot_angle_deg(out[0][b].cpu().numpy(), ref["R"][b].numpy()) <= ROT_TOL_DEG
+        assert float((out[1][b].cpu() - ref["t"][b]).abs().max()) <= T_TOL * scale
+    # train variant on tempered weights: pose / H of the reduced modes against the fp32 path
+    tm = P.build_model(ck, device=DEV, variant="train")
+    with torch.no_grad():
+        tm.egnn.embedding_out.weight.mul_(0.005); tm.egnn.embedding_out.bias.mul_(0.005)
+    res = {}
+    for impl in (3, 4, 5):
+        tm.egnn.impl = impl
+        with torch.no_grad():
+            o = tm(inp["src_feat"], inp["src_pts"], es, None, inp["tgt_feat"], inp["tgt_pts"], et, None, inp["corr"], inp["labels"], inp["gt_pose"])
+        res[impl] = (o[0].cpu(), o[1].cpu(), tm.last_aux["H"].cpu())
+    for impl in (4, 5):
+        for b in range(inp["labels"].shape[0]):
+            assert rot_angle_deg(res[impl][0][b].numpy(), res[3][0][b].numpy()) <= RED_ROT_DEG, (impl, b)
+        assert float((res[impl][1] - res[3][1]).abs().max()) <= RED_T_M * scale, impl
+        assert float((res[impl][2] - res[3][2]).abs().max()) <= RED_H_REL * float(res[3][2].abs().max()), impl
 
 
 # ---------------------------------------------------------------------------------------------

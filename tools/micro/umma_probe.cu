@@ -6,6 +6,7 @@
 //   T4  as T3 at TMEM lane offset 16 (interleaved M=64 accumulators)
 //   T5  MN-major B slice of N=16 at +32 B
 //   T6  column sums through a constant all-ones B (N=8)
+//   T7  A operand from TENSOR MEMORY as packed bf16 pairs (TS mode, kind::f16)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_probe umma_probe.cu ; run on a B200.
 #include <cstdio>
 #include <cstdlib>
@@ -16,16 +17,6 @@
 
 using namespace egspr::tc;
 
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
-}
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) { return make_desc_sw128(addr); }
 __device__ __forceinline__ uint64_t desc_none(uint32_t addr) {
     uint64_t d = 0;
@@ -93,12 +84,43 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint16_t *gA, const ui
             umma_bf16_ss(tm + 112, desc_sw128(a + 2048 * j), desc_none(o), idesc_bf16(64, 8, 1, 0), j > 0);
         umma_commit(mbar);
     }
+    // T7: A from TENSOR MEMORY as packed bf16 pairs (column c of lane e = {A[e][2c] low half, A[e][2c+1] high half}), K = 32:
+    // two K-steps of 8 columns; B = first 64 bytes of the weight tile rows (K-major).  D -> cols 120..151 would collide,
+    // so it reuses cols 0..31 AFTER T1 was read back (second phase below).
     mbar_wait(mbar, 0);
     fence_after_sync();
     for (int c = 0; c < 128; c += 32) {
         float v[32];
         tmem_ld32(tm + ((uint32_t)((tid >> 5) * 32) << 16) + c, v);
         for (int i = 0; i < 32; ++i) out[tid * 128 + c + i] = v[i];
+    }
+    {   // second phase: T7
+        float pk[16];
+        for (int c = 0; c < 16; ++c) {
+            const uint32_t lo = gA[tid * 64 + 2 * c], hi = gA[tid * 64 + 2 * c + 1];
+            pk[c] = __uint_as_float(lo | (hi << 16));
+        }
+        tmem_st16(tm + ((uint32_t)((tid >> 5) * 32) << 16) + 256, pk);
+        tmem_wait_st();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t w = smem_u32(TW);
+            for (int j = 0; j < 2; ++j) {
+                asm volatile(
+                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tm + 160), "r"(tm + 256 + 8 * j),
+                    "l"(desc_sw128(w + 32 * j)), "r"(idesc_bf16(128, 32, 0, 0)), "r"(j)
+                    : "memory");
+            }
+            umma_commit(mbar);
+        }
+        mbar_wait(mbar, 1);
+        fence_after_sync();
+        float v[32];
+        tmem_ld32(tm + ((uint32_t)((tid >> 5) * 32) << 16) + 160, v);
+        for (int i = 0; i < 32; ++i) out[128 * 128 + tid * 32 + i] = v[i];
     }
     fence_before_sync();
     __syncthreads();
@@ -116,23 +138,23 @@ int main(int argc, char **argv) {
     for (auto &v : Y) v = rv();
     for (auto &v : W) v = rv();
     uint16_t *dA, *dY, *dW; float *dO;
-    cudaMalloc(&dA, A.size() * 2); cudaMalloc(&dY, Y.size() * 2); cudaMalloc(&dW, W.size() * 2); cudaMalloc(&dO, 128 * 128 * 4);
+    cudaMalloc(&dA, A.size() * 2); cudaMalloc(&dY, Y.size() * 2); cudaMalloc(&dW, W.size() * 2); cudaMalloc(&dO, 128 * 160 * 4);
     cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dY, Y.data(), Y.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dW, W.data(), W.size() * 2, cudaMemcpyHostToDevice);
-    cudaMemset(dO, 0, 128 * 128 * 4);
+    cudaMemset(dO, 0, 128 * 160 * 4);
     const int smem = 32768 + 8192 + 1024 + 64 + 1024;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     probe_kernel<<<1, 128, smem>>>(dA, dY, dW, dO);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 2; }
-    std::vector<float> O(128 * 128);
+    std::vector<float> O(128 * 160);
     cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
     auto a = [&](int r, int c) { return (double)bf2f(A[r * 64 + c]); };
     auto y = [&](int r, int c) { return (double)bf2f(Y[r * 64 + c]); };
     auto w = [&](int r, int c) { return (double)bf2f(W[r * 64 + c]); };
     auto lane64 = [](int m) { return (m & 15) + 32 * (m >> 4); };
-    int bad[7] = {0};
+    int bad[8] = {0};
     for (int e2 = 0; e2 < 128; ++e2)
         for (int n = 0; n < 32; ++n) {
             double r1 = 0, r2 = 0;
@@ -158,7 +180,13 @@ int main(int argc, char **argv) {
         for (int n = 0; n < 8; ++n)
             if (O[lane64(m) * 128 + 112 + n] != (float)r6) ++bad[6];
     }
-    for (int t = 1; t <= 6; ++t) printf("T%d %s (%d mismatches)\n", t, bad[t] ? "FAIL" : "PASS", bad[t]);
+    for (int e2 = 0; e2 < 128; ++e2)
+        for (int n = 0; n < 32; ++n) {
+            double r7 = 0;
+            for (int k = 0; k < 32; ++k) r7 += a(e2, k) * w(n, k);
+            if (O[128 * 128 + e2 * 32 + n] != (float)r7) ++bad[7];
+        }
+    for (int t = 1; t <= 7; ++t) printf("T%d %s (%d mismatches)\n", t, bad[t] ? "FAIL" : "PASS", bad[t]);
     if (argc > 1) {
         FILE *f = fopen(argv[1], "wb");
         if (f) {
@@ -168,6 +196,6 @@ int main(int argc, char **argv) {
         }
     }
     int tot = 0;
-    for (int t = 1; t <= 6; ++t) tot += bad[t];
+    for (int t = 1; t <= 7; ++t) tot += bad[t];
     return tot ? 1 : 0;
 }
