@@ -139,6 +139,18 @@ int egspr_head_eval(const float *feat_src, const float *feat_tgt, const float *x
                     const float *gt_pose, const float *head_pack, int pairs, int n, int top_k,
                     float *w_out, float *R, float *t, float *Hout, float *loss_parts, void *stream);
 
+/* The same with a scratch buffer (egspr_head_eval_workspace_bytes(pairs) bytes): for few pairs of large clouds (pairs <
+ * 2 x SMs and n >= 8192) the passes over the 32-wide rows (input-feature similarity, egnn_equi_loss) are split over up to
+ * EGSPR_HEAD_MAX_SPLIT CTAs per pair (needs w_out, which doubles as scratch); identical results. */
+#define EGSPR_HEAD_MAX_SPLIT 128
+size_t egspr_head_eval_workspace_bytes(int pairs);
+int egspr_head_eval_ws(const float *feat_src, const float *feat_tgt, const float *x_src,
+                       const float *x_tgt, const float *h_out_src, const float *h_out_tgt,
+                       const float *x_out_src, const float *x_out_tgt, const float *labels,
+                       const float *gt_pose, const float *head_pack, int pairs, int n, int top_k,
+                       float *w_out, float *R, float *t, float *Hout, float *loss_parts, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 /* ---- a13: train-variant weights 3dm:696-724 + Kabsch on the EGNN coords of the GT inliers -------
  * w = softmax over {i: labels!=0} of <h_out_src,h_out_tgt>, /(sum+1e-6).  Same outputs as above;
  * sim_out [pairs][n] receives the similarity scores (used by the host for top-k / BCE / sim loss). */

@@ -38,6 +38,8 @@ SIGNATURES = {
                                 _p, _p, _p, _p, _p, _p, _i, _p]),
     "egspr_kabsch": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "egspr_head_eval": (_i, [_p] * 11 + [_i, _i, _i] + [_p] * 6),
+    "egspr_head_eval_workspace_bytes": (_z, [_i]),
+    "egspr_head_eval_ws": (_i, [_p] * 11 + [_i, _i, _i] + [_p] * 6 + [_z, _p]),
     "egspr_head_train": (_i, [_p] * 6 + [_i, _i] + [_p] * 7),
     "egspr_pose_metrics": (_i, [_p] * 5 + [_i, _i, ctypes.c_double, _p, _p]),
     "egspr_feature_nn": (_i, [_p, _i, _p, _i, _p, _z, _p, _p, _p]),

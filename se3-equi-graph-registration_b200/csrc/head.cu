@@ -243,7 +243,65 @@ struct HeadEvalArgs {
         *gt_pose, *head_pack;
     int n, top_k;
     float *w_out, *R, *t, *Hout, *loss_parts;
+    // few pairs x large clouds: the per-point passes over the 32-wide rows (input-feature similarity, egnn_equi_loss) are
+    // done by head_eval_pre_kernel on `split` CTAs per pair; this kernel then starts from their partial results
+    int split;                                   // 0 = everything in this kernel
+    const unsigned long long *pre_best;          // [pairs][split] packed (similarity key, index) maxima
+    const float *pre_lp;                         // [pairs][split][2] egnn_equi_loss partial sums
 };
+
+// grid (split, pairs): chunk of the pair's points -> sim0 into the pair's row of w_out (scratch), chunk argmax, chunk loss sums
+__global__ void __launch_bounds__(256) head_eval_pre_kernel(const HeadEvalArgs a, unsigned long long *__restrict__ best_out,
+                                                            float *__restrict__ lp_out) {
+    __shared__ BlockScratch sc;
+    const int b = blockIdx.y, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t nb = (size_t)b * n;
+    const int per = (n + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    float g[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g[3 * i] = __ldg(a.gt_pose + b * 16 + 4 * i); g[3 * i + 1] = __ldg(a.gt_pose + b * 16 + 4 * i + 1);
+        g[3 * i + 2] = __ldg(a.gt_pose + b * 16 + 4 * i + 2); g[9 + i] = __ldg(a.gt_pose + b * 16 + 4 * i + 3);
+    }
+    unsigned long long best = 0ull;
+    float acc[2] = {0.f, 0.f};
+    for (int i = i0 + tid; i < i1; i += blockDim.x) {
+        const float s = dot32(a.feat_src + (nb + i) * H, a.feat_tgt + (nb + i) * H);
+        a.w_out[nb + i] = s;
+        const unsigned long long cand = ((unsigned long long)order_key(s) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+        best = cand > best ? cand : best;
+        if (a.loss_parts) {                       // as block_equi_loss (3dm:860-893)
+            const float *hs = a.h_out_src + (nb + i) * H, *ht = a.h_out_tgt + (nb + i) * H;
+            const float *xs = a.x_out_src + (nb + i) * 3, *xt = a.x_out_tgt + (nb + i) * 3;
+            const float lab = __ldg(a.labels + nb + i);
+            const float x0 = xs[0], x1 = xs[1], x2 = xs[2];
+            float ch = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float d = (g[3 * r] * x0 + g[3 * r + 1] * x1 + g[3 * r + 2] * x2 + g[9 + r]) - xt[r];
+                ch = fmaf(d, d, ch);
+            }
+            acc[0] = fmaf(ch, lab, acc[0]);
+            const float ab = dot32(hs, ht), aa = dot32(hs, hs), bb = dot32(ht, ht);
+            const float cs = ab / (fmaxf(sqrtf(aa), 1e-8f) * fmaxf(sqrtf(bb), 1e-8f));
+            acc[1] = fmaf(cs - lab, cs - lab, acc[1]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if (lane == 0) sc.red64[warp] = best;
+    block_sum<2>(acc, sc);               // (its barriers also publish red64)
+    if (tid == 0) {
+        unsigned long long m = sc.red64[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = sc.red64[w] > m ? sc.red64[w] : m;
+        best_out[(size_t)b * gridDim.x + blockIdx.x] = m;
+        lp_out[((size_t)b * gridDim.x + blockIdx.x) * 2] = acc[0];
+        lp_out[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = acc[1];
+    }
+}
 
 __global__ void __launch_bounds__(HD_THREADS_BIG) head_eval_kernel(const HeadEvalArgs a) {
     extern __shared__ __align__(16) float dyn[];
@@ -254,6 +312,14 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_eval_kernel(const HeadEva
     float *ssim = (n > HD_MAX_N) ? a.w_out + nb : dyn;
     // 1. input-feature similarity (evl:691)
     unsigned long long best = 0ull;
+    if (a.split > 0) {                   // done by head_eval_pre_kernel: sim0 sits in this pair's row of w_out
+        if (n <= HD_MAX_N)
+            for (int i = tid; i < n; i += blockDim.x) ssim[i] = a.w_out[nb + i];
+        for (int i = tid; i < a.split; i += blockDim.x) {
+            const unsigned long long cand = a.pre_best[(size_t)b * a.split + i];
+            best = cand > best ? cand : best;
+        }
+    } else
     for (int i = tid; i < n; i += blockDim.x) {
         const float s = dot32(a.feat_src + (nb + i) * H, a.feat_tgt + (nb + i) * H);
         ssim[i] = s;
@@ -364,7 +430,13 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_eval_kernel(const HeadEva
     block_kabsch(a.x_src + nb * 3, a.x_tgt + nb * 3, 3, ssim, n, n, a.R + b * 9, a.t + b * 3,
                  a.Hout ? a.Hout + b * 9 : nullptr, sc);
     // 7. egnn_equi_loss partial sums on the EGNN outputs (evl:687)
-    if (a.loss_parts)
+    if (a.loss_parts && a.split > 0) {
+        if (tid < 2) {
+            float t2 = 0.f;
+            for (int i = 0; i < a.split; ++i) t2 += a.pre_lp[((size_t)b * a.split + i) * 2 + tid];
+            a.loss_parts[b * 2 + tid] = t2;
+        }
+    } else if (a.loss_parts)
         block_equi_loss(a.h_out_src + nb * H, a.h_out_tgt + nb * H, a.x_out_src + nb * 3, a.x_out_tgt + nb * 3,
                         a.labels + nb, a.gt_pose + b * 16, n, a.loss_parts + b * 2, sc);
 }
@@ -1036,7 +1108,21 @@ extern "C" int egspr_head_eval(const float *feat_src, const float *feat_tgt, con
                                const float *x_out_tgt, const float *labels, const float *gt_pose,
                                const float *head_pack, int pairs, int n, int top_k, float *w_out, float *R, float *t,
                                float *Hout, float *loss_parts, void *stream) {
+    return egspr_head_eval_ws(feat_src, feat_tgt, x_src, x_tgt, h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose,
+                              head_pack, pairs, n, top_k, w_out, R, t, Hout, loss_parts, nullptr, 0, stream);
+}
+
+extern "C" size_t egspr_head_eval_workspace_bytes(int pairs) {
+    return pairs > 0 ? (size_t)pairs * EGSPR_HEAD_MAX_SPLIT * 16 : 0;
+}
+
+extern "C" int egspr_head_eval_ws(const float *feat_src, const float *feat_tgt, const float *x_src, const float *x_tgt,
+                                  const float *h_out_src, const float *h_out_tgt, const float *x_out_src,
+                                  const float *x_out_tgt, const float *labels, const float *gt_pose,
+                                  const float *head_pack, int pairs, int n, int top_k, float *w_out, float *R, float *t,
+                                  float *Hout, float *loss_parts, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace egspr;
+    void *pre_scratch = (workspace && workspace_bytes >= egspr_head_eval_workspace_bytes(pairs)) ? workspace : nullptr;
     if (!feat_src || !feat_tgt || !x_src || !x_tgt || !h_out_src || !h_out_tgt || !head_pack || !R || !t || pairs <= 0 ||
         n <= 0 || top_k <= 0)
         return EGSPR_E_INVALID;
@@ -1045,7 +1131,21 @@ extern "C" int egspr_head_eval(const float *feat_src, const float *feat_tgt, con
     const size_t smem = n > HD_MAX_N ? 0 : sizeof(float) * (size_t)n;
     if (int e = ensure_smem(head_eval_kernel, smem)) return e;
     HeadEvalArgs a{feat_src, feat_tgt, x_src, x_tgt, h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose,
-                   head_pack, n, top_k, w_out, R, t, Hout, loss_parts};
+                   head_pack, n, top_k, w_out, R, t, Hout, loss_parts, 0, nullptr, nullptr};
+    // few pairs x large clouds (one CTA per pair would leave most SMs idle while it streams 2 x 2 x n x 128 bytes):
+    // the row-wide passes go to `split` CTAs per pair; needs the w_out row as scratch and the caller's partial buffers
+    if (pre_scratch && w_out && pairs < 2 * sm_count() && (size_t)n >= 8192) {
+        int split = (2 * sm_count() + pairs - 1) / pairs;
+        if (split > EGSPR_HEAD_MAX_SPLIT) split = EGSPR_HEAD_MAX_SPLIT;
+        if (split > n / 1024) split = n / 1024;
+        if (split >= 2) {
+            unsigned long long *pb = reinterpret_cast<unsigned long long *>(pre_scratch);
+            float *pl = reinterpret_cast<float *>(pb + (size_t)pairs * split);
+            a.split = split; a.pre_best = pb; a.pre_lp = pl;
+            head_eval_pre_kernel<<<dim3((unsigned)split, (unsigned)pairs), 256, 0, (cudaStream_t)stream>>>(a, pb, pl);
+            EGSPR_CHECK_LAUNCH();
+        }
+    }
     head_eval_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;

@@ -95,6 +95,39 @@ struct GridParams {        // per cloud, 16 floats
     int pad[3];
 };
 
+__device__ GridParams grid_params_from_bbox(const float (&mn)[3], const float (&ext)[3], int n, int maxc, float pts_per_cell) {
+    GridParams gp;
+    const float emax = fmaxf(fmaxf(ext[0], ext[1]), fmaxf(ext[2], 1e-30f));
+    // cells wanted: n / pts_per_cell; degenerate (flat) axes get a single cell
+    float target = fmaxf(1.0f, (float)n / pts_per_cell);
+    if (target > (float)maxc) target = (float)maxc;
+    float e[3]; int live = 0; float vol = 1.0f;
+    for (int a = 0; a < 3; ++a) { e[a] = ext[a]; if (e[a] > 1e-4f * emax) { ++live; vol *= e[a]; } }
+    float c = live ? powf(vol / target, 1.0f / (float)live) : 1.0f;
+    int dims[3]; long long total = 1;
+    for (int a = 0; a < 3; ++a) {
+        int d = (e[a] > 1e-4f * emax) ? (int)(e[a] / c) + 1 : 1;
+        if (d > 64) d = 64;
+        if (d < 1) d = 1;
+        dims[a] = d; total *= d;
+    }
+    while (total > maxc) {           // shrink the largest dimension until the grid fits
+        int am = 0;
+        for (int a = 1; a < 3; ++a) if (dims[a] > dims[am]) am = a;
+        total /= dims[am]; dims[am] -= 1; total *= dims[am];
+    }
+    for (int a = 0; a < 3; ++a) {
+        gp.mn[a] = mn[a]; gp.dims[a] = dims[a];
+        const float cs = (ext[a] > 0.f) ? ext[a] / (float)dims[a] : 1.0f;
+        gp.cs[a] = cs; gp.inv[a] = 1.0f / cs;
+    }
+    // a point may be assigned to the cell next to its geometric one when (p - mn) * inv rounds across an
+    // integer: the error is a few ulp of the coordinate magnitude
+    gp.slack = 8.0f * 1.1920929e-7f * (fmaxf(fmaxf(fabsf(mn[0]), fabsf(mn[1])), fabsf(mn[2])) + emax);
+    gp.pad[0] = gp.pad[1] = gp.pad[2] = 0;
+    return gp;
+}
+
 __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
     const float *__restrict__ x, int n, float4 *__restrict__ sorted, int *__restrict__ cell_start,
     GridParams *__restrict__ params, int maxc, float pts_per_cell) {
@@ -128,33 +161,7 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
             for (int w = 1; w < GRID_BUILD_THREADS / 32; ++w) { l = fminf(l, red[a][w]); h = fmaxf(h, red[3 + a][w]); }
             mn[a] = l; ext[a] = h - l;
         }
-        const float emax = fmaxf(fmaxf(ext[0], ext[1]), fmaxf(ext[2], 1e-30f));
-        // cells wanted: n / pts_per_cell; degenerate (flat) axes get a single cell
-        float target = fmaxf(1.0f, (float)n / pts_per_cell);
-        if (target > (float)maxc) target = (float)maxc;
-        float e[3]; int live = 0; float vol = 1.0f;
-        for (int a = 0; a < 3; ++a) { e[a] = ext[a]; if (e[a] > 1e-4f * emax) { ++live; vol *= e[a]; } }
-        float c = live ? powf(vol / target, 1.0f / (float)live) : 1.0f;
-        int dims[3]; long long total = 1;
-        for (int a = 0; a < 3; ++a) {
-            int d = (e[a] > 1e-4f * emax) ? (int)(e[a] / c) + 1 : 1;
-            if (d > 64) d = 64;
-            if (d < 1) d = 1;
-            dims[a] = d; total *= d;
-        }
-        while (total > maxc) {           // shrink the largest dimension until the grid fits
-            int am = 0;
-            for (int a = 1; a < 3; ++a) if (dims[a] > dims[am]) am = a;
-            total /= dims[am]; dims[am] -= 1; total *= dims[am];
-        }
-        for (int a = 0; a < 3; ++a) {
-            gp.mn[a] = mn[a]; gp.dims[a] = dims[a];
-            const float cs = (ext[a] > 0.f) ? ext[a] / (float)dims[a] : 1.0f;
-            gp.cs[a] = cs; gp.inv[a] = 1.0f / cs;
-        }
-        // a point may be assigned to the cell next to its geometric one when (p - mn) * inv rounds across an
-        // integer: the error is a few ulp of the coordinate magnitude
-        gp.slack = 8.0f * 1.1920929e-7f * (fmaxf(fmaxf(fabsf(mn[0]), fabsf(mn[1])), fabsf(mn[2])) + emax);
+        gp = grid_params_from_bbox(mn, ext, n, maxc, pts_per_cell);
         params[cloud] = gp;
     }
     __syncthreads();
@@ -201,6 +208,102 @@ __global__ void __launch_bounds__(GRID_BUILD_THREADS) knn_grid_build_kernel(
         const int pos = atomicAdd(&cnt[cell_of(px, py, pz)], 1);
         so[pos] = make_float4(px, py, pz, __int_as_float(i));
     }
+}
+
+// ---- split build for few, large clouds (one CTA per cloud would serialise a 131k-point counting sort on one SM):
+// bounding box (ordered-int atomics) -> per-cell counts (global atomics) -> scan (one CTA per cloud) -> scatter.  The order of
+// the points inside a cell differs from run to run; the query's selection is a total order, so its result does not. ----
+__device__ __forceinline__ unsigned f2ord(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void __launch_bounds__(256) knn_grid_bbox_kernel(const float *__restrict__ x, int n, unsigned *__restrict__ bbox) {
+    const int cloud = blockIdx.y, lane = threadIdx.x & 31;
+    const float *xc = x + (size_t)cloud * n * 3;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = __ldg(xc + 3 * i + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { atomicMin(bbox + cloud * 8 + a, f2ord(lo[a])); atomicMax(bbox + cloud * 8 + 4 + a, f2ord(hi[a])); }
+    }
+}
+
+__device__ __forceinline__ GridParams grid_params_of_cloud(const unsigned *__restrict__ bbox, int cloud, int n, int maxc, float ppc) {
+    float mn[3], ext[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { mn[a] = ord2f(bbox[cloud * 8 + a]); ext[a] = ord2f(bbox[cloud * 8 + 4 + a]) - mn[a]; }
+    return grid_params_from_bbox(mn, ext, n, maxc, ppc);
+}
+__device__ __forceinline__ int grid_cell_of(const GridParams &gp, float px, float py, float pz) {
+    const int nx = gp.dims[0], ny = gp.dims[1], nz = gp.dims[2];
+    const int cx = min(nx - 1, max(0, (int)((px - gp.mn[0]) * gp.inv[0])));
+    const int cy = min(ny - 1, max(0, (int)((py - gp.mn[1]) * gp.inv[1])));
+    const int cz = min(nz - 1, max(0, (int)((pz - gp.mn[2]) * gp.inv[2])));
+    return (cz * ny + cy) * nx + cx;
+}
+
+// pass 0: counts into cell_start (zeroed);  pass 1: scatter through `cursor` (= exclusive offsets)
+template <int PASS>
+__global__ void __launch_bounds__(256) knn_grid_count_scatter_kernel(const float *__restrict__ x, int n, const unsigned *__restrict__ bbox,
+                                                                     int *__restrict__ cell_start, int *__restrict__ cursor,
+                                                                     float4 *__restrict__ sorted, GridParams *__restrict__ params,
+                                                                     int maxc, float ppc) {
+    __shared__ GridParams gp;
+    const int cloud = blockIdx.y;
+    if (threadIdx.x == 0) {
+        gp = grid_params_of_cloud(bbox, cloud, n, maxc, ppc);
+        if (PASS == 0 && blockIdx.x == 0) params[cloud] = gp;
+    }
+    __syncthreads();
+    const float *xc = x + (size_t)cloud * n * 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float px = __ldg(xc + 3 * i), py = __ldg(xc + 3 * i + 1), pz = __ldg(xc + 3 * i + 2);
+        const int c = grid_cell_of(gp, px, py, pz);
+        if (PASS == 0) atomicAdd(cell_start + (size_t)cloud * (maxc + 1) + c, 1);
+        else sorted[(size_t)cloud * n + atomicAdd(cursor + (size_t)cloud * (maxc + 1) + c, 1)] = make_float4(px, py, pz, __int_as_float(i));
+    }
+}
+
+// exclusive scan of the cell counts of one cloud (<= GRID_MAXC cells) -> cell_start and the scatter cursors
+__global__ void __launch_bounds__(1024) knn_grid_scan_kernel(const GridParams *__restrict__ params, int n, int *__restrict__ cell_start,
+                                                             int *__restrict__ cursor, int maxc) {
+    __shared__ int wtot[32];
+    __shared__ int carry_s;
+    const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GridParams gp = params[cloud];
+    const int ncell = gp.dims[0] * gp.dims[1] * gp.dims[2];
+    int *cs = cell_start + (size_t)cloud * (maxc + 1), *cu = cursor + (size_t)cloud * (maxc + 1);
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < ncell; base += 1024) {
+        const int i = base + tid;
+        const int v = i < ncell ? cs[i] : 0;
+        int sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+        if (lane == 31) wtot[warp] = sc;
+        __syncthreads();
+        if (warp == 0) {
+            int t = wtot[lane], u = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += w; }
+            wtot[lane] = u - t;
+        }
+        __syncthreads();
+        const int excl = carry_s + wtot[warp] + sc - v;
+        if (i < ncell) { cs[i] = excl; cu[i] = excl; }
+        __syncthreads();
+        if (tid == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) cs[ncell] = n;
 }
 
 constexpr int GQ_WARPS = 8;
@@ -411,7 +514,8 @@ __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int 
 
 extern "C" size_t egspr_knn_workspace_bytes(int clouds, int n) {
     using namespace egspr;
-    return (size_t)clouds * ((size_t)n * sizeof(float4) + (size_t)(grid_capacity(n) + 1) * sizeof(int) + sizeof(GridParams)) + 256;
+    // per cloud: cell-sorted points | cell offsets | scatter cursors (split build) | grid parameters | bounding box (8 uints)
+    return (size_t)clouds * ((size_t)n * sizeof(float4) + 2 * (size_t)(grid_capacity(n) + 1) * sizeof(int) + sizeof(GridParams) + 32) + 256;
 }
 
 extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t *nbr, void *workspace,
@@ -432,13 +536,29 @@ extern "C" int egspr_knn_build(const float *x, int clouds, int n, int k, int32_t
     float4 *sorted = (float4 *)w;
     int *cell_start = (int *)(w + (size_t)clouds * n * sizeof(float4));
     const int maxc = grid_capacity(n);
-    GridParams *params = (GridParams *)(cell_start + (size_t)clouds * (maxc + 1));
-    const size_t build_smem = (size_t)(maxc + 1) * sizeof(int);
-    if (build_smem > 48 * 1024 &&
-        cudaFuncSetAttribute(knn_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem) != cudaSuccess)
-        return EGSPR_E_LAUNCH;
+    int *cursor = cell_start + (size_t)clouds * (maxc + 1);
+    GridParams *params = (GridParams *)(cursor + (size_t)clouds * (maxc + 1));
+    unsigned *bbox = (unsigned *)(params + clouds);
     constexpr float ppc = 2.0f;      // target points per cell (measured optimum at 2048-point clouds, k = 16)
-    knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, build_smem, st>>>(x, n, sorted, cell_start, params, maxc, ppc);
+    if (n >= 8192 && clouds <= 8) {
+        // few large clouds: the build split over many CTAs per cloud (measured on B200: 2 x 131k points 0.59 -> 0.46 ms for
+        // build + query; from 16 clouds up the one-CTA-per-cloud kernel is faster than the 4 launches + memsets)
+        int split = (4 * sm_count() + clouds - 1) / clouds;
+        if (split > (n + 1023) / 1024) split = (n + 1023) / 1024;
+        if (cudaMemsetAsync(bbox, 0xff, (size_t)clouds * 32, st) != cudaSuccess) return EGSPR_E_LAUNCH;          // min slots: 0xffffffff
+        for (int c = 0; c < clouds; ++c)
+            if (cudaMemsetAsync(bbox + c * 8 + 4, 0, 16, st) != cudaSuccess) return EGSPR_E_LAUNCH;              // max slots: 0
+        if (cudaMemsetAsync(cell_start, 0, (size_t)clouds * (maxc + 1) * sizeof(int), st) != cudaSuccess) return EGSPR_E_LAUNCH;
+        dim3 g((unsigned)split, (unsigned)clouds);
+        knn_grid_bbox_kernel<<<g, 256, 0, st>>>(x, n, bbox);
+        knn_grid_count_scatter_kernel<0><<<g, 256, 0, st>>>(x, n, bbox, cell_start, cursor, sorted, params, maxc, ppc);
+        knn_grid_scan_kernel<<<clouds, 1024, 0, st>>>(params, n, cell_start, cursor, maxc);
+        knn_grid_count_scatter_kernel<1><<<g, 256, 0, st>>>(x, n, bbox, cell_start, cursor, sorted, params, maxc, ppc);
+    } else {
+        const size_t build_smem = (size_t)(maxc + 1) * sizeof(int);
+        if (build_smem > 48 * 1024 && !opt_in_smem(knn_grid_build_kernel, build_smem)) return EGSPR_E_LAUNCH;
+        knn_grid_build_kernel<<<clouds, GRID_BUILD_THREADS, build_smem, st>>>(x, n, sorted, cell_start, params, maxc, ppc);
+    }
     if (k <= 16) launch_knn_sub<16, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);       // 16 lanes per query
     else launch_knn_sub<32, 1>(sorted, cell_start, params, clouds, n, k, nbr, maxc, st);               // 16 < k <= 32
     EGSPR_CHECK_LAUNCH();

@@ -60,6 +60,8 @@ class RegistrationEngine:
         self.agg_ws = z(G, H)
         # outputs
         self.R = z(B, 3, 3); self.t = z(B, 3); self.Hm = z(B, 3, 3); self.w = z(B, N); self.loss_parts = z(B, 2)
+        self.head_ws_bytes = _lib.lib().egspr_head_eval_workspace_bytes(B)
+        self.head_ws = torch.empty(max(self.head_ws_bytes, 16), dtype=torch.uint8, device=dev)
         self.h_out = None
         self._graph = [None, None]
         self._graph_key = [None, None]
@@ -106,7 +108,8 @@ class RegistrationEngine:
             _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), None, 0, st), "egspr_knn_build"); n_launch += 1
         else:
             _lib.check(lib.egspr_knn_build(p(self.x), C, N, k, p(self.nbr), p(self.knn_ws), self.knn_ws_bytes, st),
-                       "egspr_knn_build"); n_launch += 2
+                       "egspr_knn_build")
+            n_launch += 5 if (N >= 8192 and C <= 8) else 2      # split grid build (bbox, count, scan, scatter) + query
         mark("knn")
         _lib.check(lib.egspr_csr_from_nbr(p(self.nbr), C, N, k, p(self.csr_ptr), p(self.csr_row), p(self.csr_col),
                                           p(self.csr_eid), p(self.ws), self.ws_bytes, p(self.err), st), "egspr_csr_from_nbr")
@@ -133,10 +136,11 @@ class RegistrationEngine:
             cur = nxt
         self.h_out = self.h[cur].view(C, N, H)
         ho, xo = self.h_out, self.x_out
-        _lib.check(lib.egspr_head_eval(p(self.feat[:B]), p(self.feat[B:]), p(self.x[:B]), p(self.x[B:]),
-                                       p(ho[:B]), p(ho[B:]), p(xo[:B]), p(xo[B:]), p(self.labels), p(self.gt_pose),
-                                       p(head), B, N, int(self.model.top_k), p(self.w), p(self.R), p(self.t), p(self.Hm),
-                                       p(self.loss_parts), st), "egspr_head_eval"); n_launch += 1
+        _lib.check(lib.egspr_head_eval_ws(p(self.feat[:B]), p(self.feat[B:]), p(self.x[:B]), p(self.x[B:]),
+                                          p(ho[:B]), p(ho[B:]), p(xo[:B]), p(xo[B:]), p(self.labels), p(self.gt_pose),
+                                          p(head), B, N, int(self.model.top_k), p(self.w), p(self.R), p(self.t), p(self.Hm),
+                                          p(self.loss_parts), p(self.head_ws), self.head_ws_bytes, st), "egspr_head_eval_ws")
+        n_launch += 2 if (B < 2 * 148 and N >= 8192) else 1
         mark("head")
         self.launches_per_step = n_launch
 
