@@ -347,9 +347,21 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_eval_kernel(const HeadEva
         __syncthreads();
         if (tid < 256) sc.hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += blockDim.x) {
-            const unsigned key = order_key(ssim[i]);
-            if ((key & pmask) == prefix) atomicAdd(&sc.hist[(key >> shift) & 0xffu], 1u);
+        // four independent loads in flight per thread (large clouds keep sim0 in global memory) and warp-aggregated
+        // histogram updates (similarities crowd into a few bins: one atomic per distinct bin and warp, not per lane)
+        for (int base = 0; base < n; base += 4 * blockDim.x) {        // block-uniform trip count: __match_any_sync needs whole warps
+            const int i0 = base + tid;
+            float v4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int i = i0 + q * blockDim.x; v4[q] = i < n ? ssim[i] : 0.f; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned key = order_key(v4[q]);
+                const bool in = (i0 + q * (int)blockDim.x < n) && (key & pmask) == prefix;
+                const unsigned bin = in ? ((key >> shift) & 0xffu) : 0x100u;
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sc.hist[bin], (unsigned)__popc(peers));
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -410,21 +422,26 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_eval_kernel(const HeadEva
     block_sum<1>(part, sc);
     const float inv_s = 1.0f / (part[0] + 1e-6f);                                  // evl:771
     float mx = -3.4e38f;
-    for (int i = tid; i < n; i += blockDim.x) { const float f = ssim[i] * inv_s; ssim[i] = f; mx = fmaxf(mx, f); }
+    // (the four passes below keep four independent loads in flight per thread; per-thread partial sums are taken in
+    // index order i, i + T, i + 2T, ... exactly as a plain strided loop would)
+#define EGSPR_PASS4(BODY)                                                                              \
+    for (int i0 = tid; i0 < n; i0 += 4 * blockDim.x) {                                                 \
+        float v4[4];                                                                                   \
+        _Pragma("unroll") for (int q = 0; q < 4; ++q) { const int i = i0 + q * blockDim.x; v4[q] = i < n ? ssim[i] : 0.f; } \
+        _Pragma("unroll") for (int q = 0; q < 4; ++q) { const int i = i0 + q * blockDim.x; if (i < n) { const float v = v4[q]; BODY } } \
+    }
+    EGSPR_PASS4({ const float f = v * inv_s; ssim[i] = f; mx = fmaxf(mx, f); })
     mx = block_max(mx, sc);
     float z[1] = {0.f};
-    for (int i = tid; i < n; i += blockDim.x) { const float e = expf(ssim[i] - mx); ssim[i] = e; z[0] += e; }   // softmax evl:774
+    EGSPR_PASS4({ const float e = expf(v - mx); ssim[i] = e; z[0] += e; })                     // softmax evl:774
     block_sum<1>(z, sc);
     const float inv_z = 1.0f / z[0];
     float sw[1] = {0.f};
-    for (int i = tid; i < n; i += blockDim.x) { const float w = ssim[i] * inv_z; ssim[i] = w; sw[0] += w; }
+    EGSPR_PASS4({ const float w = v * inv_z; ssim[i] = w; sw[0] += w; })
     block_sum<1>(sw, sc);
     const float inv_w = 1.0f / (sw[0] + 1e-6f);                                    // evl:783
-    for (int i = tid; i < n; i += blockDim.x) {
-        const float w = ssim[i] * inv_w;
-        ssim[i] = w;
-        if (a.w_out) a.w_out[nb + i] = w;
-    }
+    EGSPR_PASS4({ const float w = v * inv_w; ssim[i] = w; if (a.w_out) a.w_out[nb + i] = w; })
+#undef EGSPR_PASS4
     __syncthreads();
     // 6. Kabsch on the original coordinates, all n points (evl:717-718, 786-818)
     block_kabsch(a.x_src + nb * 3, a.x_tgt + nb * 3, 3, ssim, n, n, a.R + b * 9, a.t + b * 3,
@@ -885,9 +902,21 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) train_loss_forward_kernel(cons
         __syncthreads();
         if (tid < 256) sc.hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += blockDim.x) {
-            const unsigned key = order_key(ssim[i]);
-            if ((key & pmask) == prefix) atomicAdd(&sc.hist[(key >> shift) & 0xffu], 1u);
+        // four independent loads in flight per thread (large clouds keep sim0 in global memory) and warp-aggregated
+        // histogram updates (similarities crowd into a few bins: one atomic per distinct bin and warp, not per lane)
+        for (int base = 0; base < n; base += 4 * blockDim.x) {        // block-uniform trip count: __match_any_sync needs whole warps
+            const int i0 = base + tid;
+            float v4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int i = i0 + q * blockDim.x; v4[q] = i < n ? ssim[i] : 0.f; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned key = order_key(v4[q]);
+                const bool in = (i0 + q * (int)blockDim.x < n) && (key & pmask) == prefix;
+                const unsigned bin = in ? ((key >> shift) & 0xffu) : 0x100u;
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sc.hist[bin], (unsigned)__popc(peers));
+            }
         }
         __syncthreads();
         if (tid == 0) {
