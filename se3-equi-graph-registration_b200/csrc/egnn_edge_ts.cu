@@ -427,16 +427,18 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             }
             umma_commit(mbar_u);
         }
-        // stage csr_ptr[nstart ...] of this tile's rows for the segment sums (visible after barriers 2, 3)
         const int rlast = s_rlast[0];
         int *sp = sptr2 + par * V_SPTR;
-        sp[ht] = pt0; sp[ht + 128] = pt1;
         float v[32];
         TS_MARK(3);
         mbar_wait(mbar, phase); phase ^= 1;
         TS_MARK(4);
         fence_after_sync();
         tmem_ld32(tmem_w, v);
+        // stage csr_ptr[nstart ...] of this tile's rows for the segment sums (visible after barriers 2, 3).  The two loads
+        // were issued at the top of the tile; consuming them here, after the stage-1 MMA wait, hides their L2 latency
+        // (consumed right after the first barrier they stalled every warp for ~800 cycles per tile)
+        sp[ht] = pt0; sp[ht + 128] = pt1;
         {   // the next tile's endpoint coordinates (rn, cn were loaded at the top of this tile)
             const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
             xrn0 = t0.x; xrn1 = t0.y; xrn2 = t0.z; xcn0 = t1.x; xcn1 = t1.y; xcn2 = t1.z;

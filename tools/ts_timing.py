@@ -1,10 +1,11 @@
 """Developer script (gpurun): per-phase clock64() timeline of one group of the impl-5 edge kernel.
-Needs a library built with -DEGSPR_TS_TIMING (EGSPR_LIB_PATH)."""
+Needs build/timing/libegspr_b200.so (tools/build_timing.sh, -DEGSPR_TS_TIMING)."""
 import ctypes, os, sys, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import se3_equi_graph_registration_b200 as P
 from se3_equi_graph_registration_b200 import _lib
+_lib.LIB_PATH = os.path.join(ROOT, "build", "timing", "libegspr_b200.so")
+import se3_equi_graph_registration_b200 as P
 import bench
 model = P.build_model(bench.CKPT, device="cuda:0")
 data = P.synthetic.make_batch(5, 64, n=2048)
