@@ -185,17 +185,23 @@ int egspr_feature_nn(const float *a, int na, const float *b, int nb, void *works
 /* ---- E_GCL.forward (3dm:280-289) backward for every cloud of the batch.
  * Inputs saved by the forward pass: the layer INPUT state h, x4, P, Q and the per-node message sums agg (what
  * egspr_egcl_forward left in agg_ws).  Nothing per-edge is saved: the edge kernel recomputes each edge's forward.
- * csr_*: the row-major CSR of the forward pass; csc_ptr [G+1] / csc_eid [E]: the same edges grouped by col =
- * edge_index[1] (egspr_csr_from_edges on the edge tensor with its two rows swapped gives exactly these as its
- * csr_ptr / csr_eid outputs).
+ * csr_*: the row-major CSR of the forward pass; csc_ptr [G+1] / csc_pos [E]: the same edges grouped by col =
+ * edge_index[1], each entry = the edge's POSITION in the row-major CSR (egspr_csr_edge_positions; the per-edge
+ * gradients live in row-CSR order so that a node's row list is one contiguous run of rows).
  * dh_out [G][32], dx_out [G][3]: gradient w.r.t. the layer outputs (h', coord').  Writes dh_in [G][32], dx_in [G][3]
  * (gradient w.r.t. the layer inputs; must not alias the *_out buffers) and adds to grad_pack [EGSPR_LAYER_PACK_FLOATS].
  * workspace: egspr_egcl_backward_workspace_bytes(G, E).  Data path is deterministic (segment sums in CSR order);
  * weight gradients are reduced per CTA and combined with one atomicAdd per entry and CTA. */
 size_t egspr_egcl_backward_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+/* pos_of_edge [E]: row-CSR position of edge (cloud, original id) at [cloud * edges_per_cloud + id].  With csc_eid (the
+ * original ids of the col-grouped lists, i.e. the csr_eid output of egspr_csr_from_edges on the swapped edge tensor) also
+ * csc_pos [E] = the positions in col-grouped order.  For k-NN graphs (edge id = centre * k + slot) the col-grouped order IS
+ * the original order: csc_ptr[g] = g * k and csc_pos = pos_of_edge (pass csc_eid = NULL). */
+int egspr_csr_edge_positions(const int32_t *csr_row, const int32_t *csr_eid, const int32_t *csc_eid, int n_per_cloud,
+                             int64_t edges_per_cloud, int64_t num_edges, int32_t *pos_of_edge, int32_t *csc_pos, void *stream);
 int egspr_egcl_backward(const float *h, const float *x4, const float *P, const float *Q, const float *agg,
                         const int32_t *csr_ptr, const int32_t *csr_row, const int32_t *csr_col,
-                        const int32_t *csr_eid, const int32_t *csc_ptr, const int32_t *csc_eid,
+                        const int32_t *csr_eid, const int32_t *csc_ptr, const int32_t *csc_pos,
                         const float *edge_attr, float edge_attr_const, int64_t num_nodes,
                         int64_t edges_per_cloud, int n_per_cloud, const float *layer_pack,
                         const float *dh_out, const float *dx_out, float *dh_in, float *dx_in,

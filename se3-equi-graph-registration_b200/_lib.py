@@ -44,6 +44,7 @@ SIGNATURES = {
     "egspr_pose_metrics": (_i, [_p] * 5 + [_i, _i, ctypes.c_double, _p, _p]),
     "egspr_feature_nn": (_i, [_p, _i, _p, _i, _p, _z, _p, _p, _p]),
     "egspr_egcl_backward_workspace_bytes": (_z, [_l, _l]),
+    "egspr_csr_edge_positions": (_i, [_p, _p, _p, _i, _l, _l, _p, _p, _p]),
     "egspr_egcl_backward": (_i, [_p] * 11 + [_p, _f, _l, _l, _i] + [_p] * 7 + [_z, _p]),
     "egspr_linear32_forward": (_i, [_p, _l, _p, _p, _p]),
     "egspr_linear32_backward": (_i, [_p, _p, _l, _p, _p, _p, _p]),

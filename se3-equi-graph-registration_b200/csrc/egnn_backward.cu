@@ -6,7 +6,7 @@
 //   edge_backward_tc_kernel    (egnn_edge_bwd_tc.cu, tcgen05) thread = edge (row-CSR order): recomputes the edge's forward
 //                              from the layer input (nothing per-edge is kept from the forward pass) and pushes
 //                              (dagg[row], dx_out[row]) back to dpre (= dP[row] = dQ[col]) and the two endpoints'
-//                              coordinate gradients, written per ORIGINAL edge id
+//                              coordinate gradients, written in row-CSR order (one row per edge position)
 //   node_gather_backward_kernel thread = node: sums dpre / dx over the node's row list (row-CSR) and col list
 //                              (col-CSR), then the P/Q halves of the first edge Linear back to dh
 // Weight gradients: every kernel stages the rows of its outer products in shared memory per 128-row tile, each
@@ -147,7 +147,7 @@ constexpr int NOS = BT + 4;         // feature-major row stride of their "out" t
 // ---------------------------------------------------------------------------------------------------------------
 struct GatherArgs {
     const float *h;
-    const int32_t *csr_ptr, *csr_eid, *csc_ptr, *csc_eid;
+    const int32_t *csr_ptr, *csc_ptr, *csc_pos;
     int64_t num_nodes, edges_per_cloud;
     int n_per_cloud;
     const float *pack;
@@ -183,29 +183,28 @@ __global__ void __launch_bounds__(GT, 1) node_gather_backward_kernel(const Gathe
         float4 dp = make_float4(0.f, 0.f, 0.f, 0.f), dq = dp, hv = dp;
         float dxa = 0.f;                                               // lanes 0..2 carry x, y, z
         if (n < G) {
-            const int64_t ebase = (n / a.n_per_cloud) * a.edges_per_cloud;
-            for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; p += 8) {   // edges with row == n
-                const int mine = p + sub < pe ? __ldg(a.csr_eid + p + sub) : -1;
+            // edges with row == n: dpre / dxe are stored in row-CSR order, so this list is one contiguous run of rows
+            for (int p = __ldg(a.csr_ptr + n), pe = __ldg(a.csr_ptr + n + 1); p < pe; p += 8) {
                 float4 t[8];
                 float tx[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int ej = __shfl_sync(gmask, mine, j, 8);
-                    const int64_t ge = ebase + (ej < 0 ? 0 : ej);
-                    t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
-                    tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + sub);
+                    const bool in = p + j < pe;
+                    const int64_t ge = in ? p + j : p;
+                    t[j] = in ? ldg4(a.dpre + ge * H + 4 * sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    tx[j] = (!in || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + sub);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { dp.x += t[j].x; dp.y += t[j].y; dp.z += t[j].z; dp.w += t[j].w; dxa += tx[j]; }
             }
             for (int p = __ldg(a.csc_ptr + n), pe = __ldg(a.csc_ptr + n + 1); p < pe; p += 8) {   // edges with col == n
-                const int mine = p + sub < pe ? __ldg(a.csc_eid + p + sub) : -1;
+                const int mine = p + sub < pe ? __ldg(a.csc_pos + p + sub) : -1;      // row-CSR position of the edge
                 float4 t[8];
                 float tx[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int ej = __shfl_sync(gmask, mine, j, 8);
-                    const int64_t ge = ebase + (ej < 0 ? 0 : ej);
+                    const int64_t ge = ej < 0 ? 0 : ej;
                     t[j] = ej < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(a.dpre + ge * H + 4 * sub);
                     tx[j] = (ej < 0 || sub >= 3) ? 0.f : __ldg(a.dxe + ge * 8 + 4 + sub);
                 }
@@ -359,6 +358,34 @@ static unsigned grid_for(int64_t tiles, int ctas_per_sm) {
 
 }  // namespace egspr
 
+namespace egspr {
+// pos[cloud * epc + eid] = p for every row-CSR position p;  cpos[q] = pos[cloud(q) * epc + ceid[q]] for a col-grouped list
+__global__ void csr_positions_kernel(const int32_t *__restrict__ csr_row, const int32_t *__restrict__ csr_eid, int n, int64_t epc,
+                                     int64_t E, int32_t *__restrict__ pos) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E; p += (int64_t)gridDim.x * blockDim.x)
+        pos[(int64_t)(__ldg(csr_row + p) / n) * epc + __ldg(csr_eid + p)] = (int32_t)p;
+}
+__global__ void csc_positions_kernel(const int32_t *__restrict__ pos, const int32_t *__restrict__ ceid, int64_t epc, int64_t E,
+                                     int32_t *__restrict__ cpos) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < E; q += (int64_t)gridDim.x * blockDim.x)
+        cpos[q] = __ldg(pos + (q / epc) * epc + __ldg(ceid + q));
+}
+}  // namespace egspr
+
+extern "C" int egspr_csr_edge_positions(const int32_t *csr_row, const int32_t *csr_eid, const int32_t *csc_eid, int n_per_cloud,
+                                        int64_t edges_per_cloud, int64_t num_edges, int32_t *pos_of_edge, int32_t *csc_pos,
+                                        void *stream) {
+    using namespace egspr;
+    if (!csr_row || !csr_eid || !pos_of_edge || n_per_cloud <= 0 || edges_per_cloud <= 0 || num_edges <= 0) return EGSPR_E_INVALID;
+    if (csc_eid && !csc_pos) return EGSPR_E_INVALID;
+    int64_t g = (num_edges + 255) / 256;
+    if (g > 8 * sm_count()) g = 8 * sm_count();
+    csr_positions_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(csr_row, csr_eid, n_per_cloud, edges_per_cloud, num_edges, pos_of_edge);
+    if (csc_eid) csc_positions_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(pos_of_edge, csc_eid, edges_per_cloud, num_edges, csc_pos);
+    EGSPR_CHECK_LAUNCH();
+    return EGSPR_OK;
+}
+
 extern "C" size_t egspr_egcl_backward_workspace_bytes(int64_t num_nodes, int64_t num_edges) {
     if (num_nodes <= 0 || num_edges < 0) return 0;
     // dagg [G][32] | dpre [E][32] | dxe [E][8] | the tensor-core edge kernel's per-thread scratch
@@ -367,13 +394,13 @@ extern "C" size_t egspr_egcl_backward_workspace_bytes(int64_t num_nodes, int64_t
 
 extern "C" int egspr_egcl_backward(const float *h, const float *x4, const float *P, const float *Q, const float *agg,
                                    const int32_t *csr_ptr, const int32_t *csr_row, const int32_t *csr_col,
-                                   const int32_t *csr_eid, const int32_t *csc_ptr, const int32_t *csc_eid,
+                                   const int32_t *csr_eid, const int32_t *csc_ptr, const int32_t *csc_pos,
                                    const float *edge_attr, float edge_attr_const, int64_t num_nodes,
                                    int64_t edges_per_cloud, int n_per_cloud, const float *layer_pack,
                                    const float *dh_out, const float *dx_out, float *dh_in, float *dx_in,
                                    float *grad_pack, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace egspr;
-    if (!h || !x4 || !P || !Q || !agg || !csr_ptr || !csr_row || !csr_col || !csr_eid || !csc_ptr || !csc_eid ||
+    if (!h || !x4 || !P || !Q || !agg || !csr_ptr || !csr_row || !csr_col || !csr_eid || !csc_ptr || !csc_pos ||
         !layer_pack || !dh_out || !dx_out || !dh_in || !dx_in || !grad_pack || !workspace || num_nodes <= 0 ||
         n_per_cloud <= 0 || edges_per_cloud <= 0 || num_nodes % n_per_cloud != 0)
         return EGSPR_E_INVALID;
@@ -395,7 +422,7 @@ extern "C" int egspr_egcl_backward(const float *h, const float *x4, const float 
     EdgeBwdArgs ea{x4, P, Q, csr_ptr, csr_row, csr_col, csr_eid, edge_attr, edge_attr_const, num_nodes, edges_per_cloud,
                    n_per_cloud, layer_pack, dagg, dx_out, dpre, dxe, grad_pack, stash};
     if (int e = launch_edge_backward_tc(ea, st)) return e;
-    GatherArgs ga{h, csr_ptr, csr_eid, csc_ptr, csc_eid, num_nodes, edges_per_cloud, n_per_cloud, layer_pack, dpre, dxe,
+    GatherArgs ga{h, csr_ptr, csc_ptr, csc_pos, num_nodes, edges_per_cloud, n_per_cloud, layer_pack, dpre, dxe,
                   dx_out, dh_in, dx_in, grad_pack};
     node_gather_backward_kernel<<<grid_for(ntiles, occ_gather), GT, GB_SMEM, st>>>(ga);
     EGSPR_CHECK_LAUNCH();

@@ -278,16 +278,16 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
 #endif
 
     // per-tile edge state, fetched ONE TILE AHEAD (indices at the top of the previous tile, coordinates in its middle)
-    struct EdgeIn { int r, c; int64_t ge; float ea; bool valid; float xr[3], xc[3], dxo[3]; };
+    struct EdgeIn { int r, c; float ea; bool valid; float xr[3], xc[3], dxo[3]; };
     auto load_indices = [&](int64_t tile, int &r_, int &c_, int &eid_, bool &valid_) {
         const int64_t p0 = tile * 128 + ht;
         valid_ = p0 < E;
         const int64_t p = valid_ ? p0 : E - 1;          // idle slots redo the last edge with zero upstream gradient
-        r_ = ldg_now(a.csr_row + p); c_ = ldg_now(a.csr_col + p); eid_ = ldg_now(a.csr_eid + p);
+        r_ = ldg_now(a.csr_row + p); c_ = ldg_now(a.csr_col + p);
+        eid_ = a.edge_attr ? ldg_now(a.csr_eid + p) : 0;              // the original edge id only addresses a per-edge edge_attr
     };
     auto load_coords = [&](EdgeIn &e, int eid_) {
-        e.ge = (int64_t)(e.r / a.n_per_cloud) * a.edges_per_cloud + eid_;
-        e.ea = a.edge_attr ? ldg_now(a.edge_attr + e.ge) : a.edge_attr_const;
+        e.ea = a.edge_attr ? ldg_now(a.edge_attr + (int64_t)(e.r / a.n_per_cloud) * a.edges_per_cloud + eid_) : a.edge_attr_const;
         const float4 t0 = ldg4_now(a.x4 + (int64_t)e.r * 4), t1 = ldg4_now(a.x4 + (int64_t)e.c * 4);
         e.xr[0] = t0.x; e.xr[1] = t0.y; e.xr[2] = t0.z; e.xc[0] = t1.x; e.xc[1] = t1.y; e.xc[2] = t1.z;
         e.dxo[0] = e.dxo[1] = e.dxo[2] = 0.f;
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
         XB_MARK(0);
         const int r = cur.r, c = cur.c;
         const bool valid = cur.valid;
-        const int64_t ge = cur.ge;
         // ---- this tile's P[row] / Q[col] rows -> shared memory with cp.async (no registers, a tile's worth of latency
         // hidden behind the geometry): Q rows gathered COALESCED (8 lanes per 128-byte row) into tile C, P rows (few distinct
         // rows per warp) copied by their own thread into tile B.  Both tiles were last read by the previous tile's
@@ -618,17 +617,17 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
 #endif
             umma_commit(mbarC_u);
         }
-        {   // dpre = the gradient of P[row] and of Q[col], by ORIGINAL edge id.  Written COALESCED: 8 lanes per 128-byte
-            // row (4 full rows per warp-wide store) out of the b0 + b1 terms this warp just wrote to tile D (16 mantissa
-            // bits) -- a row per thread touched 32 lines per store instruction.
-            const int64_t ge_w = valid ? ge : (int64_t)-1;
+        {   // dpre = the gradient of P[row] and of Q[col], one row per edge in ROW-CSR ORDER (the gather kernel reads a node's
+            // row list as one contiguous run and its col list through csc_pos).  Written COALESCED: 8 lanes per 128-byte row
+            // (4 full rows per warp-wide store) out of the b0 + b1 terms this warp just wrote to tile D (16 mantissa bits)
+            // -- a row per thread touched 32 lines per store instruction.
             const int j = lane & 7;
+            const int64_t pw = tile * 128 + hw * 32;                       // first edge position of this warp
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 // rows of one instruction: two with (row & 4) == 0 and two with (row & 4) != 0, so that their swizzled 64-byte
                 // halves cover all 32 banks (rows 4 it .. 4 it + 3 all landed on the same 16 banks: 4-way conflicts)
                 const int rl = 8 * (it >> 1) + 2 * (it & 1) + ((lane >> 3) & 1) + 4 * (lane >> 4);
-                const long long ge_s = __shfl_sync(0xffffffffu, ge_w, rl);
                 const int row = hw * 32 + rl;
                 const uint8_t *rp = bufD + row * 128 + (j & 1) * 8;
                 const uint2 t0 = *reinterpret_cast<const uint2 *>(rp + (((j >> 1) ^ (row & 7)) << 4));
@@ -638,7 +637,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
                 o.y = __uint_as_float(t0.x & 0xffff0000u) + __uint_as_float(t1.x & 0xffff0000u);
                 o.z = __uint_as_float(t0.y << 16) + __uint_as_float(t1.y << 16);
                 o.w = __uint_as_float(t0.y & 0xffff0000u) + __uint_as_float(t1.y & 0xffff0000u);
-                if (ge_s >= 0) *reinterpret_cast<float4 *>(a.dpre + ge_s * H + 4 * j) = o;
+                if (pw + rl < E) *reinterpret_cast<float4 *>(a.dpre + (pw + rl) * H + 4 * j) = o;
             }
         }
         mbar_wait(mbar, phase); phase ^= 1;
@@ -654,8 +653,9 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             float dxr[3], dxc[3];
             edge_geometry_backward(cur.xr, cur.xc, g, gg, gde, dxr, dxc);
             if (valid) {
-                *reinterpret_cast<float4 *>(a.dxe + ge * 8) = make_float4(dxr[0], dxr[1], dxr[2], 0.f);
-                *reinterpret_cast<float4 *>(a.dxe + ge * 8 + 4) = make_float4(dxc[0], dxc[1], dxc[2], 0.f);
+                const int64_t pe = tile * 128 + ht;                         // row-CSR position of this thread's edge
+                *reinterpret_cast<float4 *>(a.dxe + pe * 8) = make_float4(dxr[0], dxr[1], dxr[2], 0.f);
+                *reinterpret_cast<float4 *>(a.dxe + pe * 8 + 4) = make_float4(dxc[0], dxc[1], dxc[2], 0.f);
             }
         }
         XB_MARK(27);

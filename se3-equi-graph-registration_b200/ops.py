@@ -71,7 +71,7 @@ class BatchGraph:
     edges_per_cloud: int
     err: torch.Tensor     # [1] i32, 1 if an index was out of range
     cptr: torch.Tensor = None   # [G+1] i32  the same edges grouped by col (backward pass only, see with_csc)
-    ceid: torch.Tensor = None   # [E] i32
+    cpos: torch.Tensor = None   # [E] i32    row-CSR position of every entry of the col-grouped lists
     edges: torch.Tensor = None  # the [C,2,E] i64 edge tensor the graph was built from (kept for with_csc)
     nbr: torch.Tensor = None    # ... or the k-NN ids it was built from
 
@@ -124,28 +124,37 @@ _IMPLICIT_CSC = {}
 
 
 def with_csc(graph, nbr=None):
-    """Adds the col-grouped edge lists the backward pass needs (graph.cptr / graph.ceid): the CSR of the same edge
-    tensor with its two rows swapped.  Graphs built from k-NN ids pass `nbr` (the edge tensor is rebuilt from it)."""
+    """Adds the col-grouped edge lists the backward pass needs: graph.cptr [G+1] and graph.cpos [E] = the row-CSR position
+    of every entry (the per-edge gradients are stored in row-CSR order).  k-NN graphs: edge e = i * k + s has col = i, so
+    the col-grouped order is the original order -- cptr[g] = g * k is a constant of the shape and cpos is one small
+    kernel; general graphs: the CSR of the edge tensor with its two rows swapped gives the lists, then the positions."""
     if graph.cptr is not None:
         return graph
     nbr = nbr if nbr is not None else graph.nbr
+    lib = _lib.lib()
+    C, N, epc = graph.clouds, graph.n, graph.edges_per_cloud
+    E = C * epc
+    dev = graph.ptr.device
+    pos = torch.empty(E, dtype=torch.int32, device=dev)
     if nbr is not None and graph.edges is None:
-        # k-NN graph: edge e = i * k + s has col = i, so the col-grouped lists are the original edge order --
-        # cptr[g] = g * k, ceid = 0 .. N k - 1 per cloud: constants of the shape, no second CSR build
-        C, N, k = nbr.shape
-        key = (C, N, k, str(nbr.device))
-        c = _IMPLICIT_CSC.get(key)
-        if c is None:
-            cptr = (torch.arange(C * N + 1, dtype=torch.int64, device=nbr.device) * k).to(torch.int32)
-            ceid = torch.arange(N * k, dtype=torch.int32, device=nbr.device).repeat(C)
-            c = _IMPLICIT_CSC[key] = (cptr, ceid)
-        graph.cptr, graph.ceid = c
+        k = nbr.shape[2]
+        key = (C, N, k, str(dev))
+        cptr = _IMPLICIT_CSC.get(key)
+        if cptr is None:
+            cptr = _IMPLICIT_CSC[key] = (torch.arange(C * N + 1, dtype=torch.int64, device=dev) * k).to(torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.egspr_csr_edge_positions(_ptr(graph.row), _ptr(graph.eid), None, N, epc, E, _ptr(pos), None, _stream()),
+                       "egspr_csr_edge_positions")
+        graph.cptr, graph.cpos = cptr, pos
         return graph
-    edges = graph.edges if graph.edges is not None else (nbr_to_edges(nbr) if nbr is not None else None)
-    if edges is None:
+    if graph.edges is None:
         raise ValueError("with_csc needs the edge tensor (or the k-NN ids) the graph was built from")
-    t = csr_from_edges(edges.flip(1).contiguous(), graph.n)
-    graph.cptr, graph.ceid = t.ptr, t.eid
+    t = csr_from_edges(graph.edges.flip(1).contiguous(), N)
+    cpos = torch.empty(E, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.egspr_csr_edge_positions(_ptr(graph.row), _ptr(graph.eid), _ptr(t.eid), N, epc, E, _ptr(pos), _ptr(cpos), _stream()),
+                   "egspr_csr_edge_positions")
+    graph.cptr, graph.cpos = t.ptr, cpos
     return graph
 
 
@@ -387,7 +396,7 @@ def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_o
     (views of one persistent gradient buffer in the training step); otherwise new zero-filled packs are allocated.
     Returns dfeat [C,N,32] | None, dx [C,N,3], layer grad packs (list), embed_in grad pack | None, embed_out grad pack | None."""
     if graph.cptr is None:
-        raise ValueError("the backward pass needs graph.cptr / graph.ceid: call ops.with_csc(graph) first")
+        raise ValueError("the backward pass needs graph.cptr / graph.cpos: call ops.with_csc(graph) first")
     C, N = graph.clouds, graph.n
     G, L = C * N, len(layer_packs)
     dev = saved["feat"].device
@@ -410,7 +419,7 @@ def egnn_backward(saved, graph, layer_packs, embed_in_pack, embed_out_pack, dh_o
             dx_in = torch.empty((G, 3), dtype=torch.float32, device=dev)
             _lib.check(lib.egspr_egcl_backward(
                 _ptr(saved["hs"][i]), _ptr(saved["x4"][i]), _ptr(saved["Ps"][i]), _ptr(saved["Qs"][i]), _ptr(saved["aggs"][i]),
-                _ptr(graph.ptr), _ptr(graph.row), _ptr(graph.col), _ptr(graph.eid), _ptr(graph.cptr), _ptr(graph.ceid),
+                _ptr(graph.ptr), _ptr(graph.row), _ptr(graph.col), _ptr(graph.eid), _ptr(graph.cptr), _ptr(graph.cpos),
                 _ptr(saved["edge_attr"]), saved["edge_attr_const"], G, graph.edges_per_cloud, N, _ptr(layer_packs[i]),
                 _ptr(dh), _ptr(dx), _ptr(dh_in), _ptr(dx_in), _ptr(gp), _ptr(ws), ws_bytes, st), "egspr_egcl_backward")
             gpacks[i] = gp

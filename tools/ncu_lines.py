@@ -11,15 +11,22 @@ ia, ie, iss = h.index('Source'), h.index('Instructions Executed'), h.index('Warp
 rc = [i for i, c in enumerate(h) if c.startswith('stall_') and 'Not Issued' not in c]
 body = [r for r in rows[hi + 1:] if len(r) > iss]
 dis = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout
-lines, cur = [], None
+funcs, lines, cur = {}, None, None
 for l in dis.splitlines():
+    m = re.match(r'\s*\.section\s+\.text\.(\S+?),', l)
+    if m:
+        lines = funcs.setdefault(m.group(1), [])
+        continue
     m = re.search(r'//## File "([^"]*)", line (\d+)', l)
     if m:
         cur = (m.group(1).split('/')[-1], int(m.group(2)))
         continue
-    if re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+\S', l):
+    if lines is not None and re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+\S', l):
         lines.append(cur)
-print(len(body), 'profiled instructions,', len(lines), 'disassembled')
+# the profiled kernel = the function of the cubin with the same number of instructions
+match = [k for k, v in funcs.items() if len(v) == len(body)]
+print(len(body), 'profiled instructions; functions:', {k[:40]: len(v) for k, v in funcs.items()})
+lines = funcs[match[0]] if match else max(funcs.values(), key=len)
 n = min(len(body), len(lines))
 agg, reasons, execs = collections.Counter(), collections.defaultdict(collections.Counter), collections.Counter()
 for i in range(n):
