@@ -1163,10 +1163,10 @@ extern "C" int egspr_head_eval_ws(const float *feat_src, const float *feat_tgt, 
                    head_pack, n, top_k, w_out, R, t, Hout, loss_parts, 0, nullptr, nullptr};
     // few pairs x large clouds (one CTA per pair would leave most SMs idle while it streams 2 x 2 x n x 128 bytes):
     // the row-wide passes go to `split` CTAs per pair; needs the w_out row as scratch and the caller's partial buffers
-    if (pre_scratch && w_out && pairs < 2 * sm_count() && (size_t)n >= 8192) {
+    if (pre_scratch && w_out && pairs < 2 * sm_count() && (size_t)n >= 2048) {
         int split = (2 * sm_count() + pairs - 1) / pairs;
         if (split > EGSPR_HEAD_MAX_SPLIT) split = EGSPR_HEAD_MAX_SPLIT;
-        if (split > n / 1024) split = n / 1024;
+        if (split > n / 512) split = n / 512;
         if (split >= 2) {
             unsigned long long *pb = reinterpret_cast<unsigned long long *>(pre_scratch);
             float *pl = reinterpret_cast<float *>(pb + (size_t)pairs * split);

@@ -140,7 +140,7 @@ class RegistrationEngine:
                                           p(ho[:B]), p(ho[B:]), p(xo[:B]), p(xo[B:]), p(self.labels), p(self.gt_pose),
                                           p(head), B, N, int(self.model.top_k), p(self.w), p(self.R), p(self.t), p(self.Hm),
                                           p(self.loss_parts), p(self.head_ws), self.head_ws_bytes, st), "egspr_head_eval_ws")
-        n_launch += 2 if (B < 2 * 148 and N >= 8192) else 1
+        n_launch += 2 if (B < 2 * 148 and N >= 2048) else 1
         mark("head")
         self.launches_per_step = n_launch
 
