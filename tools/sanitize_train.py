@@ -31,3 +31,11 @@ for i in range(2):
     step.load(batches[i])
     print("lean", step._step().tolist()[:5])
 torch.cuda.synchronize()
+# the inference path as well: engine (k-NN, CSR, embed, 3 layers, eval head incl. the split pre-pass) in fp32, TF32 and bf16 modes
+eng = P.RegistrationEngine(P.build_model(os.path.join(ROOT, "tests", "golden", "checkpoint-3dmatch.pth"), device=DEV), batch=2, n=2048, k=16, use_graph=False)
+dd = P.synthetic.make_batch(11, 2, n=2048)
+for impl in (0, 4, 5):
+    eng.impl = impl
+    R, t = eng.register(dd["src_feat"], dd["src_pts"], dd["tgt_feat"], dd["tgt_pts"], dd["labels"], dd["gt_pose"])
+    torch.cuda.synchronize()
+    print("engine impl", impl, float(R.sum()))
