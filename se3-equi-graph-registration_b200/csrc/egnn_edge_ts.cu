@@ -46,11 +46,12 @@ constexpr int VG_MT = 0;                              // float[128][36]  message
 constexpr int V_SPTR = 256;           // csr_ptr entries of a tile's rows staged in shared memory
 constexpr int VG_DXS = VG_MT + 128 * V_MROW * 4;      // float4[2][128]  coord_diff * s of the tile (by tile parity)
 constexpr int VG_CARRY = VG_DXS + 2 * 128 * 16;       // float[2][36]    running sums of a row that spans tiles
-constexpr int VG_SPTR = VG_CARRY + 2 * 36 * 4;        // int[2][V_SPTR]  csr_ptr[nstart ...] of the tile (by tile parity)
-constexpr int VG_QT = VG_SPTR + 2 * V_SPTR * 4;       // float[128][36]  Q[col] row of every edge of the tile (coalesced cp.async gather)
+constexpr int VG_SPTR = VG_CARRY + 2 * 36 * 4;        // int[3][V_SPTR]  csr_ptr[nstart ...] of the tile (tile number mod 3: the
+                                                      // coordinate pass of tile t reads its window while tile t+2 may already stage its own)
+constexpr int VG_QT = VG_SPTR + 3 * V_SPTR * 4;       // float[128][36]  Q[col] row of every edge of the tile (coalesced cp.async gather)
 constexpr int VG_RLAST = VG_QT + 128 * V_MROW * 4;    // int             aggregation row of the tile's last edge
 constexpr int VG_MBAR = VG_RLAST + 8;
-constexpr int VG_SIZE = ((VG_MBAR + 8 + 127) / 128) * 128;
+constexpr int VG_SIZE = ((VG_MBAR + 16 + 127) / 128) * 128;   // two mbarriers: stages 2/3 | stage 1 (issued one tile ahead)
 constexpr int VS_TMEM = VS_GRP + V_GROUPS * VG_SIZE;
 constexpr int VS_END = VS_TMEM + 16;
 constexpr size_t V_SMEM_BYTES = VS_END + 1024;        // + slack for the manual 1024-byte alignment
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         par[128 + tid] = __ldg(a.layer_pack + OFF_WC2 + tid);
     }
     if (tid < 32) tmem_alloc(smem_u32(tmem_holder), 512);
-    if (ht == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (ht == 0) { mbar_init(mbar, 1); mbar_init(mbar + 8, 1); fence_mbar_init(); }
     fence_proxy_async();            // the weight tiles were written through the generic proxy
     fence_before_sync();
     __syncthreads();
@@ -248,7 +249,9 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     const uint64_t dW2hi = make_desc_sw128(w_s + 4096), dW2lo = make_desc_sw128(w_s + 8192);
     const uint64_t dW3hi = make_desc_sw128(w_s + 12288), dW3lo = make_desc_sw128(w_s + 16384);
     const uint32_t mbar_u = __shfl_sync(0xffffffffu, mbar, 0);
-    uint32_t phase = 0;
+    // stage 1 has its own barrier: its MMA is committed while slower warps may still be waiting for stage 3 of the
+    // same tile, and a parity wait cannot tell phases two completions apart
+    uint32_t phase = 0, phase1 = 0;
 
     // ---- this group's contiguous range of aggregation rows ----
     const int64_t G = a.num_nodes;
@@ -265,11 +268,10 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     // coordinate segment sums of one finished tile: threads 112..127 of the group (warp 3, which has the least
     // feature-row work), ONE aggregation row per thread, all three components as a float4 -- runs beside the
     // feature sums of the following tile, off the other warps' critical path
-    auto coord_pass = [&](int tpar, int tp0, int tend_, int nfirst, int nlast, float4 x_pre) {
+    auto coord_pass = [&](int tpar, const int *sp, int tp0, int tend_, int nfirst, int nlast, float4 x_pre) {
         if (ht < 112) return;
         bool first = true;
         const float4 *dx_t = dxs2 + tpar * 128;
-        const int *sp = sptr2 + tpar * V_SPTR;
         for (int n = nfirst + (ht - 112); n <= nlast; n += 16) {
             const float4 x_old = first ? x_pre : ldg4(a.x4 + (int64_t)n * 4);
             first = false;
@@ -296,6 +298,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         }
     };
     int prev_p0 = 0, prev_tend = 0, prev_nstart = 0, prev_rlast = -1;     // the tile whose coordinate pass is pending
+    const int *prev_sp = sptr2;
+    int sbuf = 0;                    // tile number mod 3
 
     // Q[col] rows of a tile, gathered COALESCED: 8 lanes fetch the 8 16-byte chunks of one row, so a warp-wide
     // cp.async touches 4 full 128-byte lines (4 L1 wavefronts) instead of 32 quarter-sectors of 32 different lines
@@ -372,6 +376,33 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
     float dxn = 0.f, dyn = 0.f, dzn = 0.f;      // coord_diff of this thread's edge in the next tile
     if (pbeg < pend)
         geometry_to_tmem(xrn0, xrn1, xrn2, xcn0, xcn1, xcn2, edge_attr_of(rn, min(pbeg + ht, pend - 1)), dxn, dyn, dzn);
+    // The stage-1 product of a tile is issued at the END of the previous tile (its operand is already in tensor memory)
+    // into the columns of A_lo, which are free between the stage-3 MMA of one tile and the stage-2 operand of the next:
+    // its round trip runs under the stage-3 epilogue and the loads at the top of the tile instead of in front of them.
+    auto issue_stage1 = [&]() {
+        fence_after_sync();
+        if constexpr (BF16) {
+            issue_bf16_ts(tAlo, tA1, dX1);
+        } else {
+            umma_tf32_ts(tAlo, tA1 + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
+            umma_tf32_ts(tAlo, tA1 + 8, dX1 + 2, IDESC_TF32_M128_N32, 1);
+        }
+        if constexpr (!FAST) {
+            umma_tf32_ts(tAlo, tA1 + 16, dX1 + 0, IDESC_TF32_M128_N32, 1);     // lo x Whi
+            umma_tf32_ts(tAlo, tA1 + 24, dX1 + 2, IDESC_TF32_M128_N32, 1);
+            umma_tf32_ts(tAlo, tA1 + 0, dX1 + 4, IDESC_TF32_M128_N32, 1);      // hi x Wlo
+            umma_tf32_ts(tAlo, tA1 + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
+        }
+        umma_commit(mbar_u + 8);
+    };
+    tmem_wait_st();
+    fence_before_sync();
+    bar_sync(bar_id, 128);
+    // fp32 mode (6 + 12 + 12 MMAs per tile and group on an in-order tensor pipe): an early stage-1 batch delays the other
+    // groups' stage-2/3 batches, which ARE on their critical paths (measured 306 -> 313 us); there it is issued at the top
+    // of its own tile (still without a barrier: the operand was complete at the previous tile's stage-3 barrier)
+    constexpr bool EARLY_S1 = MODE != 0;
+    if (EARLY_S1 && pbeg < pend && hw_u == 0 && elect_one()) issue_stage1();
 #ifdef EGSPR_TS_TIMING
     int tile_no = -1;
 #endif
@@ -381,6 +412,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         if (grp != 1) tile_no = 1000;
 #endif
         TS_MARK(0);
+        if (!EARLY_S1 && hw_u == 0 && elect_one()) issue_stage1();
         const int tend = min(p0 + 128, pend);
         int p = p0 + ht;
         if (p >= pend) p = pend - 1;               // idle slot: recompute the last edge, never reduced
@@ -406,38 +438,17 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         }
         if (ht == tend - 1 - p0) s_rlast[0] = r;
         const float dx = dxn, dy = dyn, dz = dzn;       // stage-1 operand of this tile was written one tile ahead
-        tmem_wait_st();
-        fence_before_sync();
         TS_MARK(1);
-        bar_sync(bar_id, 128);
         TS_MARK(2);
-        if (hw_u == 0 && elect_one()) {     // stage 1 is issued by warp 0, stage 2 by warp 1, stage 3 by warp 2
-            fence_after_sync();
-            if constexpr (BF16) {
-                issue_bf16_ts(tD, tA1, dX1);
-            } else {
-            umma_tf32_ts(tD, tA1 + 0, dX1 + 0, IDESC_TF32_M128_N32, 0);      // hi x Whi
-            umma_tf32_ts(tD, tA1 + 8, dX1 + 2, IDESC_TF32_M128_N32, 1);
-            }
-            if constexpr (!FAST) {
-                umma_tf32_ts(tD, tA1 + 16, dX1 + 0, IDESC_TF32_M128_N32, 1);     // lo x Whi
-                umma_tf32_ts(tD, tA1 + 24, dX1 + 2, IDESC_TF32_M128_N32, 1);
-                umma_tf32_ts(tD, tA1 + 0, dX1 + 4, IDESC_TF32_M128_N32, 1);      // hi x Wlo
-                umma_tf32_ts(tD, tA1 + 8, dX1 + 6, IDESC_TF32_M128_N32, 1);
-            }
-            umma_commit(mbar_u);
-        }
-        const int rlast = s_rlast[0];
-        int *sp = sptr2 + par * V_SPTR;
+        int *sp = sptr2 + sbuf * V_SPTR;
         float v[32];
         TS_MARK(3);
-        mbar_wait(mbar, phase); phase ^= 1;
+        mbar_wait(mbar + 8, phase1); phase1 ^= 1;
         TS_MARK(4);
         fence_after_sync();
-        tmem_ld32(tmem_w, v);
-        // stage csr_ptr[nstart ...] of this tile's rows for the segment sums (visible after barriers 2, 3).  The two loads
-        // were issued at the top of the tile; consuming them here, after the stage-1 MMA wait, hides their L2 latency
-        // (consumed right after the first barrier they stalled every warp for ~800 cycles per tile)
+        tmem_ld32(tmem_w + 64, v);
+        // stage csr_ptr[nstart ...] of this tile's rows for the segment sums (visible after the two barriers below).  The
+        // loads were issued at the top of the tile; consuming them here, after the stage-1 wait, hides their L2 latency
         sp[ht] = pt0; sp[ht + 128] = pt1;
         {   // the next tile's endpoint coordinates (rn, cn were loaded at the top of this tile)
             const float4 t0 = ldg4(a.x4 + (int64_t)rn * 4), t1 = ldg4(a.x4 + (int64_t)cn * 4);
@@ -463,6 +474,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         TS_MARK(5);
         bar_sync(bar_id, 128);
         TS_MARK(6);
+        const int rlast = s_rlast[0];   // written at the top of the tile, before the barrier above
         if (hw_u == 1 && elect_one()) {
             fence_after_sync();
             if constexpr (BF16) issue_bf16_ts(tD, tAhi, dW2hi);
@@ -549,12 +561,13 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             }
         }
         // the previous tile's coordinate sums (its dxs were completed before this tile's barriers)
-        if (prev_rlast >= 0) coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast, x_pre);
+        if (prev_rlast >= 0) coord_pass(par ^ 1, prev_sp, prev_p0, prev_tend, prev_nstart, prev_rlast, x_pre);
         // ---- accumulator -> registers, SiLU + wc2 epilogue (:219-229, :264) ----
         TS_MARK(10);
         mbar_wait(mbar, phase); phase ^= 1;
         TS_MARK(11);
         fence_after_sync();
+        if (EARLY_S1 && p0 + 128 < pend && hw_u == 2 && elect_one()) issue_stage1();     // the next tile's stage 1
         tmem_ld32(tmem_w, v);
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -566,7 +579,8 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         }
         const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         dxs2[par * 128 + ht] = make_float4(dx * s, dy * s, dz * s, 0.f);                  // trans = coord_diff * s
-        prev_p0 = p0; prev_tend = tend; prev_nstart = nstart; prev_rlast = rlast;
+        prev_p0 = p0; prev_tend = tend; prev_nstart = nstart; prev_rlast = rlast; prev_sp = sp;
+        sbuf = (sbuf == 2) ? 0 : sbuf + 1;
         nstart = (ptr_at(sp, nstart, rlast + 1) <= tend) ? rlast + 1 : rlast;
     }
     cp_async_wait_all();             // the look-ahead gather of the (non-existent) tile after the last one
@@ -574,7 +588,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
         fence_before_sync();
         bar_sync(bar_id, 128);      // the last tile's dxs are complete
         const int n = prev_nstart + (ht - 112);
-        coord_pass(par ^ 1, prev_p0, prev_tend, prev_nstart, prev_rlast,
+        coord_pass(par ^ 1, prev_sp, prev_p0, prev_tend, prev_nstart, prev_rlast,
                    (ht >= 112 && n <= prev_rlast) ? ldg4(a.x4 + (int64_t)n * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
     // rows after the last edge of the range have no edges at all: zero aggregate, unchanged coordinates

@@ -2,6 +2,9 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from se3_equi_graph_registration_b200 import _lib
+if len(sys.argv) > 1:        # A/B runs: a developer build of the library (build/<name>/libegspr_b200.so)
+    _lib.LIB_PATH = os.path.join(ROOT, "build", sys.argv[1], "libegspr_b200.so")
 import se3_equi_graph_registration_b200 as P
 import bench
 impls = [int(x) for x in os.environ.get("EGSPR_IMPLS", "1,3").split(",")]
