@@ -490,7 +490,7 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
             "steps": steps, "loss": float(loss), "grad_norm": float(gn_t), "loss_finite": finite,
             "replicas_identical": replicas_identical, "embedding_out_scale": TRAIN_TEMPER,
             "shipped_checkpoint": shipped, "launch_mode": mode,
-            "kernels_per_step": 35 if mode == "cuda graph" else None, "cpu_baseline": cpu}
+            "kernels_per_step": 36 if mode == "cuda graph" else None, "cpu_baseline": cpu}
 
 
 def cpu_train_baseline(pairs=2, reps=2):

@@ -10,7 +10,7 @@ Two forms of the step:
   train_step        the loop body as written in the reference: model(...) -> training_loss -> loss.backward() ->
                     optimizer.step(), through the nn.Module API and torch.autograd (whose backward passes are the gradient
                     kernels).  Drop-in, eager.
-  GraphedTrainStep  the same arithmetic as a fixed launch sequence (~35 kernels, no autograd, no per-parameter tensor
+  GraphedTrainStep  the same arithmetic as a fixed launch sequence (36 launches, no autograd, no per-parameter tensor
                     ops), captured once as a CUDA graph: k-NN -> CSR -> weight packs (one gather) -> EGNN forward ->
                     head + losses -> backward kernels -> gradients (one gather) -> all-reduce -> optimizer.
 """
@@ -65,7 +65,7 @@ def train_step(model, optimizer, batch, group=None):
 
 
 class GraphedTrainStep:
-    """The training step as ONE CUDA graph of ~35 kernels.
+    """The training step as ONE CUDA graph of 36 launches.
 
     batch = (src_feat, src_pts, tgt_feat, tgt_pts, corr, labels, gt_pose), as the reference's loader yields them
     (3dm:975-979); the k-NN graphs of 3dm:1003-1089 are built inside the step, directly as CSR (edge_attr = the reference's
