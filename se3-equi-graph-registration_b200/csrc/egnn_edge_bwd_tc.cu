@@ -315,16 +315,19 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
         const int r = cur.r, c = cur.c;
         const bool valid = cur.valid;
         // ---- this tile's P[row] / Q[col] rows -> shared memory with cp.async (no registers, a tile's worth of latency
-        // hidden behind the geometry): Q rows gathered COALESCED (8 lanes per 128-byte row) into tile C, P rows (few distinct
-        // rows per warp) copied by their own thread into tile B.  Both tiles were last read by the previous tile's
-        // stage-5 weight-gradient MMAs.
+        // hidden behind the geometry), both gathered COALESCED: 8 lanes per 128-byte row, 4 rows per warp-wide instruction
+        // (4 L1 wavefronts).  With every thread copying its own P row, an instruction wrote 32 different shared-memory rows
+        // = 32 wavefronts, and those 8 instructions were 36 % of the kernel's shared-memory wavefronts (ncu, source page).
+        // Q -> tile C, P -> tile B; both tiles were last read by the previous tile's stage-5 weight-gradient MMAs.
         if (tile > tile0) { mbar_wait(mbarB, phase_w ^ 1); fence_after_sync(); }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c_src = __shfl_sync(0xffffffffu, c, 4 * i + (lane >> 3));
+            const int r_src = __shfl_sync(0xffffffffu, r, 4 * i + (lane >> 3));
             const uint32_t row = (uint32_t)(hw * 32 + 4 * i + (lane >> 3));
-            cp_async16_cg(bufC_s + row * 128 + ((((uint32_t)lane & 7u) ^ (row & 7u)) << 4), a.Q + (int64_t)c_src * H + 4 * (lane & 7));
-            cp_async16_cg(bufB_s + own_row + (((uint32_t)i ^ own_sw) << 4), a.P + (int64_t)r * H + 4 * i);
+            const uint32_t off = row * 128 + ((((uint32_t)lane & 7u) ^ (row & 7u)) << 4);
+            cp_async16_cg(bufC_s + off, a.Q + (int64_t)c_src * H + 4 * (lane & 7));
+            cp_async16_cg(bufB_s + off, a.P + (int64_t)r_src * H + 4 * (lane & 7));
         }
         cp_async_commit();
         int rn = 0, cn = 0, eidn = 0;
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
         }
         float v[32];
         cp_async_wait_all();
-        __syncwarp();                                   // the Q rows of this warp's edges were written by its other lanes
+        __syncwarp();                                   // the P / Q rows of this warp's edges were written by its other lanes
         XB_MARK(4);
         mbar_wait(mbar, phase); phase ^= 1;
         XB_MARK(5);
@@ -625,9 +628,9 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
             const int64_t pw = tile * 128 + hw * 32;                       // first edge position of this warp
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                // rows of one instruction: two with (row & 4) == 0 and two with (row & 4) != 0, so that their swizzled 64-byte
-                // halves cover all 32 banks (rows 4 it .. 4 it + 3 all landed on the same 16 banks: 4-way conflicts)
-                const int rl = 8 * (it >> 1) + 2 * (it & 1) + ((lane >> 3) & 1) + 4 * (lane >> 4);
+                // rows of one instruction: within each HALF-warp (a 64-bit access is served per half-warp) one row with
+                // (row & 4) == 0 and one with (row & 4) != 0, so that their swizzled 64-byte halves cover all 32 banks
+                const int rl = 8 * (it >> 1) + 2 * (it & 1) + 4 * ((lane >> 3) & 1) + (lane >> 4);
                 const int row = hw * 32 + rl;
                 const uint8_t *rp = bufD + row * 128 + (j & 1) * 8;
                 const uint2 t0 = *reinterpret_cast<const uint2 *>(rp + (((j >> 1) ^ (row & 7)) << 4));

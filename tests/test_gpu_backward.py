@@ -216,11 +216,14 @@ def test_graphed_train_step_equals_eager(golden_dir):
         finals[mode] = {k: v.detach().clone() for k, v in model.named_parameters()}
     assert np.all(np.isfinite(losses["graph"]))
     assert np.allclose(losses["eager"], losses["graph"], rtol=2e-3), losses
-    moved = 0.0
+    # Adam divides by sqrt(v): an element whose gradient is at rounding level (the two paths sum the same terms in a
+    # different order, and weight-gradient atomics land in launch order) may take a step of a different size, so a few
+    # elements differ by a fraction of one step (lr = 1e-4; six steps move a weight by <= 6e-4).  Bound the worst element
+    # by half a step and the typical element much tighter.
     for k in finals["eager"]:
-        d = float((finals["eager"][k] - finals["graph"][k]).abs().max())
-        assert d <= 2e-5, (k, d)                                    # 6 Adam steps of 1e-4 move a weight by <= 6e-4
-        moved = max(moved, d)
+        d = (finals["eager"][k] - finals["graph"][k]).abs()
+        assert float(d.max()) <= 5e-5, (k, float(d.max()))
+        assert float(d.mean()) <= 2e-6, (k, float(d.mean()))
 
 
 def test_fused_train_losses_match_torch_formulas(golden_dir):
