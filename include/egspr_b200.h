@@ -38,7 +38,7 @@ extern "C" {
 
 /* layer-pack layout (floats) produced by the host mirror from the live nn.Parameters; see
  * se3-equi-graph-registration_b200/packing.py and DESIGN.md "weight packs" */
-#define EGSPR_LAYER_PACK_FLOATS 7104
+#define EGSPR_LAYER_PACK_FLOATS 8128
 #define EGSPR_EMBED_PACK_FLOATS 1056
 #define EGSPR_HEAD_PACK_FLOATS 2640
 
@@ -97,11 +97,14 @@ int egspr_node_embed(const float *feat, const float *x3, int64_t num_nodes, cons
  * edges_in_d=0 has a zero edge_attr column in its pack).
  * impl: 0 = auto (the tensor-core path if agg_ws != NULL, else the fused CUDA-core kernel);
  *       1 / 2 = fused fp32 CUDA-core kernel with 64 / 256 nodes per block (edge, reduce and node phases
- *           in one launch);
+ *           in one launch).  Reads the per-head [4][8][8] layout of the second edge Linear: layers with 4
+ *           heads only (packing.py fills that region with NaN for other head counts);
  *       3 = tensor-core path: edge kernel (first edge Linear's geometry block, the heads' second Linear
  *           and coord_mlp.0 on tcgen05 with the A operand handed over through tensor memory, 3xTF32 =
  *           fp32-level accuracy; streaming in-order segment sums) + node kernel (node MLP, residual, next
  *           layer's P/Q or embedding_out, also tcgen05); needs agg_ws [num_nodes][32] floats of scratch.
+ *           The heads' second Linear is read as ONE block-diagonal 32 x 32 matrix (pack offset 7104), so
+ *           this path and egspr_egcl_backward take any num_heads dividing 32 (E_GCL(num_heads=...), 3dm:186-207).
  *       4 = impl 3 with the edge kernel in reduced precision (BASELINE config 2's "looser bound" edge MLP):
  *           single-pass TF32 operands (10-bit mantissa, round to nearest) and SiLU through MUFU.TANH;
  *           segment sums, node kernel and everything else as in impl 3.

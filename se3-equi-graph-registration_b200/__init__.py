@@ -14,11 +14,12 @@ from .engine import RegistrationEngine, PipelinedEngine  # noqa: F401
 from . import train  # noqa: F401
 
 
-def build_model(checkpoint=None, device="cuda:0", n_layers=3, variant="eval"):
+def build_model(checkpoint=None, device="cuda:0", n_layers=3, variant="eval", num_heads=4):
     """EGNN(32,32,32,in_edge_nf=1,n_layers=3) + CrossAttentionPoseRegression(hidden_nf=32), the
     configuration of the reference scripts (src/eval_egnn_metrics.py:1371-1375).  variant: 'eval' = the class of the
-    evaluation script (default here: the inference engine), 'train' = the class of the training scripts."""
-    egnn = EGNN(32, 32, 32, in_edge_nf=1, device=device, n_layers=n_layers)
+    evaluation script (default here: the inference engine), 'train' = the class of the training scripts.  num_heads: 4 for
+    the shipped checkpoints; any divisor of 32 for models trained with another head count."""
+    egnn = EGNN(32, 32, 32, in_edge_nf=1, device=device, n_layers=n_layers, num_heads=num_heads)
     model = CrossAttentionPoseRegression(egnn, num_nodes=2048, hidden_nf=32, device=device, variant=variant).to(device)
     if checkpoint is not None:
         load_checkpoint(checkpoint, None, egnn, model, device=device)

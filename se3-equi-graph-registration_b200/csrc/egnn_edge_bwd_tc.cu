@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
     for (int i = tid; i < 1024; i += X_THREADS) {
         const int o = i >> 5, k = i & 31;
         {
-            const float w = ((o >> 3) == (k >> 3)) ? __ldg(a.pack + OFF_W2P + 64 * (o >> 3) + 8 * (k & 7) + (o & 7)) : 0.f;
+            const float w = __ldg(a.pack + OFF_W2F + i);
             const float h0 = trunc16(w);
             *reinterpret_cast<uint16_t *>(base + XS_W + 4096 + sw128_off_bf16(o, k)) = (uint16_t)(__float_as_uint(h0) >> 16);
             *reinterpret_cast<uint16_t *>(base + XS_W + 4096 + sw128_off_bf16(o, 32 + k)) = (uint16_t)(__float_as_uint(w - h0) >> 16);
@@ -723,10 +723,8 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
         for (int sl = 0; sl < R_SLOTS; ++sl) val += red[sl * R_N + i];
         int dst = -1;
         if (i < R_W2) dst = OFF_WC1 + i;
-        else if (i < R_WG) {                                   // dW2[o][i2] -> pack [head][in][out], same-head entries only
-            const int o = (i - R_W2) >> 5, i2 = (i - R_W2) & 31;
-            if ((o >> 3) == (i2 >> 3)) dst = OFF_W2P + 64 * (o >> 3) + 8 * (i2 & 7) + (o & 7);
-        } else if (i < R_WG + 384) dst = OFF_WG + (i - R_WG);
+        else if (i < R_WG) dst = OFF_W2F + (i - R_W2);       // dW2[o][i2], the full matrix (the host keeps the heads' diagonal blocks)
+        else if (i < R_WG + 384) dst = OFF_WG + (i - R_WG);
         else if (i < R_WG + 416) dst = OFF_WEA + (i - R_WG - 384);
         else if (i < R_BC1) dst = -1;                          // geo rows 13..15 are padding
         else if (i < R_B2) { dst = OFF_BC1 + (i - R_BC1); red[i] = val; }      // kept for the d ln beta product below

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             float w1 = 0.f;
             if (kk < 12) w1 = __ldg(a.layer_pack + OFF_WG + 32 * kk + o);
             else if (kk == 12) w1 = __ldg(a.layer_pack + OFF_WEA + o);
-            const float w2 = ((o >> 3) == (k >> 3)) ? __ldg(a.layer_pack + OFF_W2P + 64 * (o >> 3) + 8 * (k & 7) + (o & 7)) : 0.f;
+            const float w2 = __ldg(a.layer_pack + OFF_W2F + i);
             const float w3 = __ldg(a.layer_pack + OFF_WC1 + i);
             const int off = sw128_off_bf16(o, k);
             *reinterpret_cast<uint16_t *>(base + VS_W + off) = (uint16_t)(pack_bf16x2(w1, 0.f) & 0xffffu);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             *reinterpret_cast<float *>(base + VS_W + sw128_off(o, k)) = (k < 16) ? hi : (w - hi);
         }
         {   // stage 2: block-diagonal of the heads' second Linear, pack layout [head][in][out]
-            const float w = ((o >> 3) == (k >> 3)) ? __ldg(a.layer_pack + OFF_W2P + 64 * (o >> 3) + 8 * (k & 7) + (o & 7)) : 0.f;
+            const float w = __ldg(a.layer_pack + OFF_W2F + i);
             const float hi = FAST ? tf32_rna(w) : tf32_hi(w);
             *reinterpret_cast<float *>(base + VS_W + 4096 + sw128_off(o, k)) = hi;
             *reinterpret_cast<float *>(base + VS_W + 8192 + sw128_off(o, k)) = w - hi;

@@ -16,7 +16,8 @@ constexpr int H = EGSPR_HIDDEN;  // hidden width
 
 // ---- layer pack offsets (floats); mirrored by packing.py -------------------------------------
 constexpr int OFF_WG = 0;        // [12][32]   geo rows of the first edge Linear (cols 64..75), out-contiguous
-constexpr int OFF_W2P = 384;     // [4][8][8]  second edge Linear per head, [head][in][out]
+constexpr int OFF_W2P = 384;     // [4][8][8]  second edge Linear per head, [head][in][out]: num_heads = 4 only (CUDA-core
+                                 //            kernels, impl 1 / 2); NaN for other head counts
 constexpr int OFF_B2 = 640;      // [32]
 constexpr int OFF_LNG = 672;     // [32]
 constexpr int OFF_LNB = 704;     // [32]
@@ -34,8 +35,10 @@ constexpr int OFF_WQT = 5984;    // [32][32]   first edge Linear, h[col] block, 
 constexpr int OFF_BQ = 7008;     // [32]       first edge Linear bias (heads concatenated)
 constexpr int OFF_WEA = 7040;    // [32]       first edge Linear edge_attr column (zeros if edges_in_d=0)
 constexpr int PQ_PART = 7072 - 4960;
+constexpr int OFF_W2F = 7104;    // [32][32]   second edge Linear of ALL heads as one block-diagonal matrix, [out][in] (any
+                                 //            num_heads dividing 32; the tensor-core kernels read this, never OFF_W2P)
 constexpr int LAYER_PACK = EGSPR_LAYER_PACK_FLOATS;
-static_assert(LAYER_PACK >= 7072, "pack size");
+static_assert(LAYER_PACK >= OFF_W2F + 1024, "pack size");
 // embed pack: WT [32][32] ([in][out]) + bias [32]
 constexpr int EMBED_PACK = EGSPR_EMBED_PACK_FLOATS;
 // head pack: W0T [64][32], b0 [32], W1T [32][16], b1 [16], w2 [16], b2 [1]

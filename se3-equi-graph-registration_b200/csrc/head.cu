@@ -849,6 +849,15 @@ __global__ void __launch_bounds__(CB_THREADS) corr_loss_backward_kernel(const He
     }
 }
 
+// d acos(clamp(c, -1, 1)) / dc.  Outside [-1, 1] the clamp blocks the gradient (0, as torch.clamp).  AT c == +-1 exactly
+// torch's autograd returns -+inf (clamp passes the boundary, acos' is singular there): a prediction that equals the ground
+// truth to fp32 rounding -- reachable on noise-free synthetic pairs -- then turns every EGNN gradient into NaN and the next
+// Adam step destroys the model.  Deliberate deviation from the reference at that single point: a zero subgradient.
+__device__ __forceinline__ float acos_slope(float c) {
+    const float s = 1.0f - c * c;
+    return s > 0.f ? -1.0f / sqrtf(s) : 0.f;
+}
+
 // ---- training losses on the device: 3dm:681-694 (top-k of the output-feature similarity), 3dm:760-781
 // (BCE of mlp([h_s | h_t][top-k]) against the labels; MSE between the z-scored similarity and the z-scored input-feature
 // similarity, mean / unbiased std over the whole batch), plus pose_loss 3dm:896-962 and the loop's total 3dm:1118. ----
@@ -1042,13 +1051,13 @@ __global__ void __launch_bounds__(1024) train_loss_finalize_kernel(const float *
             for (int j = 0; j < 3; ++j) tr = fmaf(Rb[i * 3 + j], G[i * 4 + j], tr);
         const float c = (tr - 1.0f) * 0.5f, cc = fminf(fmaxf(c, -1.0f), 1.0f);
         pl[0] += (double)acosf(cc);
-        const float kr = (c < -1.0f || c > 1.0f) ? 0.f : -0.5f / sqrtf(1.0f - cc * cc);
+        const float kr = 0.5f * acos_slope(c);
         const float t0 = t[b * 3], t1 = t[b * 3 + 1], t2 = t[b * 3 + 2], g0 = G[3], g1 = G[7], g2 = G[11];
         const float dot = t0 * g0 + t1 * g1 + t2 * g2;
         const float nt = sqrtf(t0 * t0 + t1 * t1 + t2 * t2), ng = sqrtf(g0 * g0 + g1 * g1 + g2 * g2);
         const float cs = dot / (nt * ng), cl = fminf(fmaxf(cs, -1.0f), 1.0f);
         pl[1] += (double)acosf(cl);
-        const float kt = (cs < -1.0f || cs > 1.0f) ? 0.f : -1.0f / sqrtf(1.0f - cl * cl);
+        const float kt = acos_slope(cs);
         const float ia = 1.0f / (nt * ng), bb = cs / (nt * nt), sc = scale / (float)pairs;       // .mean() over the pairs 3dm:1118
         if (dR) {
 #pragma unroll
@@ -1087,7 +1096,7 @@ __global__ void pose_loss_kernel(const float *__restrict__ R, const float *__res
     const float cc = fminf(fmaxf(c, -1.0f), 1.0f);
     rot_loss[b] = acosf(cc);
     if (gR) {
-        const float k = (c < -1.0f || c > 1.0f) ? 0.f : -0.5f / sqrtf(1.0f - cc * cc);   // d acos(c)/dc * dc/dtr
+        const float k = 0.5f * acos_slope(c);   // d acos(c)/dc * dc/dtr
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -1100,7 +1109,7 @@ __global__ void pose_loss_kernel(const float *__restrict__ R, const float *__res
     const float cl = fminf(fmaxf(cs, -1.0f), 1.0f);
     trans_loss[b] = acosf(cl);
     if (gt_) {
-        const float k = (cs < -1.0f || cs > 1.0f) ? 0.f : -1.0f / sqrtf(1.0f - cl * cl);
+        const float k = acos_slope(cs);
         // d cos / d t = g / (|t||g|) - cos * t / |t|^2
         const float a = 1.0f / (nt * ng), bb = cs / (nt * nt);
         gt_[b * 3] = k * (g0 * a - bb * t0); gt_[b * 3 + 1] = k * (g1 * a - bb * t1); gt_[b * 3 + 2] = k * (g2 * a - bb * t2);

@@ -92,6 +92,7 @@ class RegistrationEngine:
         B, N, k = self.B, self.N, self.k
         C = 2 * B
         G = C * N
+        self.model.egnn.check_impl(self.impl)
         layers, pin, pout = self.model.egnn.packs()
         head = self.model._pack_head.get()
         st = ops._stream()

@@ -197,7 +197,7 @@ class E_GCL(nn.Module):
 # EGNN
 # ---------------------------------------------------------------------------------------------
 class EGNN(nn.Module):
-    """3dm:293-340.  `num_heads` is an extra keyword (default 4): the shipped checkpoints carry 4
+    """3dm:293-340.  `num_heads` is an extra keyword (default 4; any divisor of 32): the shipped checkpoints carry 4
     edge-MLP heads per layer although the reference constructor never forwards num_heads
     (SURVEY F2), so 4 is what makes `load_state_dict(strict=True)` succeed."""
 
@@ -218,7 +218,15 @@ class EGNN(nn.Module):
         self._pack_out = packing.PackCache(lambda: list(self.embedding_out.parameters()),
                                            lambda: packing.pack_linear32(self.embedding_out))
         self.impl = 0
+        self.num_heads = num_heads
         self.to(device)                                                                     # 3dm:326
+
+    def check_impl(self, impl):
+        """The CUDA-core kernels (impl 1 / 2) read the per-head [4][8][8] layout of the second edge Linear: 4 heads only.
+        The tensor-core kernels (impl 0 / 3 / 4 / 5 and the backward pass) take any head count dividing 32."""
+        if int(impl) in (1, 2) and self.num_heads != 4:
+            raise NotImplementedError(f"impl {int(impl)} (CUDA-core E_GCL kernels) supports num_heads=4 only; this EGNN has "
+                                      f"{self.num_heads} -- use the tensor-core path (impl 0)")
 
     def packs(self):
         layers = [self._modules["gcl_%d" % i].layer_pack() for i in range(self.n_layers)]
@@ -233,6 +241,7 @@ class EGNN(nn.Module):
                 g._check_supported()
             spec = (gcls, self.embedding_in, self.embedding_out, ops.with_csc(graph), edge_attr, float(edge_attr_const))
             return _ag.EGNNFunction.apply(spec, h, x, *_ag.egnn_param_list(gcls, self.embedding_in, self.embedding_out))
+        self.check_impl(self.impl)
         layers, pin, pout = self.packs()
         return ops.egnn_forward(h, x, graph, layers, pin, pout, edge_attr=edge_attr,
                                 edge_attr_const=edge_attr_const, impl=self.impl)

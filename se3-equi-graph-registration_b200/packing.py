@@ -3,7 +3,7 @@ kernels.  state_dict stays the single source of truth -- packs are derived tenso
 whenever a parameter's storage or version counter changes (optimizer step, load_state_dict).
 
 Layouts mirror csrc/egspr_common.cuh (OFF_* constants).  Reference shapes:
-  gcl_i.edge_mlps.{g}.0.weight (8,77|76)  gcl_i.edge_mlps.{g}.2.weight (8,8)   3dm:202-208
+  gcl_i.edge_mlps.{g}.0.weight (d,77|76)  gcl_i.edge_mlps.{g}.2.weight (d,d), d = 32 / num_heads   3dm:202-208
   gcl_i.layer_norm (32)                                                         3dm:209
   gcl_i.node_mlp.0.weight (32,64), .2.weight (32,32)                            3dm:212-216
   gcl_i.coord_mlp.0.weight (32,32), .2.weight (1,32) no bias                    3dm:219-229
@@ -13,12 +13,12 @@ Layouts mirror csrc/egspr_common.cuh (OFF_* constants).  Reference shapes:
 import torch
 
 H = 32
-LAYER_PACK = 7104
+LAYER_PACK = 8128
 EMBED_PACK = 1056
 HEAD_PACK = 2640
 
 OFF = dict(WG=0, W2P=384, B2=640, LNG=672, LNB=704, WC1=736, BC1=1760, WC2=1792, WN1T=1824, BN1=3872,
-           WN2T=3904, BN2=4928, WPT=4960, WQT=5984, BQ=7008, WEA=7040)
+           WN2T=3904, BN2=4928, WPT=4960, WQT=5984, BQ=7008, WEA=7040, W2F=7104)
 
 
 def _put(buf, off, t):
@@ -26,19 +26,41 @@ def _put(buf, off, t):
     buf[off:off + t.numel()] = t
 
 
+# Constants a pack may hold besides parameter elements.  The index machinery (PackCache, FlatState) rebuilds packs as
+# `source[index]` with source = [0, NaN, parameters...]: while an index map is being probed the builders write the
+# constants' own element numbers instead of their values.
+_PROBING = False
+
+
+def _nan():
+    return 1.0 if _PROBING else float("nan")
+
+
+N_CONST = 2      # source elements 0 (zero) and 1 (NaN)
+
+
 def pack_layer(gcl):
-    """gcl: an E_GCL-shaped module (edge_mlps, layer_norm, node_mlp, coord_mlp)."""
+    """gcl: an E_GCL-shaped module (edge_mlps, layer_norm, node_mlp, coord_mlp), any num_heads dividing 32."""
     heads = list(gcl.edge_mlps)
     w1 = torch.cat([m[0].weight for m in heads], dim=0)        # [32, F]
     b1 = torch.cat([m[0].bias for m in heads], dim=0)
     F_in = w1.shape[1]
-    if w1.shape[0] != H or len(heads) != 4 or F_in not in (76, 77):
+    nh = len(heads)
+    if w1.shape[0] != H or H % nh != 0 or F_in not in (76, 77) or any(tuple(m[2].weight.shape) != (H // nh, H // nh) for m in heads):
         raise NotImplementedError(
-            f"egspr_b200 kernels are specialised for hidden_nf=32, num_heads=4, edges_in_d in (0,1); got "
-            f"hidden={w1.shape[0]}, heads={len(heads)}, edge feature width={F_in}")
+            f"egspr_b200 kernels are specialised for hidden_nf=32, num_heads dividing 32, edges_in_d in (0,1); got "
+            f"hidden={w1.shape[0]}, heads={nh}, edge feature width={F_in}")
+    d = H // nh
     buf = torch.zeros(LAYER_PACK, dtype=torch.float32, device=w1.device)
     _put(buf, OFF["WG"], w1[:, 64:76].t().contiguous())                       # [12][32]
-    _put(buf, OFF["W2P"], torch.stack([m[2].weight.t() for m in heads]))      # [4][in 8][out 8]
+    if nh == 4:
+        _put(buf, OFF["W2P"], torch.stack([m[2].weight.t() for m in heads]))  # [4][in 8][out 8]: the CUDA-core kernels (impl 1 / 2)
+    else:
+        buf[OFF["W2P"]:OFF["W2P"] + 256] = _nan()                             # those kernels cannot run this layer: poison, not zeros
+    w2f = torch.zeros(H, H, dtype=torch.float32, device=w1.device)            # block diagonal of the heads, [out][in]
+    for g, m in enumerate(heads):
+        w2f[d * g:d * g + d, d * g:d * g + d] = m[2].weight.detach()
+    _put(buf, OFF["W2F"], w2f)
     _put(buf, OFF["B2"], torch.cat([m[2].bias for m in heads]))
     _put(buf, OFF["LNG"], gcl.layer_norm.weight)
     _put(buf, OFF["LNB"], gcl.layer_norm.bias)
@@ -106,14 +128,17 @@ class PackCache:
         self._index = None      # (device, LongTensor [pack]) into cat([0], params...)
 
     def _make_index(self, params):
+        global _PROBING
         saved = [p.data for p in params]
-        off = 1                                              # element 0 of the gather source is the constant 0
+        off = N_CONST                                        # elements 0, 1 of the gather source are the constants 0, NaN
         try:
+            _PROBING = True
             for p in params:
                 p.data = torch.arange(off, off + p.numel(), dtype=torch.float32, device=p.device).view_as(p)
                 off += p.numel()
             idx = self._build_fn()
         finally:
+            _PROBING = False
             for p, d in zip(params, saved):
                 p.data = d
         if off >= 1 << 24:
@@ -131,7 +156,7 @@ class PackCache:
                 if self._index[1] is None:
                     self._val = self._build_fn()
                 else:
-                    src = torch.cat([torch.zeros(1, dtype=torch.float32, device=dev)] +
+                    src = torch.cat([torch.tensor([0.0, float("nan")], dtype=torch.float32, device=dev)] +
                                     [p.detach().reshape(-1).to(torch.float32) for p in params])
                     self._val = src[self._index[1]]
             self._key = key
@@ -155,14 +180,15 @@ def unpack_layer_grad(gpack, gcl):
                     _g(gpack, OFF["WG"], 12, 32).t()] +
                    ([_g(gpack, OFF["WEA"], 32, 1)] if F_in == 77 else []), dim=1)          # [32, F_in]
     b1 = _g(gpack, OFF["BQ"], 32)
-    w2 = _g(gpack, OFF["W2P"], 4, 8, 8)
+    w2 = _g(gpack, OFF["W2F"], 32, 32)          # full [out][in]; only the heads' diagonal blocks are parameters
     b2 = _g(gpack, OFF["B2"], 32)
+    d = H // len(heads)
     by_param = {}
     for g, m in enumerate(heads):
-        by_param[m[0].weight] = w1[8 * g:8 * g + 8]
-        by_param[m[0].bias] = b1[8 * g:8 * g + 8]
-        by_param[m[2].weight] = w2[g].t()
-        by_param[m[2].bias] = b2[8 * g:8 * g + 8]
+        by_param[m[0].weight] = w1[d * g:d * g + d]
+        by_param[m[0].bias] = b1[d * g:d * g + d]
+        by_param[m[2].weight] = w2[d * g:d * g + d, d * g:d * g + d]
+        by_param[m[2].bias] = b2[d * g:d * g + d]
     by_param[gcl.layer_norm.weight] = _g(gpack, OFF["LNG"], 32)
     by_param[gcl.layer_norm.bias] = _g(gpack, OFF["LNB"], 32)
     by_param[gcl.coord_mlp[0].weight] = _g(gpack, OFF["WC1"], 32, 32)
@@ -213,7 +239,7 @@ class GradUnpacker:
 
 class FlatState:
     """The training step's view of a CrossAttentionPoseRegression: ALL parameters are re-homed as views of one flat fp32
-    buffer (element 0 = a constant zero), the gradients of the live parameters (egnn.* and mlp.*, SURVEY F8: the other
+    buffer (elements 0, 1 = the constants zero and NaN), the gradients of the live parameters (egnn.* and mlp.*, SURVEY F8: the other
     12 tensors never get one and keep grad = None, like in the reference) as views of one flat gradient buffer.
       * every kernel weight pack of the model = ONE gather  pack_buf = flat[pack_index]
       * every parameter gradient            = ONE gather  flat_grad = gpack_buf[unpack_index]   (the packs are a
@@ -231,42 +257,49 @@ class FlatState:
         dev = params[0].device
         n_live = sum(p.numel() for p in live)
         total = sum(p.numel() for p in params)
-        if total + 1 >= 1 << 24:
+        global _PROBING
+        if total + N_CONST >= 1 << 24:
             raise NotImplementedError("element numbers must stay exact in fp32")
-        self.flat = torch.zeros(1 + total, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(N_CONST + total, dtype=torch.float32, device=dev)
+        self.flat[1] = float("nan")
         self.flat_grad = torch.zeros(n_live, dtype=torch.float32, device=dev)
-        off = 1
+        off = N_CONST
         with torch.no_grad():
             for p in params:
                 n = p.numel()
                 self.flat[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat[off:off + n].view_as(p)
                 if id(p) in live_ids:
-                    p.grad = self.flat_grad[off - 1:off - 1 + n].view_as(p)
+                    p.grad = self.flat_grad[off - N_CONST:off - N_CONST + n].view_as(p)
                 off += n
-            # index maps: the pack builders run once on parameters holding their own (1-based) element numbers
+            # index maps: the pack builders run once on parameters holding their own element numbers
             saved = [p.data for p in params]
-            off = 1
+            off = N_CONST
             try:
+                _PROBING = True
                 for p in params:
                     p.data = torch.arange(off, off + p.numel(), dtype=torch.float32, device=dev).view_as(p)
                     off += p.numel()
                 packs = [pack_layer(g) for g in self.layers] + [pack_linear32(egnn.embedding_in), pack_linear32(egnn.embedding_out),
                                                                  pack_head(model.mlp)]
             finally:
+                _PROBING = False
                 for p, d in zip(params, saved):
                     p.data = d
         self.pack_index = torch.cat(packs).round().to(torch.int64)
         sizes = [t.numel() for t in packs]
         self.pack_buf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         self.gpack_buf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        unpack = torch.full((n_live + 1,), -1, dtype=torch.int64, device=dev)
+        # inverse map: parameter element -> the pack position its gradient is read from.  An element that sits in two
+        # places (the second edge Linear: per-head layout AND full matrix) takes the LAST one, the full matrix, which is
+        # where the backward kernel writes.
+        unpack = torch.full((n_live + N_CONST,), -1, dtype=torch.int64, device=dev)
         pos = torch.arange(self.pack_index.numel(), dtype=torch.int64, device=dev)
-        sel = self.pack_index > 0
-        unpack[self.pack_index[sel]] = pos[sel]
-        self.unpack_index = unpack[1:]
-        if int((self.unpack_index < 0).sum()) != 0 or int(self.pack_index.max()) > n_live:
-            raise RuntimeError("weight packs do not cover the live parameters exactly once")
+        sel = self.pack_index >= N_CONST
+        unpack.scatter_reduce_(0, self.pack_index[sel], pos[sel], reduce="amax", include_self=True)
+        self.unpack_index = unpack[N_CONST:]
+        if int((self.unpack_index < 0).sum()) != 0 or int(self.pack_index.max()) >= n_live + N_CONST:
+            raise RuntimeError("weight packs do not cover the live parameters")
         self.n_live = n_live
         self._views(sizes)
         invalidate_packs()

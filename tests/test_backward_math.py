@@ -90,7 +90,15 @@ def test_layer_backward_matches_autograd(golden_dir, harness, layer, dup, per_ed
 
     close(dh_in, h64.grad, "dh")
     close(dx_in, x64.grad, "dx")
-    grads = packing.unpack_layer_grad(torch.from_numpy(gpack), gcl)
+    # the host harness (CUDA-core arithmetic, 4 heads) leaves d W2 in the per-head [head][in][out] region; the kernels of
+    # the product write the full [out][in] matrix, which is what unpack_layer_grad reads
+    gp = torch.from_numpy(gpack)
+    w2p = gp[packing.OFF["W2P"]:packing.OFF["W2P"] + 256].reshape(4, 8, 8)
+    w2f = torch.zeros(32, 32)
+    for hd in range(4):
+        w2f[8 * hd:8 * hd + 8, 8 * hd:8 * hd + 8] = w2p[hd].t()
+    gp[packing.OFF["W2F"]:packing.OFF["W2F"] + 1024] = w2f.reshape(-1)
+    grads = packing.unpack_layer_grad(gp, gcl)
     for (name, _), gk in zip(gcl.named_parameters(), grads):
         close(gk, lsd[p + name].grad, name)
 

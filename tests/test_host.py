@@ -109,9 +109,48 @@ def test_unsupported_configurations_fail_loudly():
     with pytest.raises(NotImplementedError):
         P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=1, tanh=True).packs()
     with pytest.raises(NotImplementedError):
-        P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=1, num_heads=2).packs()
+        P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=1, num_heads=3).packs()        # 32 % 3 != 0
     with pytest.raises(NotImplementedError):
         P.EGNN(33, 64, 33, in_edge_nf=1, device="cpu", n_layers=1).packs()
+    # head counts other than 4 run on the tensor-core kernels only: the CUDA-core impls refuse, and their region is poisoned
+    e2 = P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=1, num_heads=2)
+    with pytest.raises(NotImplementedError):
+        e2.check_impl(1)
+    e2.check_impl(0); e2.check_impl(5)
+    pk = e2.packs()[0][0]
+    assert torch.isnan(pk[packing.OFF["W2P"]:packing.OFF["W2P"] + 256]).all() and not torch.isnan(pk[packing.OFF["W2F"]:]).any()
+
+
+@pytest.mark.parametrize("heads", [1, 2, 4, 8, 16])
+def test_layer_pack_any_head_count(heads):
+    """pack_layer / unpack_layer_grad for every head count dividing 32 (E_GCL(num_heads=...), 3dm:186-207): the second
+    edge Linear travels as one block-diagonal [out][in] matrix; the cached (index-gather) rebuild equals the direct one;
+    the gradient unpack is the inverse permutation on the heads' blocks."""
+    torch.manual_seed(heads)
+    egnn = P.EGNN(32, 32, 32, in_edge_nf=1, device="cpu", n_layers=1, num_heads=heads)
+    gcl = egnn.gcl_0
+    d = 32 // heads
+    pk = packing.pack_layer(gcl)
+    w2f = pk[packing.OFF["W2F"]:packing.OFF["W2F"] + 1024].reshape(32, 32)
+    for g, m in enumerate(gcl.edge_mlps):
+        assert torch.equal(w2f[d * g:d * g + d, d * g:d * g + d], m[2].weight.detach())
+    mask = torch.block_diag(*[torch.ones(d, d)] * heads).bool()
+    assert float(w2f[~mask].abs().max() if (~mask).any() else 0.0) == 0.0
+    cached = gcl.layer_pack()                       # first get(): builds the index map, then gathers
+    with torch.no_grad():
+        gcl.edge_mlps[0][2].weight.mul_(1.5)
+    cached = gcl.layer_pack()                       # second get(): pure gather
+    direct = packing.pack_layer(gcl)
+    assert torch.equal(torch.nan_to_num(cached, nan=-7.0), torch.nan_to_num(direct, nan=-7.0))
+    # gradient direction: a pack-shaped gradient holding its own positions
+    gp = torch.arange(packing.LAYER_PACK, dtype=torch.float32)
+    grads = packing.unpack_layer_grad(gp, gcl)
+    for (name, prm), gk in zip(gcl.named_parameters(), grads):
+        assert gk.shape == prm.shape, name
+    for g, m in enumerate(gcl.edge_mlps):
+        gk = grads[[id(q) for q in gcl.parameters()].index(id(m[2].weight))]
+        want = gp[packing.OFF["W2F"]:packing.OFF["W2F"] + 1024].reshape(32, 32)[d * g:d * g + d, d * g:d * g + d]
+        assert torch.equal(gk, want)
 
 
 def test_no_cpu_fallback():

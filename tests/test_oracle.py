@@ -240,3 +240,22 @@ def test_knn_oracle_duplicate_heavy_properties():
         kth = key[-1]
         others = np.setdiff1d(np.arange(n), row)
         assert all((np.float32(d2[i, j]), j) > kth for j in others), i
+
+
+@pytest.mark.parametrize("heads", [1, 2, 8])
+def test_oracle_other_head_counts_match_reference_golden(golden_dir, heads):
+    """E_GCL(num_heads=h) for h in {1, 2, 8} (3dm:186-207, heads concatenated at :246): the oracle against outputs AND
+    gradients of the reference's own EGNN class built with that head count (tests/golden/make_golden_heads.py;
+    randomly initialised -- the shipped checkpoints have 4 heads)."""
+    g = torch.load(os.path.join(golden_dir, "heads_%d.pt" % heads), weights_only=False, map_location="cpu")
+    assert O.num_heads_of(g["state_dict"]) == heads
+    sd = {k: v.double().requires_grad_(True) for k, v in g["state_dict"].items()}
+    h, x = g["h"].double().requires_grad_(True), g["x"].double().requires_grad_(True)
+    ho, xo = O.egnn_forward(sd, h, x, g["row"], g["col"], g["edge_attr"].double())
+    assert float((ho - g["h_out"].double()).abs().max()) <= 1e-5 * float(g["h_out"].abs().max())
+    assert float((xo - g["x_out"].double()).abs().max()) <= 1e-5
+    ((ho * g["dh"].double()).sum() + (xo * g["dx"].double()).sum()).backward()
+    rel = lambda a, b: float((a - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+    assert rel(h.grad, g["grad_h"]) < 1e-5 and rel(x.grad, g["grad_x"]) < 1e-5
+    for k, gr in g["grads"].items():
+        assert rel(sd[k].grad, gr) < 1e-5, k
