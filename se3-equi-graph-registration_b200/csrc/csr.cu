@@ -14,15 +14,22 @@ namespace egspr {
 
 struct NbrSource {   // edges implied by nbr[cloud][i][s]: row = nbr, col = i, e = i*k+s
     const int32_t *nbr; int n, k;
+    unsigned kmul;       // ceil(2^32 / k) (0 for k = 1): e / k == umulhi(e, kmul) while e * k < 2^32 (the fused kernel: e < 2^16, k <= 64)
+    static constexpr bool kColImplied = true;        // col = e / k is in range by construction
     __device__ __forceinline__ void get(int cloud, int64_t e, int64_t epc, int &r, int &c) const {
         r = nbr[cloud * epc + e]; c = (int)((unsigned)e / (unsigned)k);      // e < n*k < 2^31: 32-bit division
     }
+    __device__ __forceinline__ int row(int cloud, int e, int64_t epc) const { return nbr[cloud * epc + e]; }
+    __device__ __forceinline__ int col_small(int cloud, int e, int64_t epc) const { return kmul ? (int)__umulhi((unsigned)e, kmul) : e; }
 };
 struct EdgeSource {  // edges[cloud][2][E] int64 (torch_cluster / reference layout)
     const int64_t *edges; int n;
+    static constexpr bool kColImplied = false;
     __device__ __forceinline__ void get(int cloud, int64_t e, int64_t epc, int &r, int &c) const {
         r = (int)edges[(cloud * 2 + 0) * epc + e]; c = (int)edges[(cloud * 2 + 1) * epc + e];
     }
+    __device__ __forceinline__ int row(int cloud, int e, int64_t epc) const { return (int)edges[(cloud * 2 + 0) * epc + e]; }
+    __device__ __forceinline__ int col_small(int cloud, int e, int64_t epc) const { return (int)edges[(cloud * 2 + 1) * epc + e]; }
 };
 
 __device__ __forceinline__ bool fix_range(int &v, int n) {
@@ -139,6 +146,10 @@ __global__ void __launch_bounds__(256) csr_emit_kernel(Src src, int n, int64_t e
 // ---- fused build for small clouds: ONE CTA per cloud does count -> scan -> fill -> rank/emit with the
 // degree counters, row offsets and the unsorted edge list all in shared memory (one launch instead of a
 // memset + four kernels, no global atomics).  Same output as the generic path.
+// The unsorted list holds (row << 16 | edge) -- both fit 16 bits at shared-memory sizes -- so the rank pass runs one
+// THREAD per entry (rank = entries of its row's list that sort before it, read from shared memory; equal rows make
+// the packed order the edge order) instead of one warp per row with a shuffle loop, which was 54 % of this kernel's
+// instructions (ncu, profiles/r02r_csr_knn_ncu.txt).
 constexpr int CF_THREADS = 1024;
 constexpr size_t CF_MAX_SMEM = 200 * 1024;
 
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(CF_THREADS) csr_fused_kernel(Src src, int n, i
     extern __shared__ int32_t cf_smem[];
     int32_t *deg = cf_smem;                 // [n]      degree, later the fill cursor
     int32_t *off = deg + n;                 // [n + 1]  exclusive offsets inside the cloud
-    int32_t *tmp = off + n + 1;             // [epc]    edge ids grouped by row, unsorted inside a row
+    int32_t *tmp = off + n + 1;             // [epc]    (row << 16 | edge id) grouped by row, unsorted inside a row
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -159,19 +170,17 @@ __global__ void __launch_bounds__(CF_THREADS) csr_fused_kernel(Src src, int n, i
     if (tid == 0) carry_s = 0;
     __syncthreads();
     for (int e0 = tid; e0 < E; e0 += 8 * CF_THREADS) {        // 8 edges per thread in flight (the loads are independent)
-        int r[8], c[8];
+        int r[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int e = e0 + u * CF_THREADS;
-            r[u] = 0; c[u] = 0;
-            if (e < E) src.get(cloud, e, epc, r[u], c[u]);
+            r[u] = 0;
+            if (e < E) r[u] = src.row(cloud, e, epc);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (e0 + u * CF_THREADS < E) {
-                bool bad = fix_range(r[u], n);
-                bad |= fix_range(c[u], n);
-                if (bad && err_flag) *err_flag = 1;
+                if (fix_range(r[u], n) && err_flag) *err_flag = 1;
                 atomicAdd(&deg[r[u]], 1);
             }
         }
@@ -206,48 +215,41 @@ __global__ void __launch_bounds__(CF_THREADS) csr_fused_kernel(Src src, int n, i
         if (cloud == clouds - 1) csr_ptr[(int64_t)clouds * n] = (int32_t)(clouds * epc);
     }
     for (int e0 = tid; e0 < E; e0 += 8 * CF_THREADS) {
-        int r[8], c[8];
+        int r[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int e = e0 + u * CF_THREADS;
-            r[u] = 0; c[u] = 0;
-            if (e < E) src.get(cloud, e, epc, r[u], c[u]);
+            r[u] = 0;
+            if (e < E) r[u] = src.row(cloud, e, epc);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int e = e0 + u * CF_THREADS;
-            if (e < E) { fix_range(r[u], n); tmp[atomicAdd(&deg[r[u]], 1)] = e; }
+            if (e < E) { fix_range(r[u], n); tmp[atomicAdd(&deg[r[u]], 1)] = (r[u] << 16) | e; }
         }
     }
     __syncthreads();
     const int64_t gbase = (int64_t)cloud * epc;
-    for (int i = warp; i < n; i += CF_THREADS / 32) {          // warp per row: rank restores ascending edge order
-        const int base = off[i], d = off[i + 1] - base;
-        const int32_t g = cloud * n + i;
-        if (d <= 32) {
-            const int e = lane < d ? tmp[base + lane] : 0x7fffffff;
+    for (int p0 = tid; p0 < E; p0 += 4 * CF_THREADS) {        // thread per entry; 4 entries (their column loads) in flight
+        int v[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * CF_THREADS;
+            v[u] = p < E ? tmp[p] : 0;
+            c[u] = src.col_small(cloud, v[u] & 0xffff, epc);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + u * CF_THREADS >= E) continue;
+            const int r = v[u] >> 16, e = v[u] & 0xffff;
+            const int base = off[r], d = off[r + 1] - base;
             int rank = 0;
-            for (int j = 0; j < d; ++j) rank += (__shfl_sync(0xffffffffu, e, j) < e);
-            if (lane < d) {
-                int r, c;
-                src.get(cloud, e, epc, r, c);
-                fix_range(c, n);
-                csr_eid[gbase + base + rank] = e;
-                csr_row[gbase + base + rank] = g;
-                csr_col[gbase + base + rank] = cloud * n + c;
-            }
-        } else {
-            for (int q = lane; q < d; q += 32) {
-                const int e = tmp[base + q];
-                int rank = 0;
-                for (int j = 0; j < d; ++j) rank += (tmp[base + j] < e);
-                int r, c;
-                src.get(cloud, e, epc, r, c);
-                fix_range(c, n);
-                csr_eid[gbase + base + rank] = e;
-                csr_row[gbase + base + rank] = g;
-                csr_col[gbase + base + rank] = cloud * n + c;
-            }
+            for (int j = 0; j < d; ++j) rank += (tmp[base + j] < v[u]);       // same row: packed order == edge order
+            if (!Src::kColImplied) { if (fix_range(c[u], n) && err_flag) *err_flag = 1; }
+            const int64_t o = gbase + base + rank;
+            csr_eid[o] = e;
+            csr_row[o] = cloud * n + r;
+            csr_col[o] = cloud * n + c[u];
         }
     }
 }
@@ -261,7 +263,7 @@ static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, 
     if (ws_bytes < egspr_csr_workspace_bytes(G, E)) return EGSPR_E_WORKSPACE;
     {   // small clouds, enough of them to fill the GPU: fused single-launch build in shared memory
         const size_t smem = sizeof(int32_t) * (size_t)(2 * (int64_t)n + 1 + epc);
-        if (smem <= CF_MAX_SMEM && clouds >= 16) {
+        if (smem <= CF_MAX_SMEM && clouds >= 16 && epc <= 65536 && n <= 32768) {      // (row << 16 | edge) must fit an int32
             if (!opt_in_smem(csr_fused_kernel<Src>, CF_MAX_SMEM)) return EGSPR_E_LAUNCH;
             csr_fused_kernel<Src><<<clouds, CF_THREADS, smem, st>>>(src, n, epc, clouds, csr_ptr, csr_row, csr_col, csr_eid, err_flag);
             EGSPR_CHECK_LAUNCH();
@@ -326,7 +328,7 @@ extern "C" int egspr_csr_from_nbr(const int32_t *nbr, int clouds, int n, int k, 
     using namespace egspr;
     if (!nbr || !csr_ptr || !csr_row || !csr_col || !csr_eid || !workspace || clouds <= 0 || n <= 0 || k <= 0)
         return EGSPR_E_INVALID;
-    NbrSource src{nbr, n, k};
+    NbrSource src{nbr, n, k, k > 1 ? (unsigned)((0x100000000ull + (unsigned)k - 1) / (unsigned)k) : 0u};
     return csr_build(src, clouds, n, (int64_t)n * k, csr_ptr, csr_row, csr_col, csr_eid, workspace,
                      workspace_bytes, err_flag, (cudaStream_t)stream);
 }
