@@ -355,7 +355,10 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
             if (s < nseg) {
                 int dz, dy, x0, x1;
                 if (L == l0) {
-                    dz = s / w0 - l0; dy = s % w0 - l0; x0 = cx - l0; x1 = cx + l0;
+                    // l0 = 1: the query's own cell row first, then the four face rows, then the corner rows -- the k-th best
+                    // falls fastest, so later batches bring fewer candidates that still pass it
+                    const int so = (l0 == 1) ? (int)((0x862075314ull >> (4 * s)) & 15ull) : s;
+                    dz = so / w0 - l0; dy = so % w0 - l0; x0 = cx - l0; x1 = cx + l0;
                 } else if (s < 8 * L) {
                     x0 = cx - L; x1 = cx + L;
                     if (s < 2 * L + 1) { dz = -L; dy = s - L; }
@@ -368,6 +371,22 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
                 }
                 const int z = cz + dz, y = cy + dy;
                 x0 = max(x0, 0); x1 = min(x1, nx - 1);
+                if (L > l0 && thr_i >= 0) {
+                    // shells: with the list full, a cell row whose nearest point is farther than the k-th best cannot
+                    // contribute (the selection is a total order, so skipping candidates that lose anyway changes
+                    // nothing); the x range shrinks to the cells the ball of radius sqrt(thr) reaches.  Conservative by
+                    // the grid's rounding slack and 1e-4 relative, so ties at the threshold are still visited.
+                    float gy = dy > 0 ? (gp.mn[1] + (float)y * gp.cs[1]) - q.y : (dy < 0 ? q.y - (gp.mn[1] + (float)(y + 1) * gp.cs[1]) : 0.f);
+                    float gz = dz > 0 ? (gp.mn[2] + (float)z * gp.cs[2]) - q.z : (dz < 0 ? q.z - (gp.mn[2] + (float)(z + 1) * gp.cs[2]) : 0.f);
+                    gy = fmaxf(gy - gp.slack, 0.f) * 0.9999f; gz = fmaxf(gz - gp.slack, 0.f) * 0.9999f;
+                    const float rem = thr_d * 1.0001f - (gy * gy + gz * gz);
+                    if (rem < 0.f) x1 = x0 - 1;
+                    else {
+                        const float rx = sqrtf(rem) * 1.0001f + gp.slack;
+                        x0 = max(x0, (int)fmaxf((q.x - rx - gp.mn[0]) * gp.inv[0], 0.f));
+                        x1 = min(x1, (int)fminf(fmaxf((q.x + rx - gp.mn[0]) * gp.inv[0], -1.f), 1e6f));
+                    }
+                }
                 if (z >= 0 && z < nz && y >= 0 && y < ny && x0 <= x1) {
                     const int rowbase = (z * ny + y) * nx;
                     start = __ldg(cs + rowbase + x0);
