@@ -282,12 +282,12 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
             int q = lo;
             for (; q + 4 <= hi; q += 4) {                             // strictly sequential edge order
                 const float4 d0 = dx_t[q], d1 = dx_t[q + 1], d2 = dx_t[q + 2], d3 = dx_t[q + 3];
-                s1.x += d0.x; s1.y += d0.y; s1.z += d0.z;
-                s1.x += d1.x; s1.y += d1.y; s1.z += d1.z;
-                s1.x += d2.x; s1.y += d2.y; s1.z += d2.z;
-                s1.x += d3.x; s1.y += d3.y; s1.z += d3.z;
+                fadd2(s1.x, s1.y, d0.x, d0.y); s1.z += d0.z;
+                fadd2(s1.x, s1.y, d1.x, d1.y); s1.z += d1.z;
+                fadd2(s1.x, s1.y, d2.x, d2.y); s1.z += d2.z;
+                fadd2(s1.x, s1.y, d3.x, d3.y); s1.z += d3.z;
             }
-            for (; q < hi; ++q) { const float4 d0 = dx_t[q]; s1.x += d0.x; s1.y += d0.y; s1.z += d0.z; }
+            for (; q < hi; ++q) { const float4 d0 = dx_t[q]; fadd2(s1.x, s1.y, d0.x, d0.y); s1.z += d0.z; }
             if (b1 <= tend_) {
                 const float4 xv = make_float4(x_old.x + s1.x, x_old.y + s1.y, x_old.z + s1.z, 0.f);   // coord + agg  :267
                 *reinterpret_cast<float4 *>(a.x4_out + (int64_t)n * 4) = xv;
@@ -547,14 +547,15 @@ __global__ void __launch_bounds__(V_THREADS, 1) egcl_edge_ts_kernel(const LayerA
                     const float4 m1 = *reinterpret_cast<const float4 *>(mt + (q + 1) * V_MROW + fq);
                     const float4 m2 = *reinterpret_cast<const float4 *>(mt + (q + 2) * V_MROW + fq);
                     const float4 m3 = *reinterpret_cast<const float4 *>(mt + (q + 3) * V_MROW + fq);
-                    s0.x += m0.x; s0.y += m0.y; s0.z += m0.z; s0.w += m0.w;
-                    s0.x += m1.x; s0.y += m1.y; s0.z += m1.z; s0.w += m1.w;
-                    s0.x += m2.x; s0.y += m2.y; s0.z += m2.z; s0.w += m2.w;
-                    s0.x += m3.x; s0.y += m3.y; s0.z += m3.z; s0.w += m3.w;
+                    // packed adds (FADD2 = two independent IEEE additions: same bits as four scalar ones, half the issue slots)
+                    fadd2(s0.x, s0.y, m0.x, m0.y); fadd2(s0.z, s0.w, m0.z, m0.w);
+                    fadd2(s0.x, s0.y, m1.x, m1.y); fadd2(s0.z, s0.w, m1.z, m1.w);
+                    fadd2(s0.x, s0.y, m2.x, m2.y); fadd2(s0.z, s0.w, m2.z, m2.w);
+                    fadd2(s0.x, s0.y, m3.x, m3.y); fadd2(s0.z, s0.w, m3.z, m3.w);
                 }
                 for (; q < hi; ++q) {
                     const float4 m0 = *reinterpret_cast<const float4 *>(mt + q * V_MROW + fq);
-                    s0.x += m0.x; s0.y += m0.y; s0.z += m0.z; s0.w += m0.w;
+                    fadd2(s0.x, s0.y, m0.x, m0.y); fadd2(s0.z, s0.w, m0.z, m0.w);
                 }
                 if (b1 <= tend) *reinterpret_cast<float4 *>(agg_out + (int64_t)n * H + fq) = s0;      // row complete: out it goes
                 else *reinterpret_cast<float4 *>(carry + (par ^ 1) * 36 + fq) = s0;

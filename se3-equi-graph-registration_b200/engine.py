@@ -245,6 +245,7 @@ class PipelinedEngine:
         self.device = self.engines[0].device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
         self._count = 0
+        self.active_lanes = len(self.engines)      # batches rotate over the first `active_lanes` lanes
 
     @property
     def impl(self):
@@ -260,7 +261,7 @@ class PipelinedEngine:
         return self.engines[0].launches_per_step
 
     def _next(self):
-        lane = self._count % len(self.engines)
+        lane = self._count % max(1, min(int(self.active_lanes), len(self.engines)))
         self._count += 1
         return lane
 
