@@ -52,40 +52,72 @@ __global__ void csr_count_kernel(Src src, int n, int64_t epc, int32_t *__restric
     }
 }
 
-// one CTA per cloud: ptr[cloud*n+i] = cloud*epc + exclusive_scan(deg); deg is reset to 0 (it
-// becomes the fill cursor)
-__global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t *__restrict__ deg, int n, int64_t epc,
-                                                        int32_t *__restrict__ ptr, int clouds) {
+// ptr = exclusive scan of the degrees over ALL nodes of the batch (every cloud's degrees sum to epc, so this equals
+// cloud*epc + the scan inside the cloud); deg is reset to 0 (it becomes the fill cursor).  Two launches over chunks of
+// 4096 nodes, any number of CTAs: a CTA per cloud serialised a 131072-node cloud on one SM (118 us of the 237 us build).
+constexpr int SC_CHUNK = 4096;
+__global__ void __launch_bounds__(1024) csr_chunk_sum_kernel(const int32_t *__restrict__ deg, int64_t G, int32_t *__restrict__ chunk_sums) {
     __shared__ int warp_tot[32];
-    __shared__ int carry_s;
-    const int cloud = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * SC_CHUNK;
+    int v = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int64_t i = base + u * 1024 + threadIdx.x; if (i < G) v += deg[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) warp_tot[warp] = v;
     __syncthreads();
-    int32_t *d = deg + (int64_t)cloud * n;
-    int32_t *p = ptr + (int64_t)cloud * n;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < n ? d[i] : 0;
-        int s = v;
+    if (warp == 0) {
+        int t = warp_tot[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-        if (lane == 31) warp_tot[warp] = s;
-        __syncthreads();
-        if (warp == 0) {
-            int t = warp_tot[lane], u = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += w; }
-            warp_tot[lane] = u - t;   // exclusive warp offsets
-        }
-        __syncthreads();
-        const int carry = carry_s;
-        const int excl = carry + warp_tot[warp] + s - v;
-        if (i < n) { p[i] = (int32_t)(cloud * epc) + excl; d[i] = 0; }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl + v;
-        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) chunk_sums[blockIdx.x] = t;
     }
-    if (cloud == clouds - 1 && threadIdx.x == 0) ptr[(int64_t)clouds * n] = (int32_t)(clouds * epc);
+}
+__global__ void __launch_bounds__(1024) csr_scan_apply_kernel(int32_t *__restrict__ deg, int64_t G, const int32_t *__restrict__ chunk_sums,
+                                                              int32_t *__restrict__ ptr, int32_t total_edges) {
+    __shared__ int warp_tot[32];
+    __shared__ int prefix_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int pre = 0;                                             // sum of the chunks before this one
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += 1024) pre += chunk_sums[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    if (lane == 0) warp_tot[warp] = pre;
+    __syncthreads();
+    if (warp == 0) {
+        int t = warp_tot[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) prefix_s = t;
+    }
+    __syncthreads();
+    // this thread's four CONSECUTIVE nodes
+    const int64_t i0 = (int64_t)blockIdx.x * SC_CHUNK + 4 * threadIdx.x;
+    int d[4], s = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { d[u] = (i0 + u < G) ? deg[i0 + u] : 0; s += d[u]; }
+    int sc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+    __syncthreads();                                         // warp_tot is reused
+    if (lane == 31) warp_tot[warp] = sc;
+    __syncthreads();
+    if (warp == 0) {
+        const int t = warp_tot[lane];
+        int u = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int w = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += w; }
+        warp_tot[lane] = u - t;
+    }
+    __syncthreads();
+    int excl = prefix_s + warp_tot[warp] + sc - s;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (i0 + u < G) { ptr[i0 + u] = excl; deg[i0 + u] = 0; }
+        excl += d[u];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) ptr[G] = total_edges;
 }
 
 template <class Src>
@@ -102,44 +134,28 @@ __global__ void csr_fill_kernel(Src src, int n, int64_t epc, int32_t *__restrict
     }
 }
 
-// warp per node: rank the row's edge ids (restores ascending edge order) and emit the sorted lists
+// thread per list entry: rank = entries of the same row's (unsorted) list with a smaller edge id -- restores ascending
+// edge order -- then emit.  (A warp per row with a shuffle loop spent most of its instructions on half-empty warps.)
 template <class Src>
-__global__ void __launch_bounds__(256) csr_emit_kernel(Src src, int n, int64_t epc, int64_t num_nodes,
+__global__ void __launch_bounds__(256) csr_emit_kernel(Src src, int n, int64_t epc, int64_t num_edges,
                                                        const int32_t *__restrict__ ptr,
                                                        const int32_t *__restrict__ tmp,
                                                        int32_t *__restrict__ csr_row,
                                                        int32_t *__restrict__ csr_col,
                                                        int32_t *__restrict__ csr_eid) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t g = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); g < num_nodes; g += warps) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < num_edges; p += (int64_t)gridDim.x * blockDim.x) {
+        const int cloud = (int)((unsigned)p / (unsigned)epc);                 // num_edges < 2^31 (checked by the caller)
+        const int e = tmp[p];
+        int r, c;
+        src.get(cloud, e, epc, r, c);
+        fix_range(r, n); fix_range(c, n);
+        const int32_t g = cloud * n + r;
         const int base = ptr[g], deg = ptr[g + 1] - base;
-        const int cloud = (int)(g / n);
-        if (deg <= 32) {
-            const int e = lane < deg ? tmp[base + lane] : 0x7fffffff;
-            int rank = 0;
-            for (int j = 0; j < deg; ++j) rank += (__shfl_sync(0xffffffffu, e, j) < e);
-            if (lane < deg) {
-                int r, c;
-                src.get(cloud, e, epc, r, c);
-                fix_range(c, n);
-                csr_eid[base + rank] = e;
-                csr_row[base + rank] = (int32_t)g;
-                csr_col[base + rank] = cloud * n + c;
-            }
-        } else {
-            for (int i = lane; i < deg; i += 32) {
-                const int e = tmp[base + i];
-                int rank = 0;
-                for (int j = 0; j < deg; ++j) rank += (tmp[base + j] < e);
-                int r, c;
-                src.get(cloud, e, epc, r, c);
-                fix_range(c, n);
-                csr_eid[base + rank] = e;
-                csr_row[base + rank] = (int32_t)g;
-                csr_col[base + rank] = cloud * n + c;
-            }
-        }
+        int rank = 0;
+        for (int j = 0; j < deg; ++j) rank += (__ldg(tmp + base + j) < e);
+        csr_eid[base + rank] = e;
+        csr_row[base + rank] = g;
+        csr_col[base + rank] = cloud * n + c;
     }
 }
 
@@ -278,11 +294,17 @@ static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, 
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, clouds);
     csr_count_kernel<<<grid, 256, 0, st>>>(src, n, epc, deg, err_flag);
-    csr_scan_kernel<<<clouds, 1024, 0, st>>>(deg, n, epc, csr_ptr, clouds);
+    {
+        const unsigned chunks = (unsigned)((G + SC_CHUNK - 1) / SC_CHUNK);
+        int32_t *chunk_sums = tmp;                 // tmp is written by the fill kernel, after the scan
+        if ((int64_t)chunks > E + 32) return EGSPR_E_WORKSPACE;
+        csr_chunk_sum_kernel<<<chunks, 1024, 0, st>>>(deg, G, chunk_sums);
+        csr_scan_apply_kernel<<<chunks, 1024, 0, st>>>(deg, G, chunk_sums, csr_ptr, (int32_t)E);
+    }
     csr_fill_kernel<<<grid, 256, 0, st>>>(src, n, epc, deg, csr_ptr, tmp);
-    int64_t gw = (G + 7) / 8;
+    int64_t gw = (E + 255) / 256;
     if (gw > 148 * 32) gw = 148 * 32;
-    csr_emit_kernel<<<(unsigned)gw, 256, 0, st>>>(src, n, epc, G, csr_ptr, tmp, csr_row, csr_col, csr_eid);
+    csr_emit_kernel<<<(unsigned)gw, 256, 0, st>>>(src, n, epc, E, csr_ptr, tmp, csr_row, csr_col, csr_eid);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
