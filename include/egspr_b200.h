@@ -235,6 +235,8 @@ int egspr_head_train_backward(const float *h_out_src, const float *h_out_tgt, co
  *   bce     [pairs]         sum over the pair's rows of BCEWithLogits(score, labels[top_idx]) (3dm:772),
  *   raw     [pairs][n]      <feat_src, feat_tgt> (3dm:773),
  *   stats   [pairs][4]      fp64 sums of sim, sim^2, raw, raw^2 (the z-scores of 3dm:776-777 use batch-wide statistics).
+ *   sim may be NULL: the kernel then recomputes <h_out_src, h_out_tgt> itself (bit-identical to egspr_head_train's sim_out)
+ *   and does not depend on egspr_head_train, so the two one-CTA-per-pair launches can run on two streams.
  * egspr_train_loss_finalize, one CTA: loss[0..4] = corr_loss (mean BCE), sim_loss = MSE(zscore(sim), zscore(raw))
  * (unbiased std, +1e-6), mean rot_loss, mean trans_loss (pose_loss 3dm:896-962; 0 when R is null), and their sum =
  * the loop's total (3dm:1118); loss[7] = scale.  Optional seeds of the backward pass, all multiplied by `scale` (the

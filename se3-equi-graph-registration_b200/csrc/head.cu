@@ -864,7 +864,7 @@ __device__ __forceinline__ float acos_slope(float c) {
 struct TrainLossArgs {
     const float *h_out_src, *h_out_tgt, *feat_src, *feat_tgt, *sim, *labels, *head_pack;
     int n, k;
-    int32_t *top_idx;       // [pairs][k]: members of the top-k set (unordered; -1 past min(k, n))
+    int32_t *top_idx;       // [pairs][k]: members of the top-k set in ascending point order (-1 past min(k, n))
     float *scores;          // [pairs][k]: mlp logits of those rows
     float *raw;             // [pairs][n]: input-feature similarity
     double *stats;          // [pairs][4]: sum sim, sum sim^2, sum raw, sum raw^2
@@ -875,17 +875,17 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) train_loss_forward_kernel(cons
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     __shared__ double dred[HD_WARPS][4];
-    __shared__ int s_count;
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const size_t nb = (size_t)b * n;
     float *ssim = dyn;                       // [n]
     int *slist = reinterpret_cast<int *>(dyn + n);      // [k]
     float *swp = dyn + n + a.k;              // [HEAD_PACK]
     for (int i = tid; i < HEAD_PACK; i += blockDim.x) swp[i] = __ldg(a.head_pack + i);
-    if (tid == 0) s_count = 0;
     double acc[4] = {0, 0, 0, 0};
     for (int i = tid; i < n; i += blockDim.x) {
-        const float s = __ldg(a.sim + nb + i);
+        // sim = <h_out_src, h_out_tgt> (3dm:681): read from egspr_head_train's output, or recomputed (same dot32, same bits)
+        // so that this kernel does not depend on that one and the two narrow launches can run side by side
+        const float s = a.sim ? __ldg(a.sim + nb + i) : dot32(a.h_out_src + (nb + i) * H, a.h_out_tgt + (nb + i) * H);
         ssim[i] = s;
         const float r = dot32(a.feat_src + (nb + i) * H, a.feat_tgt + (nb + i) * H);     // 3dm:773
         a.raw[nb + i] = r;
@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) train_loss_forward_kernel(cons
         prefix |= sc.u[1] << shift; pmask |= 0xffu << shift; want = (int)sc.u[2];
     }
     const unsigned kth_key = prefix;
-    unsigned eq_carry = 0;
+    unsigned eq_carry = 0, sel_carry = 0;
     for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + tid;
         unsigned key = 0;
@@ -954,7 +954,17 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) train_loss_forward_kernel(cons
         for (int w = 0; w < nwarps; ++w) { const unsigned c = sc.hist[w]; if (w < warp) before += c; total += c; }
         before += __popc(bal & ((1u << lane) - 1u));
         eq_carry += total;
-        if ((i < n) && (key > kth_key || (is_eq && (int)before < want))) slist[atomicAdd(&s_count, 1)] = i;
+        // members of the set go to the list in INDEX order (block-wide prefix of the selection flags, not an atomic
+        // cursor): the BCE sum below then adds the same rows in the same order on every run -- bit-reproducible loss
+        const bool sel = (i < n) && (key > kth_key || (is_eq && (int)before < want));
+        const unsigned sbal = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) sc.hist[32 + warp] = __popc(sbal);
+        __syncthreads();
+        unsigned sbefore = sel_carry, stotal = 0;
+        for (int w = 0; w < nwarps; ++w) { const unsigned c = sc.hist[32 + w]; if (w < warp) sbefore += c; stotal += c; }
+        sbefore += __popc(sbal & ((1u << lane) - 1u));
+        sel_carry += stotal;
+        if (sel) slist[sbefore] = i;
     }
     __syncthreads();
     float bsum[1] = {0.f};
@@ -1248,7 +1258,7 @@ extern "C" int egspr_train_loss_forward(const float *h_out_src, const float *h_o
                                         int pairs, int n, int top_k, int32_t *top_idx, float *scores, float *raw,
                                         double *stats, float *bce, void *stream) {
     using namespace egspr;
-    if (!h_out_src || !h_out_tgt || !feat_src || !feat_tgt || !sim || !labels || !head_pack || !top_idx || !scores || !raw ||
+    if (!h_out_src || !h_out_tgt || !feat_src || !feat_tgt || !labels || !head_pack || !top_idx || !scores || !raw ||
         !stats || !bce || pairs <= 0 || n <= 0 || top_k <= 0)
         return EGSPR_E_INVALID;
     const size_t smem = sizeof(float) * ((size_t)n + top_k + HEAD_PACK);

@@ -466,20 +466,25 @@ def pose_loss(R, t, gt_pose, need_grad=True):
 # ---------------------------------------------------------------------------------------------------------------
 # training losses on the device
 # ---------------------------------------------------------------------------------------------------------------
-def train_loss_forward(h_out_src, h_out_tgt, feat_src, feat_tgt, sim, labels, head_pack, top_k=128):
-    """3dm:681-694, 760-773 for a batch -> top_idx [B,k] i32 (unordered top-k set of sim), scores [B,k] (mlp logits),
-    raw [B,n] (input-feature similarity), stats [B,4] f64, bce [B] (per-pair BCE sums)."""
+def train_loss_outputs(B, n, top_k, dev):
+    """Output buffers of train_loss_forward (allocate them on the consumer's stream when the kernel runs on another one)."""
+    return (torch.empty((B, top_k), dtype=torch.int32, device=dev), torch.empty((B, top_k), dtype=torch.float32, device=dev),
+            torch.empty((B, n), dtype=torch.float32, device=dev), torch.empty((B, 4), dtype=torch.float64, device=dev),
+            torch.empty(B, dtype=torch.float32, device=dev))
+
+
+def train_loss_forward(h_out_src, h_out_tgt, feat_src, feat_tgt, sim, labels, head_pack, top_k=128, outs=None):
+    """3dm:681-694, 760-773 for a batch -> top_idx [B,k] i32 (the top-k set of sim, in ascending point order), scores [B,k] (mlp logits),
+    raw [B,n] (input-feature similarity), stats [B,4] f64, bce [B] (per-pair BCE sums).  sim = head_train's similarity
+    output, or None: the kernel recomputes it (same bits) and is then independent of head_train."""
     ts = [_req(v, nm, torch.float32, 3) for v, nm in ((h_out_src, "h_out_src"), (h_out_tgt, "h_out_tgt"),
                                                       (feat_src, "feat_src"), (feat_tgt, "feat_tgt"))]
-    sim = _req(sim, "sim", torch.float32, 2)
+    if sim is not None:
+        sim = _req(sim, "sim", torch.float32, 2)
     labels = _req(labels.to(torch.float32), "labels", torch.float32, 2)
     B, n, _ = ts[0].shape
-    dev = sim.device
-    top_idx = torch.empty((B, top_k), dtype=torch.int32, device=dev)
-    scores = torch.empty((B, top_k), dtype=torch.float32, device=dev)
-    raw = torch.empty((B, n), dtype=torch.float32, device=dev)
-    stats = torch.empty((B, 4), dtype=torch.float64, device=dev)
-    bce = torch.empty(B, dtype=torch.float32, device=dev)
+    dev = ts[0].device
+    top_idx, scores, raw, stats, bce = outs if outs is not None else train_loss_outputs(B, n, top_k, dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().egspr_train_loss_forward(*[_ptr(v) for v in ts], _ptr(sim), _ptr(labels), _ptr(head_pack), B, n,
                                                        int(top_k), _ptr(top_idx), _ptr(scores), _ptr(raw), _ptr(stats), _ptr(bce),

@@ -89,6 +89,7 @@ class GraphedTrainStep:
         self.labels_f = labels.to(torch.float32).reshape(B, self.N).clone()
         self.gt_pose = gt.to(torch.float32).clone()
         self.top_k = int(model.top_k)
+        self._side = None
         # optimizer state before the warm-up (None = not created yet)
         saved_state = {id(p): {n: (v.clone() if torch.is_tensor(v) else v) for n, v in st.items()} for p, st in self.opt.state.items()}
         saved_flat = self.state.flat.clone()
@@ -117,9 +118,18 @@ class GraphedTrainStep:
         graph = ops.with_csc(ops.csr_from_nbr(ops.knn_build(self.x_all, self.k)))
         h, x, saved = ops.egnn_forward_saved(self.feat_all, self.x_all, graph, st.layer_packs, st.pack_in, st.pack_out)
         hs, ht, xs, xt = h[:B], h[B:], x[:B], x[B:]
+        # the two one-CTA-per-pair kernels side by side (16 + 16 CTAs on 148 SMs): the loss kernel recomputes the
+        # similarity instead of reading head_train's, so it only depends on the EGNN outputs
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        louts = ops.train_loss_outputs(B, self.N, self.top_k, dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            top_idx, _, raw, stats, bce = ops.train_loss_forward(hs, ht, self.feat_all[:B], self.feat_all[B:], None, self.labels_f,
+                                                                 st.pack_head, self.top_k, outs=louts)
         R, t, _, sim, _, _ = ops.head_train(hs, ht, xs, xt, self.labels_f, self.gt_pose)
-        top_idx, _, raw, stats, bce = ops.train_loss_forward(hs, ht, self.feat_all[:B], self.feat_all[B:], sim, self.labels_f,
-                                                             st.pack_head, self.top_k)
+        cur.wait_stream(self._side)
         # total = corr + sim + mean rot + mean trans (3dm:1118); the seeds carry 1 / world so that the SUM all-reduce
         # below yields the mean gradient
         loss, dsim, dR, dt = ops.train_loss_finalize(sim, raw, stats, bce, self.top_k, R, t, self.gt_pose, scale=1.0 / self.world)

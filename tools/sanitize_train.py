@@ -24,7 +24,7 @@ m2 = mk(); o2 = torch.optim.Adam(m2.parameters(), lr=1e-4)
 step = P.train.GraphedTrainStep.__new__(P.train.GraphedTrainStep)
 sf, sp, tf, tp, corr, labels, gt = batches[0]
 step.model, step.opt, step.k, step.group, step.world, step.B, step.N, step.top_k = m2, o2, 16, None, 1, 2, N, 128
-step.state = packing.FlatState(m2)
+step.state = packing.FlatState(m2); step._side = None
 step.feat_all = torch.cat([sf, tf]).contiguous(); step.x_all = torch.cat([sp, tp]).contiguous()
 step.labels_f = labels.float().reshape(2, N).contiguous(); step.gt_pose = gt.float().contiguous()
 for i in range(2):
