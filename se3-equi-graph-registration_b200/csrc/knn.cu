@@ -336,12 +336,15 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     const int cx = min(nx - 1, max(0, (int)((q.x - gp.mn[0]) * gp.inv[0])));
     const int cy = min(ny - 1, max(0, (int)((q.y - gp.mn[1]) * gp.inv[1])));
     const int cz = min(nz - 1, max(0, (int)((q.z - gp.mn[2]) * gp.inv[2])));
-    float bd[E];
-    int bi[E];
+    // list entries and candidates as ONE 64-bit key (bits of d2 << 32 | index): d2 >= +0, so the unsigned order of the keys
+    // is the total order (d2, index) and every compare / select of the networks below is a 64-bit integer one.  An empty
+    // slot is (1e10, 0): no candidate with d2 >= 1e10 sorts before it (torch_cluster's best_dist), every other one does.
+    typedef unsigned long long u64;
+    constexpr u64 KEY_EMPTY = (u64)0x501502f9u << 32, KEY_NONE = ~0ull;
+    u64 bk[E];
 #pragma unroll
-    for (int j = 0; j < E; ++j) { bd[j] = 1e10f; bi[j] = -1; }
-    float thr_d = 1e10f;
-    int thr_i = -1;
+    for (int j = 0; j < E; ++j) bk[j] = KEY_EMPTY;
+    u64 thr = KEY_EMPTY;                                   // key of the k-th best; < KEY_EMPTY once the list is full
     const int kl = (k - 1) / E, kj = (k - 1) % E;          // lane / slot of the k-th entry
     const int Lmax = max(max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz)), l0);
     bool done = !valid;
@@ -371,7 +374,8 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
                 }
                 const int z = cz + dz, y = cy + dy;
                 x0 = max(x0, 0); x1 = min(x1, nx - 1);
-                if (L > l0 && thr_i >= 0) {
+                if (L > l0 && thr < KEY_EMPTY) {
+                    const float thr_d = __uint_as_float((unsigned)(thr >> 32));
                     // shells: with the list full, a cell row whose nearest point is farther than the k-th best cannot
                     // contribute (the selection is a total order, so skipping candidates that lose anyway changes
                     // nothing); the x range shrinks to the cells the ball of radius sqrt(thr) reaches.  Conservative by
@@ -407,49 +411,43 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
                     if (v <= t) lo += h;
                 }
                 const int sstart = __shfl_sync(FULL, start, lo, W), sbase = __shfl_sync(FULL, excl, lo, W);
-                float d = 3e38f;
-                int idx = 0x7fffffff;
+                u64 ck = KEY_NONE;
                 if (t < T) {
                     const float4 c = __ldg(so + sstart + (t - sbase));
                     const float dx = c.x - q.x, dy2 = c.y - q.y, dz2 = c.z - q.z;
-                    d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
-                    idx = __float_as_int(c.w);
+                    const float d = __fmaf_rn(dz2, dz2, __fmaf_rn(dy2, dy2, __fmul_rn(dx, dx)));
+                    ck = ((u64)__float_as_uint(d) << 32) | (unsigned)__float_as_int(c.w);
                 }
-                unsigned m = (__ballot_sync(FULL, d < thr_d || (d == thr_d && idx < thr_i)) >> sh) & GMASK;
+                unsigned m = (__ballot_sync(FULL, ck < thr) >> sh) & GMASK;
                 if constexpr (E == 1) {
                     // many candidates beat the k-th best (the first batches of a query): sort the batch with a
                     // bitonic network and merge it into the list in one go instead of inserting one by one
                     if (__any_sync(FULL, __popc(m) >= merge_min)) {
-                        float sd = ((m >> sl) & 1u) ? d : 3e38f;          // non-passers cannot enter the list
-                        int si = ((m >> sl) & 1u) ? idx : 0x7fffffff;
+                        u64 sk = ((m >> sl) & 1u) ? ck : KEY_NONE;        // non-passers cannot enter the list
 #pragma unroll
                         for (int size = 2; size <= W; size <<= 1) {
 #pragma unroll
                             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                                const float pd = __shfl_xor_sync(FULL, sd, stride, W);
-                                const int pi = __shfl_xor_sync(FULL, si, stride, W);
-                                const bool plt = pd < sd || (pd == sd && pi < si);           // partner sorts first
+                                const u64 pk = __shfl_xor_sync(FULL, sk, stride, W);
+                                const bool plt = pk < sk;                                     // partner sorts first
                                 const bool up = ((sl & size) == 0);                           // ascending block
                                 const bool lower = ((sl & stride) == 0);
-                                if (plt == (up == lower)) { sd = pd; si = pi; }               // keep min in the lower lane of an ascending pair
+                                if (plt == (up == lower)) sk = pk;                            // keep min in the lower lane of an ascending pair
                             }
                         }
                         // lowest W of (list, batch): elementwise min against the reversed batch is bitonic -> log2(W) merge stages
                         {
-                            const float rd = __shfl_sync(FULL, sd, W - 1 - sl, W);
-                            const int ri = __shfl_sync(FULL, si, W - 1 - sl, W);
-                            if (rd < bd[0] || (rd == bd[0] && ri < bi[0])) { bd[0] = rd; bi[0] = ri; }
+                            const u64 rk = __shfl_sync(FULL, sk, W - 1 - sl, W);
+                            if (rk < bk[0]) bk[0] = rk;
                         }
 #pragma unroll
                         for (int stride = W / 2; stride > 0; stride >>= 1) {
-                            const float pd = __shfl_xor_sync(FULL, bd[0], stride, W);
-                            const int pi = __shfl_xor_sync(FULL, bi[0], stride, W);
-                            const bool plt = pd < bd[0] || (pd == bd[0] && pi < bi[0]);
+                            const u64 pk = __shfl_xor_sync(FULL, bk[0], stride, W);
+                            const bool plt = pk < bk[0];
                             const bool lower = ((sl & stride) == 0);
-                            if (plt == lower) { bd[0] = pd; bi[0] = pi; }
+                            if (plt == lower) bk[0] = pk;
                         }
-                        thr_d = __shfl_sync(FULL, bd[0], k - 1, W);
-                        thr_i = __shfl_sync(FULL, bi[0], k - 1, W);
+                        thr = __shfl_sync(FULL, bk[0], k - 1, W);
                         m = 0;
                     }
                 }
@@ -458,33 +456,29 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
                     const bool act = m != 0;
                     const int src = act ? __ffs(m) - 1 : 0;
                     m &= m - 1;
-                    const float dd = __shfl_sync(FULL, d, src, W);
-                    const int jj = __shfl_sync(FULL, idx, src, W);
-                    const bool ins = act && (dd < thr_d || (dd == thr_d && jj < thr_i));   // thr may have dropped since the ballot
+                    const u64 cand = __shfl_sync(FULL, ck, src, W);
+                    const bool ins = act && cand < thr;                  // thr may have dropped since the ballot
                     // position = number of kept entries that sort before the candidate (empty slots never do)
                     int pos = 0;
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
-                        const bool before = (sl * E + j) < k && bi[j] >= 0 && (bd[j] < dd || (bd[j] == dd && bi[j] < jj));
+                        const bool before = (sl * E + j) < k && bk[j] < cand;
                         pos += __popc((__ballot_sync(FULL, before) >> sh) & GMASK);
                     }
-                    const float ubd = __shfl_up_sync(FULL, bd[E - 1], 1, W);
-                    const int ubi = __shfl_up_sync(FULL, bi[E - 1], 1, W);
+                    const u64 ubk = __shfl_up_sync(FULL, bk[E - 1], 1, W);
                     if (ins) {
 #pragma unroll
                         for (int j = E - 1; j >= 0; --j) {
                             const int p = sl * E + j;
-                            const float pd = (j == 0) ? ubd : bd[j - 1];
-                            const int pi = (j == 0) ? ubi : bi[j - 1];
-                            if (p > pos) { bd[j] = pd; bi[j] = pi; }
-                            else if (p == pos) { bd[j] = dd; bi[j] = jj; }
+                            const u64 pk = (j == 0) ? ubk : bk[j - 1];
+                            if (p > pos) bk[j] = pk;
+                            else if (p == pos) bk[j] = cand;
                         }
                     }
-                    float td = bd[0]; int ti = bi[0];
+                    u64 tk = bk[0];
 #pragma unroll
-                    for (int j = 1; j < E; ++j) if (kj == j) { td = bd[j]; ti = bi[j]; }
-                    thr_d = __shfl_sync(FULL, td, kl, W);
-                    thr_i = __shfl_sync(FULL, ti, kl, W);
+                    for (int j = 1; j < E; ++j) if (kj == j) tk = bk[j];
+                    thr = __shfl_sync(FULL, tk, kl, W);
                 }
             }
         }
@@ -498,13 +492,13 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
             if (cz + L < nz - 1) margin = fminf(margin, (gp.mn[2] + (float)(cz + L + 1) * gp.cs[2]) - q.z);
             const float ms = margin * 0.9999f - gp.slack;
             if (margin > 1e37f || L >= Lmax) done = true;                     // block covers the whole grid
-            else if (thr_i >= 0 && ms > 0.f && thr_d < ms * ms) done = true;  // k-th best strictly inside the block
+            else if (thr < KEY_EMPTY && ms > 0.f && __uint_as_float((unsigned)(thr >> 32)) < ms * ms) done = true;  // k-th best strictly inside the block
         }
     }
     if (valid) {
 #pragma unroll
         for (int j = 0; j < E; ++j)
-            if (sl * E + j < k) nbr[((size_t)cloud * n + qi) * k + sl * E + j] = bi[j];
+            if (sl * E + j < k) nbr[((size_t)cloud * n + qi) * k + sl * E + j] = bk[j] < KEY_EMPTY ? (int)(unsigned)bk[j] : -1;
     }
 }
 
