@@ -317,8 +317,10 @@ constexpr int GQ_WARPS = 8;
 template <int W, int E>
 __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     const float4 *__restrict__ sorted, const int *__restrict__ cell_start, const GridParams *__restrict__ params,
-    int n, int k, int32_t *__restrict__ nbr, int merge_min, int maxc, int l0) {
+    int n, int k, int32_t *__restrict__ nbr, int maxc) {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int l0 = 1;            // radius of the first block of cells          } re-swept on the final kernel: ppc 2,
+    constexpr int merge_min = 5;     // batches with >= 5 passing candidates are bitonic-merged } l0 1, merge_min 3..5 are the optimum
     // E = list entries per lane: the list holds W * E >= k entries
     constexpr int QPW = 32 / W;                    // queries per warp
     constexpr unsigned GMASK = (W == 32) ? 0xffffffffu : ((1u << W) - 1u);
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
     const int w0 = 2 * l0 + 1;         // the first step scans the whole (2 l0 + 1)^3 block (shells 0 .. l0 together)
     for (int L = l0; !__all_sync(FULL, done); ++L) {
         const int w = 2 * L - 1;
+        const unsigned winv = 65536u / (unsigned)w + 1u;      // rr / w == (rr * winv) >> 16 while rr * w < 65536 (L <= 20)
         const int nseg = done ? 0 : ((L == l0) ? w0 * w0 : 8 * L + 2 * w * w);
         for (int s0 = 0; __any_sync(FULL, s0 < nseg); s0 += W) {
             const int s = s0 + sl;
@@ -369,7 +372,8 @@ __global__ void __launch_bounds__(GQ_WARPS * 32) knn_grid_query_sub_kernel(
                     else { const int t = s - 2 * (2 * L + 1); dy = (t >= w) ? L : -L; dz = (t >= w ? t - w : t) - (L - 1); }
                 } else {
                     const int t = s - 8 * L, rr = t >> 1;
-                    dz = rr / w - (L - 1); dy = rr % w - (L - 1);
+                    const int qd = (L <= 20) ? (int)(((unsigned)rr * winv) >> 16) : rr / w;
+                    dz = qd - (L - 1); dy = (rr - qd * w) - (L - 1);
                     x0 = x1 = (t & 1) ? cx + L : cx - L;
                 }
                 const int z = cz + dz, y = cy + dy;
@@ -507,9 +511,7 @@ static void launch_knn_sub(const float4 *sorted, const int *cell_start, const Gr
                            int32_t *nbr, int maxc, cudaStream_t st) {
     constexpr int QPB = GQ_WARPS * (32 / W);
     dim3 grid((n + QPB - 1) / QPB, clouds);
-    constexpr int merge_min = 5;     // batches with >= 5 passing candidates are bitonic-merged (measured optimum)
-    constexpr int l0 = 1;            // radius of the first block of cells
-    knn_grid_query_sub_kernel<W, E><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, merge_min, maxc, l0);
+    knn_grid_query_sub_kernel<W, E><<<grid, GQ_WARPS * 32, 0, st>>>(sorted, cell_start, params, n, k, nbr, maxc);
 }
 
 __global__ void nbr_to_edges_kernel(const int32_t *__restrict__ nbr, int n, int k,
