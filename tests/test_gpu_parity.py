@@ -639,3 +639,45 @@ def test_module_api_rejects_bad_edge_indices_and_loop_false(model):
     assert np.array_equal(e0[0].view(n, 8).cpu().numpy(), want)
     with pytest.raises(NotImplementedError):
         P.unsorted_segment_sum(torch.ones(4, 2, device=DEV, requires_grad=True), torch.tensor([0, 1, 1, 2], device=DEV), 3)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_knn_grid_randomized_shapes_equal_the_scan(seed):
+    """The cell-grid query (shell pruning by the k-th best distance, x-range trimming, 64-bit (d2, index) keys) against the
+    brute-force scan kernel and -- on a subset -- the C oracle: clustered / planar / collinear / duplicate-heavy /
+    lattice (exact ties everywhere) / anisotropic clouds, scales 1e-3 .. 1e4 with offsets, n = 3 .. 9000, k = 1 .. 32.
+    Pruning may only skip candidates that lose anyway: ids must stay bit-identical."""
+    rng = np.random.default_rng(100 + seed)
+    for it in range(24):
+        n = int(rng.choice([3, 17, 100, 333, 1024, 2048, 4096, 9000]))
+        C = int(rng.choice([1, 2, 5]))
+        k = int(rng.choice([1, 4, 8, 16, 16, 24, 32]))
+        kind = rng.choice(["uniform", "cluster", "plane", "line", "dups", "lattice", "shell", "aniso"])
+        pts = rng.random((C, n, 3))
+        if kind == "cluster":
+            centres = rng.random((C, 6, 3))
+            pts = centres[np.arange(C)[:, None], rng.integers(0, 6, (C, n))] + 0.01 * rng.standard_normal((C, n, 3))
+        elif kind == "plane":
+            pts[..., 2] = 0.5
+        elif kind == "line":
+            pts[..., 1:] = 0.25
+        elif kind == "dups":
+            src = rng.integers(0, max(1, n // 7), (C, n))
+            pts = np.take_along_axis(pts, src[..., None].repeat(3, -1), axis=1)
+        elif kind == "lattice":
+            m = int(np.ceil(n ** (1 / 3)))
+            g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n]
+            pts = np.broadcast_to(g, (C, n, 3)).astype(np.float64) / m
+        elif kind == "shell":
+            v = rng.standard_normal((C, n, 3)); pts = v / np.linalg.norm(v, axis=-1, keepdims=True)
+        elif kind == "aniso":
+            pts = pts * np.array([100.0, 100.0, 6.0])
+        scale = float(rng.choice([1e-3, 1.0, 3.0, 100.0, 1e4]))
+        off = float(rng.choice([0.0, -5.0, 1000.0])) * scale
+        xh = (pts * scale + off).astype(np.float32)
+        x = torch.from_numpy(xh).to(DEV).contiguous()
+        a = ops.knn_build(x, k)
+        b = ops.knn_build(x, k, brute_force=True)
+        assert torch.equal(a, b), (kind, n, C, k, scale, off)
+        if n <= 1024:
+            assert np.array_equal(a.cpu().numpy(), knn_oracle.knn(xh, k)), (kind, n, C, k, scale, off)
