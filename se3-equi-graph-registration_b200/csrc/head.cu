@@ -58,39 +58,82 @@ __device__ __forceinline__ float block_max(float v, BlockScratch &sc) {
     return m;
 }
 
+// ---- one sweep of one-sided Jacobi (Hestenes) on the columns of A, accumulating the rotations in V; returns whether any pair
+// was rotated.  t = tan(theta) from the column norms alpha, beta and the inner product gamma without forming zeta:
+//   t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)),  zeta = (beta - alpha) / (2 gamma)   ==   2 gamma sgn(delta) / (|delta| + sqrt(delta^2 + 4 gamma^2))
+// -- one sqrt, one division and one rsqrt per rotation (fp64 sqrt / div are ~100-cycle software sequences, and this loop
+// runs on ONE thread of the CTA: it was most of the head kernels' serial tail).
+template <typename T>
+__device__ __forceinline__ bool jacobi_sweep(T (&A)[3][3], T (&V)[3][3], T tol2) {
+    bool rotated = false;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+        const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
+        T alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { alpha += A[i][p] * A[i][p]; beta += A[i][q] * A[i][q]; gamma += A[i][p] * A[i][q]; }
+        if (gamma * gamma > tol2 * (alpha * beta) && gamma != T(0)) {        // |gamma| > tol sqrt(alpha beta)
+            rotated = true;
+            const T delta = beta - alpha;
+            const T t = (T(2) * gamma * copysign(T(1), delta)) / (fabs(delta) + sqrt(delta * delta + T(4) * gamma * gamma));
+            const T c = rsqrt(T(1) + t * t), s = c * t;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const T ap = A[i][p], aq = A[i][q];
+                A[i][p] = c * ap - s * aq; A[i][q] = s * ap + c * aq;
+                const T vp = V[i][p], vq = V[i][q];
+                V[i][p] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
+            }
+        }
+    }
+    return rotated;
+}
+
 // ---- 3x3 SVD by one-sided Jacobi in fp64, R = V diag(1,1,det) U^T  (3dm:741-751) ---------------
 // Hm = U diag(sg) W^T with sg descending; d = -1 if det(W U^T) < 0 (the reference then flips the smallest-sigma
 // row of Vt).  Returns false for Hm == 0 (any basis; R = I).
 __device__ bool kabsch_svd(const double (&Hm)[3][3], double (&U)[3][3], double (&W)[3][3], double (&sg)[3], double &d) {
     double A[3][3], V[3][3];
+    {   // fp32 sweeps first (MUFU-speed rotations) bring V to ~1e-7 of the answer; V is re-orthonormalised in fp64
+        // (Gram-Schmidt) and the fp64 sweeps below then converge quadratically from there: 1-2 sweeps instead of 4-6.
+        // Scaled by the largest entry so that squares of tiny H (~1e-6 I) stay normal fp32 numbers.
+        double hmax = 0.0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { A[i][j] = Hm[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
-    for (int sweep = 0; sweep < 40; ++sweep) {
-        bool rotated = false;
+            for (int j = 0; j < 3; ++j) hmax = fmax(hmax, fabs(Hm[i][j]));
+        float Af[3][3], Vf[3][3];
+        const double sc = hmax > 0.0 ? 1.0 / hmax : 0.0;
 #pragma unroll
-        for (int pq = 0; pq < 3; ++pq) {
-            const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
-            double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { alpha += A[i][p] * A[i][p]; beta += A[i][q] * A[i][q]; gamma += A[i][p] * A[i][q]; }
-            if (fabs(gamma) > 1e-17 * sqrt(alpha * beta) && gamma != 0.0) {
-                rotated = true;
-                const double zeta = (beta - alpha) / (2.0 * gamma);
-                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+            for (int j = 0; j < 3; ++j) { Af[i][j] = (float)(Hm[i][j] * sc); Vf[i][j] = (i == j) ? 1.f : 0.f; }
+        for (int sweep = 0; sweep < 6; ++sweep)
+            if (!jacobi_sweep<float>(Af, Vf, 1e-12f)) break;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double ap = A[i][p], aq = A[i][q];
-                    A[i][p] = c * ap - s * aq; A[i][q] = s * ap + c * aq;
-                    const double vp = V[i][p], vq = V[i][q];
-                    V[i][p] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
-                }
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) V[i][j] = (double)Vf[i][j];
+        // Gram-Schmidt on the columns of V (they are orthonormal to ~1e-7 already)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int l = 0; l < j; ++l) {
+                const double dot = V[0][j] * V[0][l] + V[1][j] * V[1][l] + V[2][j] * V[2][l];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) V[i][j] -= dot * V[i][l];
             }
+            const double inv = rsqrt(V[0][j] * V[0][j] + V[1][j] * V[1][j] + V[2][j] * V[2][j]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) V[i][j] *= inv;
         }
-        if (!rotated) break;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) A[i][j] = Hm[i][0] * V[0][j] + Hm[i][1] * V[1][j] + Hm[i][2] * V[2][j];      // A = H V
     }
+    for (int sweep = 0; sweep < 40; ++sweep)
+        if (!jacobi_sweep<double>(A, V, 1e-34)) break;
     double sig[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) sig[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
