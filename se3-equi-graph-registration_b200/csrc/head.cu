@@ -1169,7 +1169,7 @@ __global__ void pose_loss_kernel(const float *__restrict__ R, const float *__res
     }
 }
 
-static int head_threads(int n) { return n > HD_BIG_N ? HD_THREADS_BIG : HD_THREADS; }
+static int head_threads(int n) { return n > HD_BIG_N ? HD_THREADS_BIG : (n > 1024 ? 512 : HD_THREADS); }
 
 template <class K>
 static int ensure_smem(K kernel, size_t bytes) {
