@@ -21,6 +21,7 @@ struct NbrSource {   // edges implied by nbr[cloud][i][s]: row = nbr, col = i, e
     }
     __device__ __forceinline__ int row(int cloud, int e, int64_t epc) const { return nbr[cloud * epc + e]; }
     __device__ __forceinline__ int col_small(int cloud, int e, int64_t epc) const { return kmul ? (int)__umulhi((unsigned)e, kmul) : e; }
+    bool kmul_ok(int64_t epc) const { return epc * (int64_t)k < ((int64_t)1 << 32); }      // exactness range of col_small
 };
 struct EdgeSource {  // edges[cloud][2][E] int64 (torch_cluster / reference layout)
     const int64_t *edges; int n;
@@ -270,6 +271,126 @@ __global__ void __launch_bounds__(CF_THREADS) csr_fused_kernel(Src src, int n, i
     }
 }
 
+// ---- mid-size k-NN clouds (their degree counters + edge list do not fit one CTA's shared memory): the same fused build with
+// `split` CTAs per cloud, CTA j owning the rows [j R, (j + 1) R) of the cloud.  Every CTA scans ALL edges of its cloud
+// (the neighbour table is L2-resident; `split` <= 8) and keeps those whose row it owns; the number of edges with a
+// smaller row -- the range's offset in the cloud's lists -- falls out of the same scan, so the CTAs of a cloud never talk
+// to each other.  The unsorted list holds (local row << 18 | edge).  A range whose edges exceed the list's capacity
+// (duplicate-heavy clouds send every edge to a few low-index rows) is done in several rounds of as many whole rows as
+// fit; a k-NN row has at most n <= 16384 entries, which always fits.
+constexpr int CS_ROWS = 2048;                       // rows per CTA
+constexpr int CS_CAP = (int)(CF_MAX_SMEM / 4) - (2 * CS_ROWS + 1);      // list entries per round
+
+__global__ void __launch_bounds__(CF_THREADS) csr_split_kernel(NbrSource src, int n, int64_t epc, int clouds,
+                                                               int32_t *__restrict__ csr_ptr, int32_t *__restrict__ csr_row,
+                                                               int32_t *__restrict__ csr_col, int32_t *__restrict__ csr_eid,
+                                                               int32_t *__restrict__ err_flag) {
+    extern __shared__ int32_t cf_smem[];
+    int32_t *deg = cf_smem;                 // [CS_ROWS]      degree, later the fill cursor
+    int32_t *off = deg + CS_ROWS;           // [CS_ROWS + 1]  exclusive offsets inside the range
+    int32_t *tmp = off + CS_ROWS + 1;       // [CS_CAP]       (local row << 18 | edge id), unsorted inside a row
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s, below_s, round_end_s;
+    const int cloud = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * CS_ROWS, R = min(CS_ROWS, n - r0);
+    const int E = (int)epc;
+    for (int i = tid; i < CS_ROWS; i += CF_THREADS) deg[i] = 0;
+    if (tid == 0) { carry_s = 0; below_s = 0; }
+    __syncthreads();
+    int below = 0;                          // edges of the cloud with row < r0
+    for (int e0 = tid; e0 < E; e0 += 8 * CF_THREADS) {
+        int r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * CF_THREADS;
+            r[u] = e < E ? src.row(cloud, e, epc) : 0x7fffffff;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (e0 + u * CF_THREADS < E) {
+                if (fix_range(r[u], n) && err_flag) *err_flag = 1;
+                below += r[u] < r0;
+                const int l = r[u] - r0;
+                if ((unsigned)l < (unsigned)R) atomicAdd(&deg[l], 1);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0 && below) atomicAdd(&below_s, below);
+    __syncthreads();
+    for (int base = 0; base < CS_ROWS; base += CF_THREADS) {       // exclusive scan of deg -> off; deg becomes the cursor
+        const int i = base + tid;
+        const int v = i < R ? deg[i] : 0;
+        int sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+        if (lane == 31) warp_tot[warp] = sc;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane], u = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, u, o); if (lane >= o) u += w; }
+            warp_tot[lane] = u - t;
+        }
+        __syncthreads();
+        const int excl = carry_s + warp_tot[warp] + sc - v;
+        if (i < R) {
+            off[i] = excl; deg[i] = excl;
+            csr_ptr[(int64_t)cloud * n + r0 + i] = (int32_t)(cloud * epc) + below_s + excl;
+        }
+        __syncthreads();
+        if (tid == CF_THREADS - 1) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        off[R] = carry_s;
+        if (cloud == clouds - 1 && r0 + R == n) csr_ptr[(int64_t)clouds * n] = (int32_t)(clouds * epc);
+    }
+    __syncthreads();
+    const int64_t gbase = (int64_t)cloud * epc + below_s;
+    for (int a = 0; a < R;) {               // rounds of whole rows [a, b) whose lists fit the shared-memory list
+        if (tid == 0) {
+            int lo = a + 1, hi = R;         // largest b with off[b] - off[a] <= CS_CAP (a single row always fits)
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] - off[a] <= CS_CAP) lo = mid; else hi = mid - 1; }
+            round_end_s = lo;
+        }
+        __syncthreads();
+        const int b = round_end_s, oa = off[a], cnt = off[b] - oa;
+        for (int e0 = tid; e0 < E; e0 += 8 * CF_THREADS) {
+            int r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * CF_THREADS;
+                r[u] = e < E ? src.row(cloud, e, epc) : 0x7fffffff;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * CF_THREADS;
+                if (e < E) {
+                    fix_range(r[u], n);
+                    const int l = r[u] - r0;
+                    if (l >= a && l < b) tmp[atomicAdd(&deg[l], 1) - oa] = (l << 18) | e;
+                }
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p < cnt; p += CF_THREADS) {          // thread per entry: rank inside its row's list, emit
+            const int v = tmp[p];
+            const int l = v >> 18, e = v & 0x3ffff;
+            const int base = off[l] - oa, d = off[l + 1] - off[l];
+            int rank = 0;
+            for (int j = 0; j < d; ++j) rank += (tmp[base + j] < v);
+            const int64_t o = gbase + off[l] + rank;
+            csr_eid[o] = e;
+            csr_row[o] = cloud * n + r0 + l;
+            csr_col[o] = cloud * n + src.col_small(cloud, e, epc);
+        }
+        __syncthreads();
+        a = b;
+    }
+}
+
 template <class Src>
 static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, int32_t *csr_row,
                      int32_t *csr_col, int32_t *csr_eid, void *ws, size_t ws_bytes, int32_t *err_flag,
@@ -282,6 +403,16 @@ static int csr_build(Src src, int clouds, int n, int64_t epc, int32_t *csr_ptr, 
         if (smem <= CF_MAX_SMEM && clouds >= 16 && epc <= 65536 && n <= 32768) {      // (row << 16 | edge) must fit an int32
             if (!opt_in_smem(csr_fused_kernel<Src>, CF_MAX_SMEM)) return EGSPR_E_LAUNCH;
             csr_fused_kernel<Src><<<clouds, CF_THREADS, smem, st>>>(src, n, epc, clouds, csr_ptr, csr_row, csr_col, csr_eid, err_flag);
+            EGSPR_CHECK_LAUNCH();
+            return EGSPR_OK;
+        }
+    }
+    if constexpr (Src::kColImplied) {   // k-NN tables of mid-size clouds: split build, `split` CTAs per cloud
+        const int split = (n + CS_ROWS - 1) / CS_ROWS;
+        if (split <= 8 && epc < (1 << 18) && (int64_t)split * clouds >= 16 && src.kmul_ok(epc)) {
+            if (!opt_in_smem(csr_split_kernel, CF_MAX_SMEM)) return EGSPR_E_LAUNCH;
+            csr_split_kernel<<<dim3((unsigned)split, (unsigned)clouds), CF_THREADS, CF_MAX_SMEM, st>>>(src, n, epc, clouds, csr_ptr, csr_row,
+                                                                                                      csr_col, csr_eid, err_flag);
             EGSPR_CHECK_LAUNCH();
             return EGSPR_OK;
         }

@@ -681,3 +681,27 @@ def test_knn_grid_randomized_shapes_equal_the_scan(seed):
         assert torch.equal(a, b), (kind, n, C, k, scale, off)
         if n <= 1024:
             assert np.array_equal(a.cpu().numpy(), knn_oracle.knn(xh, k)), (kind, n, C, k, scale, off)
+
+
+@pytest.mark.parametrize("C,N,k,kind", [(64, 2048, 16, "uniform"), (16, 4096, 16, "uniform"), (16, 4096, 16, "identical"),
+                                        (4, 9000, 16, "dups"), (4, 9000, 8, "uniform"), (2, 16384, 16, "uniform"),
+                                        (16, 16384, 16, "dups"), (2, 20000, 16, "uniform"), (16, 4096, 32, "identical")])
+def test_csr_from_nbr_every_build_path_exact(C, N, k, kind):
+    """The reverse-k-NN lists from a neighbour table on every build path -- one CTA per cloud (<= 2048-point clouds), the
+    split build (`split` CTAs per cloud owning 2048 rows each; all-identical / duplicate-heavy clouds send every edge to a
+    few low-index rows and force its multi-round path), the generic kernels (few or very large clouds) -- against a stable
+    sort of the edge list by row: ptr / row / col / eid bit-exact."""
+    g = torch.Generator().manual_seed(N + k)
+    x = torch.rand(C, N, 3, generator=g)
+    if kind == "identical":
+        x[:] = 0.25
+    elif kind == "dups":
+        src = torch.randint(0, max(1, N // 50), (C, N), generator=g)
+        x = torch.gather(x, 1, src[..., None].expand(-1, -1, 3))
+    nbr = ops.knn_build(x.to(DEV).contiguous(), k)
+    gr = ops.csr_from_nbr(nbr)
+    row = nbr.cpu().long().reshape(C, N * k)
+    col = torch.arange(N).repeat_interleave(k)[None].expand(C, -1)
+    ptr, r, c, e = _csr_reference(row, col, C, N)
+    assert torch.equal(gr.ptr.cpu().long(), ptr) and torch.equal(gr.row.cpu().long(), r)
+    assert torch.equal(gr.col.cpu().long(), c) and torch.equal(gr.eid.cpu().long(), e)
