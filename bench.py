@@ -277,12 +277,13 @@ def run_ours(args, rank, local_rank, world):
     def e2e_loop(n):
         # `lanes` batches in flight: batch i + lanes is submitted as soon as the caller has read batch i's poses on the
         # host, so its upload runs under the kernels of the lanes - 1 batches still in flight
-        tks = [pipe.submit(*[host[i % n_rot][k] for k in keys]) for i in range(min(args.e2e_lanes, n))]
+        depth = args.e2e_depth or args.e2e_lanes
+        tks = [pipe.submit(*[host[i % n_rot][k] for k in keys]) for i in range(min(depth, n))]
         out = None
         for i in range(n):
             out = pipe.collect(tks[i])
-            if i + args.e2e_lanes < n:
-                tks.append(pipe.submit(*[host[(i + args.e2e_lanes) % n_rot][k] for k in keys]))
+            if i + depth < n:
+                tks.append(pipe.submit(*[host[(i + depth) % n_rot][k] for k in keys]))
         return out
 
     pipe.synchronize()
@@ -581,6 +582,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="3dmatch", choices=sorted(WORKLOADS))
     ap.add_argument("--lanes", type=int, default=3, help="batches in flight in the resident-input loop (value)")
+    ap.add_argument("--e2e-depth", type=int, default=0, help="batches submitted ahead in the host-to-host loop (0 = e2e-lanes; up to "
+                    "2 x e2e-lanes: every lane has two input sets, so one batch can be uploaded and queued behind the running one)")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="batches in flight in the host-to-host loop (e2e): with three, the batches "
                     "finish in convoys and their uploads queue up behind each other (measured slower)")
     args = ap.parse_args()
