@@ -2,7 +2,8 @@
 // step, src/3dmatch_train_egnn_with_batch.py:1125, through E_GCL.forward 3dm:280-289 and EGNN.forward 3dm:328-340).
 //
 // Three kernels per layer, deterministic data path (no atomics on activations):
-//   node_mlp_backward_kernel   thread = node: node_model (3dm:252-260) backward -> dh (direct part), dagg
+//   node_mlp_backward_ts_kernel (egnn_node_ts.cu, tcgen05) thread = node: node_model (3dm:252-260) backward -> dh (direct
+//                              part), dagg; its weight-gradient outer products run beside the MMAs
 //   edge_backward_tc_kernel    (egnn_edge_bwd_tc.cu, tcgen05) thread = edge (row-CSR order): recomputes the edge's forward
 //                              from the layer input (nothing per-edge is kept from the forward pass) and pushes
 //                              (dagg[row], dx_out[row]) back to dpre (= dP[row] = dQ[col]) and the two endpoints'
@@ -22,28 +23,6 @@ using namespace bwd;
 constexpr int BT = 128;    // threads per CTA = rows (edges / nodes) per tile
 constexpr int RS = 33;     // stash row stride in floats: odd -> own-row writes and column reads are conflict-free
 
-// acc[q] += sum over the tile's rows of In[e][i] * Out[e][8 ob + q],  i = tid & 31, ob = tid >> 5
-__device__ __forceinline__ void outer8(float (&acc)[8], const float *__restrict__ sIn, const float *__restrict__ sOut) {
-    const int i = threadIdx.x & 31, ob = (threadIdx.x >> 5) * 8;
-#pragma unroll 4
-    for (int e = 0; e < BT; ++e) {
-        const float a = sIn[e * RS + i];
-        const float *o = sOut + e * RS + ob;
-#pragma unroll
-        for (int q = 0; q < 8; q += 2) fma2(acc[q], acc[q + 1], a, a, o[q], o[q + 1]);
-    }
-}
-// in_major: gradient matrix stored [in][out] (transposed packs) else [out][in]
-__device__ __forceinline__ void flush8(const float (&acc)[8], float *__restrict__ gp, bool in_major) {
-    const int i = threadIdx.x & 31, ob = (threadIdx.x >> 5) * 8;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) atomicAdd(gp + (in_major ? 32 * i + ob + q : 32 * (ob + q) + i), acc[q]);
-}
-
-__device__ __forceinline__ void stash_row(float *__restrict__ dst, const float (&v)[32]) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) dst[j] = v[j];
-}
 __device__ __forceinline__ void load_row32g(float (&v)[32], const float *__restrict__ p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -56,89 +35,6 @@ __device__ __forceinline__ void store_row32g(float *__restrict__ p, const float 
     for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4 *>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
-__device__ __forceinline__ void add_row32g(float (&v)[32], const float *__restrict__ p) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 t = ldg4(p + 4 * i);
-        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// node MLP backward
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int NB_W_LO = B_WN1T, NB_W_N = B_BN2 + 32 - B_WN1T;       // pack slice this kernel reads
-constexpr size_t NB_SMEM = sizeof(float) * (NB_W_N + 5 * BT * RS);
-
-__global__ void __launch_bounds__(BT) node_mlp_backward_kernel(const float *__restrict__ h, const float *__restrict__ agg,
-                                                               const float *__restrict__ dh_out, int64_t G,
-                                                               const int32_t *__restrict__ csr_ptr,
-                                                               const float *__restrict__ pack, float *__restrict__ dh_in,
-                                                               float *dagg, float *__restrict__ gpack) {
-    extern __shared__ __align__(16) float smem[];
-    float *sw = smem;                                   // pack[NB_W_LO, +NB_W_N)
-    float *sA = smem + NB_W_N, *sDout = sA + BT * RS, *sH = sDout + BT * RS, *sAgg = sH + BT * RS, *sDz = sAgg + BT * RS;
-    for (int i = threadIdx.x; i < NB_W_N; i += BT) sw[i] = __ldg(pack + NB_W_LO + i);
-    __syncthreads();
-    const float *w = sw - NB_W_LO;
-    float accW2[8] = {0}, accW1h[8] = {0}, accW1a[8] = {0};
-    float colDout = 0.f, colDz = 0.f, colDagg = 0.f;
-    const int64_t tiles = (G + BT - 1) / BT;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t n = tile * BT + threadIdx.x;
-        float *rA = sA + threadIdx.x * RS, *rD = sDout + threadIdx.x * RS, *rH = sH + threadIdx.x * RS,
-              *rG = sAgg + threadIdx.x * RS, *rZ = sDz + threadIdx.x * RS;
-        float dout[32], dz1[32];
-        float deg = 0.f;
-        if (n < G) {
-            deg = (float)(__ldg(csr_ptr + n + 1) - __ldg(csr_ptr + n));
-            {
-                float t[32];
-                load_row32g(t, h + n * H);
-                stash_row(rH, t);
-                load_row32g(t, agg + n * H);
-                stash_row(rG, t);
-            }
-            load_row32g(dout, dh_out + n * H);
-            stash_row(rD, dout);
-            node_backward(w, rH, rG, dout, rD, rA, rZ, dh_in + n * H, dagg + n * H);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dz1[j] = rZ[j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { dout[j] = 0.f; dz1[j] = 0.f; rA[j] = 0.f; rH[j] = 0.f; rG[j] = 0.f; rZ[j] = 0.f; rD[j] = 0.f; }
-        }
-        colDout += warp_colsum32(dout);
-        colDz += warp_colsum32(dz1);
-        {   // d LayerNorm beta, aggregate part: sum_e dagg[row_e] = sum_n deg(n) dagg[n]  (the message m_e enters agg[row_e]
-            // once per edge; the coord-MLP part of dm is added by the edge kernel).  dagg[n] was just written by this thread.
-            float dg[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dg[j] = 0.f;
-            if (n < G) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 t = *reinterpret_cast<const float4 *>(dagg + n * H + 4 * j);
-                    dg[4 * j] = deg * t.x; dg[4 * j + 1] = deg * t.y; dg[4 * j + 2] = deg * t.z; dg[4 * j + 3] = deg * t.w;
-                }
-            }
-            colDagg += warp_colsum32(dg);
-        }
-        __syncthreads();
-        outer8(accW2, sA, sDout);        // dWn2T[i][o] += a[i] dout[o]
-        outer8(accW1h, sH, sDz);         // dWn1T[i][o] += h[i] dz1[o]
-        outer8(accW1a, sAgg, sDz);       // dWn1T[32+i][o] += agg[i] dz1[o]
-        __syncthreads();
-    }
-    flush8(accW2, gpack + B_WN2T, true);
-    flush8(accW1h, gpack + B_WN1T, true);
-    flush8(accW1a, gpack + B_WN1T + 1024, true);
-    const int lane = threadIdx.x & 31;
-    atomicAdd(gpack + B_BN2 + lane, colDout);
-    atomicAdd(gpack + B_BN1 + lane, colDz);
-    atomicAdd(gpack + B_LNB + lane, colDagg);
-}
-
 constexpr int NT = 1024;            // threads of the 8-lanes-per-row kernels
 constexpr int NOS = BT + 4;         // feature-major row stride of their "out" tiles
 
@@ -412,13 +308,10 @@ extern "C" int egspr_egcl_backward(const float *h, const float *x4, const float 
     float *dpre = dagg + (size_t)num_nodes * 32;
     float *dxe = dpre + (size_t)E * 32;
     float *stash = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(dxe + (size_t)E * 8) + 255) & ~(uintptr_t)255);
-    int occ_node = 1, occ_gather = 1;
-    if (int e = prep_kernel(node_mlp_backward_kernel, NB_SMEM, occ_node)) return e;
+    int occ_gather = 1;
     if (int e = prep_kernel(node_gather_backward_kernel, GB_SMEM, occ_gather, GT)) return e;
     const int64_t ntiles = (num_nodes + BT - 1) / BT;
-    node_mlp_backward_kernel<<<grid_for(ntiles, occ_node), BT, NB_SMEM, st>>>(h, agg, dh_out, num_nodes, csr_ptr, layer_pack, dh_in, dagg,
-                                                                              grad_pack);
-    EGSPR_CHECK_LAUNCH();
+    if (int e = launch_node_mlp_backward_ts(h, agg, dh_out, num_nodes, csr_ptr, layer_pack, dh_in, dagg, grad_pack, st)) return e;
     EdgeBwdArgs ea{x4, P, Q, csr_ptr, csr_row, csr_col, csr_eid, edge_attr, edge_attr_const, num_nodes, edges_per_cloud,
                    n_per_cloud, layer_pack, dagg, dx_out, dpre, dxe, grad_pack, stash};
     if (int e = launch_edge_backward_tc(ea, st)) return e;

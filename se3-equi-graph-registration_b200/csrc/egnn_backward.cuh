@@ -21,6 +21,9 @@ struct EdgeBwdArgs {
 
 int launch_edge_backward_tc(const EdgeBwdArgs &a, cudaStream_t st);      // egnn_edge_bwd_tc.cu
 size_t edge_backward_tc_stash_bytes();
+// node_model backward on tcgen05 (egnn_node_ts.cu)
+int launch_node_mlp_backward_ts(const float *h, const float *agg, const float *dh_out, int64_t G, const int32_t *csr_ptr,
+                                const float *pack, float *dh_in, float *dagg, float *gpack, cudaStream_t st);
 
 // sum over the 32 lanes of v[lane'] for every column: returns, in lane L, sum over lanes of v[L]
 __device__ __forceinline__ float warp_colsum32(const float (&v)[32]) {

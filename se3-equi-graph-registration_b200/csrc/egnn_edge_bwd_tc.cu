@@ -717,7 +717,11 @@ __global__ void __launch_bounds__(X_THREADS, 1) edge_backward_tc_kernel(const Ed
     }
     fence_before_sync();
     __syncthreads();
-    for (int i = tid; i < R_N; i += X_THREADS) {
+    // every CTA starts at a different entry: all CTAs reach this loop together, and 148 atomics onto the same address in
+    // the same order serialise in L2
+    const int rot = (int)((blockIdx.x * 211u) % (unsigned)R_N);
+    for (int i0 = tid; i0 < R_N; i0 += X_THREADS) {
+        const int i = (i0 + rot) % R_N;
         float val = 0.f;
 #pragma unroll
         for (int sl = 0; sl < R_SLOTS; ++sl) val += red[sl * R_N + i];
