@@ -1071,12 +1071,13 @@ __global__ void __launch_bounds__(1024) train_loss_finalize_kernel(const float *
     const double var_r = fmax((st[3] - (double)M * mu_r * mu_r) / (double)(M - 1), 0.0);
     const double sd_s = sqrt(var_s), sd_r = sqrt(var_r);
     const double is = 1.0 / (sd_s + 1e-6), ir = 1.0 / (sd_r + 1e-6);                             // 3dm:776-777
+    const double two_over_M = 2.0 / (double)M;      // (an fp64 division per element in each pass was most of this kernel's time)
     // pass 1: sim loss and the two sums its gradient needs
     double a1[4] = {0, 0, 0, 0};       // sum d^2, sum g, sum g (sim - mu)
     for (long long i = tid; i < M; i += blockDim.x) {
         const double s = (double)sim[i] - mu_s;
         const double d = s * is - ((double)raw[i] - mu_r) * ir;
-        const double g = 2.0 * d / (double)M;
+        const double g = d * two_over_M;
         a1[0] += d * d; a1[1] += g; a1[2] += g * s;
     }
     block_sum_d(a1);
@@ -1087,7 +1088,7 @@ __global__ void __launch_bounds__(1024) train_loss_finalize_kernel(const float *
         for (long long i = tid; i < M; i += blockDim.x) {
             const double s = (double)sim[i] - mu_s;
             const double d = s * is - ((double)raw[i] - mu_r) * ir;
-            const double g = 2.0 * d / (double)M;
+            const double g = d * two_over_M;
             dsim[i] = (float)((double)scale * ((g - gmean) * is - s * kcoef));
         }
     }
