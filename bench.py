@@ -441,7 +441,7 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
     mode = "cuda graph"
     try:
         graphed = P.train.GraphedTrainStep(model, opt, batches[0], k=K_NEIGH)
-        step = lambda i: graphed(batches[i % 4])
+        step = lambda i: graphed(batches[i % 4], next_batch=batches[(i + 1) % 4])     # the loader knows the next batch: its graph is built under this step
     except Exception as e:                                   # capture refused (e.g. a collective that cannot be captured)
         mode = f"eager ({type(e).__name__})"
         torch.cuda.synchronize()

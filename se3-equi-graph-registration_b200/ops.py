@@ -49,6 +49,37 @@ def knn_build(x, k, brute_force=False):
     return nbr
 
 
+def build_train_graph(x, k, out=None):
+    """k-NN graph of x [C,N,3] as the CSR + column positions the training step needs (knn_build -> csr_from_nbr ->
+    with_csc), written into the buffer set `out` of an earlier call when given: same addresses on every call, so a
+    captured CUDA graph can consume a graph that another stream rebuilds between its replays.  -> BatchGraph (its
+    private `_bufs` holds the two workspaces)."""
+    x = _req(x, "x", torch.float32, 3)
+    C, N, D = x.shape
+    if D != 3:
+        raise ValueError("k-NN is built over 3-d points")
+    if out is None:
+        return with_csc(csr_from_nbr(knn_build(x, k)))
+    lib = _lib.lib()
+    g = out
+    if (g.clouds, g.n, g.edges_per_cloud) != (C, N, N * k) or g.nbr is None:
+        raise ValueError("the buffer set was built for another shape")
+    dev = x.device
+    bufs = g.__dict__.get("_bufs")
+    if bufs is None:
+        bufs = g.__dict__["_bufs"] = (torch.empty(lib.egspr_knn_workspace_bytes(C, N), dtype=torch.uint8, device=dev),
+                                      torch.empty(lib.egspr_csr_workspace_bytes(C * N, C * N * k), dtype=torch.uint8, device=dev))
+    kws, cws = bufs
+    with torch.cuda.device(dev):
+        st = _stream()
+        _lib.check(lib.egspr_knn_build(_ptr(x), C, N, k, _ptr(g.nbr), _ptr(kws), kws.numel(), st), "egspr_knn_build")
+        _lib.check(lib.egspr_csr_from_nbr(_ptr(g.nbr), C, N, k, _ptr(g.ptr), _ptr(g.row), _ptr(g.col), _ptr(g.eid),
+                                          _ptr(cws), cws.numel(), _ptr(g.err), st), "egspr_csr_from_nbr")
+        _lib.check(lib.egspr_csr_edge_positions(_ptr(g.row), _ptr(g.eid), None, N, N * k, C * N * k, _ptr(g.cpos), None, st),
+                   "egspr_csr_edge_positions")
+    return g
+
+
 def nbr_to_edges(nbr):
     """nbr [C,N,k] i32 -> edges [C,2,N*k] i64 in torch_cluster.knn_graph layout."""
     nbr = _req(nbr, "nbr", torch.int32, 3)

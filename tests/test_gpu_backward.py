@@ -442,3 +442,29 @@ def test_graphed_train_step_with_two_heads_equals_eager():
         losses[mode] = out
     assert np.all(np.isfinite(losses["graph"]))
     assert np.allclose(losses["eager"], losses["graph"], rtol=2e-3), losses
+
+
+def test_graphed_train_step_pipelined_graph_build_equals_plain(golden_dir):
+    """step(batch, next_batch=...) builds the next batch's k-NN graph on a forked stream inside the current step's CUDA
+    graph (the wide k-NN / CSR kernels run beside the narrow head kernels); the losses and the final parameters must equal
+    the plain step(batch) sequence -- also when an announcement is wrong or missing (the step then builds its own graph)."""
+    keys = ("src_feat", "src_pts", "tgt_feat", "tgt_pts", "corr", "labels", "gt_pose")
+    batches = [tuple(P.synthetic.make_batch(60 + i, 2, n=512)[k].to(DEV) for k in keys) for i in range(3)]
+    order = [0, 1, 2, 0, 2, 1, 1, 0]
+    res = {}
+    for mode in ("plain", "pipelined"):
+        model = _model(golden_dir, 0.005)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+        step = P.train.GraphedTrainStep(model, opt, batches[0], k=16, warmup=2)
+        out = []
+        for j, bi in enumerate(order):
+            if mode == "plain":
+                out.append(float(step(batches[bi])))
+            else:
+                nxt = batches[order[j + 1]] if j + 1 < len(order) else None
+                if j == 4:
+                    nxt = batches[0]             # a wrong announcement: the next call gets another batch and must rebuild
+                out.append(float(step(batches[bi], next_batch=nxt)))
+        res[mode] = (out, torch.cat([p.detach().flatten() for p in model.parameters()]).cpu())
+    assert np.allclose(res["plain"][0], res["pipelined"][0], rtol=1e-5), res
+    assert float((res["plain"][1] - res["pipelined"][1]).abs().max()) < 1e-6

@@ -22,4 +22,5 @@ def timeit(fn, n=20):
     return a.elapsed_time(b) / n, (time.perf_counter() - t0) * 1e3 / n
 print("replay only      : %.3f ms (events) %.3f ms (wall)" % timeit(lambda i: step.graph.replay()))
 print("load + replay    : %.3f ms (events) %.3f ms (wall)" % timeit(lambda i: step(batches[i % 4])))
+print("load + replay, next batch announced (its graph is built under this step): %.3f ms (events) %.3f ms (wall)" % timeit(lambda i: step(batches[i % 4], next_batch=batches[(i + 1) % 4])))
 print("eager _step()    : %.3f ms (events) %.3f ms (wall)" % timeit(lambda i: step._step(), 5))
