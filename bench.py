@@ -494,7 +494,8 @@ def train_step_bench(P, dev, rank, world, barrier, steps, warmup):
             shipped = {"error": f"{type(e).__name__}: {e}"[:200]}
     gn_t = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters() if p.grad is not None))
     return {"workload": "BASELINE configs[3]: 3DMatch training step, fwd + bwd + Adam, 16 pairs/GPU x 2 clouds x 2048 pts, "
-                        "k-NN graph build included; ONE all-reduce of the persistent flat gradient (25,953 fp32, NCCL) when n_gpus > 1",
+                        "k-NN graph build included (every step builds the NEXT batch's graph on a forked stream under its own head kernels and trains on the graph "
+                        "the previous step built); ONE all-reduce of the persistent flat gradient (25,953 fp32, NCCL) when n_gpus > 1",
             "pairs_per_gpu": B, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": "pairs/s (training)",
             "steps": steps, "loss": float(loss), "grad_norm": float(gn_t), "loss_finite": finite,
             "replicas_identical": replicas_identical, "embedding_out_scale": TRAIN_TEMPER,
