@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(256) head_eval_pre_kernel(const HeadEvalArgs a
     }
 }
 
-__global__ void __launch_bounds__(HD_THREADS_BIG) head_eval_kernel(const HeadEvalArgs a) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) head_eval_kernel(const HeadEvalArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -507,7 +508,8 @@ struct HeadTrainArgs {
     float *w_out, *sim_out, *R, *t, *Hout, *loss_parts;
 };
 
-__global__ void __launch_bounds__(HD_THREADS_BIG) head_train_kernel(const HeadTrainArgs a) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) head_train_kernel(const HeadTrainArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
@@ -549,7 +551,8 @@ __global__ void __launch_bounds__(HD_THREADS_BIG) head_train_kernel(const HeadTr
                         a.labels + nb, a.gt_pose + b * 16, n, a.loss_parts + b * 2, sc);
 }
 
-__global__ void __launch_bounds__(HD_THREADS_BIG) kabsch_kernel(const float *__restrict__ p, const float *__restrict__ q,
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) kabsch_kernel(const float *__restrict__ p, const float *__restrict__ q,
                                                             const float *__restrict__ w, const float *__restrict__ mask,
                                                             int n, float *R, float *t, float *Hout) {
     extern __shared__ __align__(16) float dyn[];
@@ -658,7 +661,8 @@ __device__ __forceinline__ MlpRow mlp_row(const float *__restrict__ w, float zs,
     return r;
 }
 
-__global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(const HeadTrainBwdArgs a) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) head_train_backward_kernel(const HeadTrainBwdArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     __shared__ float gsh[24];      // G_H [9], dcs' [3], dct' [3], cs [3], ct [3], ok
@@ -1189,8 +1193,10 @@ extern "C" int egspr_kabsch(const float *p, const float *q, const float *w, cons
     if (!p || !q || !w || !R || !t || pairs <= 0 || n < 0) return EGSPR_E_INVALID;
     if (n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
     const size_t smem = sizeof(float) * (size_t)(n > 0 ? n : 1);
-    if (int e = ensure_smem(kabsch_kernel, smem)) return e;
-    kabsch_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(p, q, w, mask, n, R, t, Hout);
+    const bool big_cta = head_threads(n) > 512;        // <= 512 threads: 128 registers per thread, the fp64 SVD stays in registers
+    if (int e = big_cta ? ensure_smem(kabsch_kernel<1024>, smem) : ensure_smem(kabsch_kernel<512>, smem)) return e;
+    if (big_cta) kabsch_kernel<1024><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(p, q, w, mask, n, R, t, Hout);
+    else kabsch_kernel<512><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(p, q, w, mask, n, R, t, Hout);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
@@ -1221,7 +1227,8 @@ extern "C" int egspr_head_eval_ws(const float *feat_src, const float *feat_tgt, 
     if (loss_parts && (!x_out_src || !x_out_tgt || !labels || !gt_pose)) return EGSPR_E_INVALID;
     if (n > HD_MAX_N && !w_out) return EGSPR_E_WORKSPACE;      // large clouds: the weights row doubles as scratch
     const size_t smem = n > HD_MAX_N ? 0 : sizeof(float) * (size_t)n;
-    if (int e = ensure_smem(head_eval_kernel, smem)) return e;
+    const bool big_cta = head_threads(n) > 512;        // <= 512 threads: 128 registers per thread, the fp64 SVD stays in registers
+    if (int e = big_cta ? ensure_smem(head_eval_kernel<1024>, smem) : ensure_smem(head_eval_kernel<512>, smem)) return e;
     HeadEvalArgs a{feat_src, feat_tgt, x_src, x_tgt, h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose,
                    head_pack, n, top_k, w_out, R, t, Hout, loss_parts, 0, nullptr, nullptr};
     // few pairs x large clouds (one CTA per pair would leave most SMs idle while it streams 2 x 2 x n x 128 bytes):
@@ -1238,7 +1245,8 @@ extern "C" int egspr_head_eval_ws(const float *feat_src, const float *feat_tgt, 
             EGSPR_CHECK_LAUNCH();
         }
     }
-    head_eval_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    if (big_cta) head_eval_kernel<1024><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    else head_eval_kernel<512><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
@@ -1253,9 +1261,11 @@ extern "C" int egspr_head_train(const float *h_out_src, const float *h_out_tgt, 
     if (loss_parts && !gt_pose) return EGSPR_E_INVALID;
     if (n > HD_MAX_N && !w_out) return EGSPR_E_WORKSPACE;
     const size_t smem = n > HD_MAX_N ? 0 : sizeof(float) * (size_t)n;
-    if (int e = ensure_smem(head_train_kernel, smem)) return e;
+    const bool big_cta = head_threads(n) > 512;        // <= 512 threads: 128 registers per thread, the fp64 SVD stays in registers
+    if (int e = big_cta ? ensure_smem(head_train_kernel<1024>, smem) : ensure_smem(head_train_kernel<512>, smem)) return e;
     HeadTrainArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose, n, w_out, sim_out, R, t, Hout, loss_parts};
-    head_train_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    if (big_cta) head_train_kernel<1024><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    else head_train_kernel<512><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
@@ -1267,8 +1277,10 @@ static int head_train_backward_impl(const egspr::HeadTrainBwdArgs &a, int pairs,
         return EGSPR_E_INVALID;
     if (2 * n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
     const size_t smem = sizeof(float) * 2 * (size_t)n;
-    if (int e = ensure_smem(head_train_backward_kernel, smem)) return e;
-    head_train_backward_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    const bool big_cta = head_threads(n) > 512;        // <= 512 threads: 128 registers per thread, the fp64 SVD stays in registers
+    if (int e = big_cta ? ensure_smem(head_train_backward_kernel<1024>, smem) : ensure_smem(head_train_backward_kernel<512>, smem)) return e;
+    if (big_cta) head_train_backward_kernel<1024><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    else head_train_backward_kernel<512><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     if (a.top_idx) {
         corr_loss_backward_kernel<<<dim3((unsigned)pairs, CB_SPLIT), CB_THREADS, 0, (cudaStream_t)stream>>>(a);
