@@ -508,8 +508,7 @@ struct HeadTrainArgs {
     float *w_out, *sim_out, *R, *t, *Hout, *loss_parts;
 };
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT) head_train_kernel(const HeadTrainArgs a) {
+__global__ void __launch_bounds__(HD_THREADS_BIG) head_train_kernel(const HeadTrainArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     const int b = blockIdx.x, n = a.n, tid = threadIdx.x;
@@ -661,8 +660,7 @@ __device__ __forceinline__ MlpRow mlp_row(const float *__restrict__ w, float zs,
     return r;
 }
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT) head_train_backward_kernel(const HeadTrainBwdArgs a) {
+__global__ void __launch_bounds__(HD_THREADS_BIG) head_train_backward_kernel(const HeadTrainBwdArgs a) {
     extern __shared__ __align__(16) float dyn[];
     __shared__ BlockScratch sc;
     __shared__ float gsh[24];      // G_H [9], dcs' [3], dct' [3], cs [3], ct [3], ok
@@ -1261,11 +1259,9 @@ extern "C" int egspr_head_train(const float *h_out_src, const float *h_out_tgt, 
     if (loss_parts && !gt_pose) return EGSPR_E_INVALID;
     if (n > HD_MAX_N && !w_out) return EGSPR_E_WORKSPACE;
     const size_t smem = n > HD_MAX_N ? 0 : sizeof(float) * (size_t)n;
-    const bool big_cta = head_threads(n) > 512;        // <= 512 threads: 128 registers per thread, the fp64 SVD stays in registers
-    if (int e = big_cta ? ensure_smem(head_train_kernel<1024>, smem) : ensure_smem(head_train_kernel<512>, smem)) return e;
+    if (int e = ensure_smem(head_train_kernel, smem)) return e;
     HeadTrainArgs a{h_out_src, h_out_tgt, x_out_src, x_out_tgt, labels, gt_pose, n, w_out, sim_out, R, t, Hout, loss_parts};
-    if (big_cta) head_train_kernel<1024><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
-    else head_train_kernel<512><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    head_train_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     return EGSPR_OK;
 }
@@ -1277,10 +1273,8 @@ static int head_train_backward_impl(const egspr::HeadTrainBwdArgs &a, int pairs,
         return EGSPR_E_INVALID;
     if (2 * n > HD_MAX_N) return EGSPR_E_UNSUPPORTED;
     const size_t smem = sizeof(float) * 2 * (size_t)n;
-    const bool big_cta = head_threads(n) > 512;        // <= 512 threads: 128 registers per thread, the fp64 SVD stays in registers
-    if (int e = big_cta ? ensure_smem(head_train_backward_kernel<1024>, smem) : ensure_smem(head_train_backward_kernel<512>, smem)) return e;
-    if (big_cta) head_train_backward_kernel<1024><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
-    else head_train_backward_kernel<512><<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
+    if (int e = ensure_smem(head_train_backward_kernel, smem)) return e;
+    head_train_backward_kernel<<<pairs, head_threads(n), smem, (cudaStream_t)stream>>>(a);
     EGSPR_CHECK_LAUNCH();
     if (a.top_idx) {
         corr_loss_backward_kernel<<<dim3((unsigned)pairs, CB_SPLIT), CB_THREADS, 0, (cudaStream_t)stream>>>(a);
